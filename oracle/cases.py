@@ -1,0 +1,85 @@
+"""Oracle (test infrastructure): the seeded synthetic inputs shared by the golden generator, the tests,
+``smoke()`` and ``bench.py``.  Everything is derived from integer seeds so the GPU box can
+rebuild inputs without the reference tree."""
+import torch
+
+
+def _g(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def hift_case(B=2, T=24, seed=0):
+    g = _g(1000 + seed)
+    mel = torch.randn(B, 80, T, generator=g) * 2 - 5
+    noise = torch.randn(B, T * 480, 9, generator=g)
+    rand_ini = torch.rand(B, 9, generator=g)
+    rand_ini[:, 0] = 0
+    return mel, noise, rand_ini
+
+
+def flow_case(N=31, P=20, seed=1):
+    g = _g(2000 + seed)
+    token = torch.randint(0, 6561, (1, N), dtype=torch.int32, generator=g)
+    ptok = torch.randint(0, 6561, (1, P), dtype=torch.int32, generator=g)
+    pfeat = torch.rand(1, 2 * P, 80, generator=g) * 13.5 - 11.5        # log-mel range, log(1e-5) = -11.5
+    emb = torch.randn(1, 192, generator=g)
+    return token, ptok, pfeat, emb
+
+
+def estimator_case(T=64, seed=2):
+    """export_onnx.py:34-41 recipe: x, mu, cond ~ U[0,1) [2,80,T], mask = 1, t ~ U[0,1) [2], spks [2,80]."""
+    g = _g(3000 + seed)
+    x = torch.rand(2, 80, T, generator=g)
+    mask = torch.ones(2, 1, T)
+    mu = torch.rand(2, 80, T, generator=g)
+    t = torch.rand(2, generator=g)
+    spks = torch.rand(2, 80, generator=g)
+    cond = torch.rand(2, 80, T, generator=g)
+    return x, mask, mu, t, spks, cond
+
+
+def lm_case(n_text=7, n_prompt_text=4, n_prompt_speech=9, seed=3, n_uniform=400):
+    g = _g(4000 + seed)
+    text = torch.randint(0, 151643, (1, n_text), dtype=torch.int32, generator=g)
+    ptext = torch.randint(0, 151643, (1, n_prompt_text), dtype=torch.int32, generator=g)
+    ptok = torch.randint(0, 6561, (1, n_prompt_speech), dtype=torch.int32, generator=g)
+    U = torch.rand(n_uniform, 2, generator=g)
+    return text, ptext, ptok, U
+
+
+def sampling_case(n=64, V=6564, seed=4):
+    """Random log-prob vectors of varying peakiness + random decoded histories + uniforms."""
+    g = _g(5000 + seed)
+    temps = torch.rand(n, 1, generator=g) * 6 + 0.5
+    logits = torch.randn(n, V, generator=g) * temps
+    logp = torch.log_softmax(logits, dim=-1)
+    hist = torch.randint(0, V, (n, 12), generator=g)
+    # make repetitions likely: plant the arg-max in half of the histories
+    am = logp.argmax(dim=-1)
+    for i in range(0, n, 2):
+        hist[i, -3] = am[i]
+    U = torch.rand(n, 2, generator=g)
+    ignore_eos = torch.arange(n) % 3 != 0
+    return logp, hist, U, ignore_eos
+
+
+def mel_case(B=2, n=24000, seed=5):
+    g = _g(6000 + seed)
+    return torch.rand(B, n, generator=g) * 1.6 - 0.8
+
+
+def z10_utterance(i, n_text=None):
+    """canonical ~10 s zero-shot utterance; utterance i of a batch uses seed 1986+i.
+    Ragged variant: n_text in {40..60} when n_text is None and i >= 0 (config #3)."""
+    g = _g(1986 + i)
+    if n_text is None:
+        n_text = 50
+    text = torch.randint(0, 151643, (1, n_text), dtype=torch.int32, generator=g)
+    ptext = torch.randint(0, 151643, (1, 12), dtype=torch.int32, generator=g)
+    ptok = torch.randint(0, 6561, (1, 75), dtype=torch.int32, generator=g)
+    pfeat = torch.rand(1, 150, 80, generator=g) * 13.5 - 11.5
+    emb = torch.randn(1, 192, generator=g)
+    return dict(text=text, prompt_text=ptext, llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok,
+                prompt_speech_feat=pfeat, llm_embedding=emb, flow_embedding=emb)
