@@ -1,0 +1,307 @@
+// extern "C" boundary of libcvk (include/cvk.h): argument checking, error translation, no exceptions across the ABI.
+#include "common.cuh"
+#include <string.h>
+
+// stage entry points implemented in hift.cu / flow.cu / llm.cu / mel.cu
+void hift_build(cvk_ctx* ctx);
+void hift_f0(cvk_ctx* ctx, const float* mel, const int* lens, int B, float* f0_out, cudaStream_t st);
+void hift_source(cvk_ctx* ctx, const float* f0, const int* lens, int B, const float* noise, float* source_out, cudaStream_t st);
+void hift_decode(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* source, float* wav, cudaStream_t st);
+void hift_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* noise, const float* cache_source,
+                    const int* cache_lens, float* wav, float* source_out, cudaStream_t st);
+void flow_build(cvk_ctx* ctx, const int* cfg, int ncfg);
+void flow_encoder(cvk_ctx* ctx, const int32_t* tokens, const int* lens, int B, int streaming, int context_len, float* h, cudaStream_t st);
+void flow_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
+                    int B, int streaming, float* out, cudaStream_t st);
+void flow_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float* cond, const int* lens, int B, const float* z,
+                    int n_timesteps, float cfg_rate, int streaming, float* out, cudaStream_t st);
+void flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
+                    const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, cudaStream_t st);
+void flow_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device);
+void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg);
+cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context);
+void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s);
+void llm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const int* text_lens, const int32_t* speech,
+                 const int* speech_lens, int B, cudaStream_t st);
+void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
+                int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, cudaStream_t st);
+void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, cudaStream_t st);
+void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
+                    const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st);
+void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, cudaStream_t st);
+void mel_init(cvk_ctx* ctx);
+
+#define CVK_API_BEGIN            \
+  if (!ctx) return CVK_ERR_INVALID; \
+  try {                          \
+    cudaSetDevice(ctx->device);
+#define CVK_API_END                                  \
+    return CVK_OK;                                   \
+  } catch (const CvkError& e) {                      \
+    ctx->last_error = e.what();                      \
+    return e.code;                                   \
+  } catch (const std::exception& e) {                \
+    ctx->last_error = std::string("internal: ") + e.what(); \
+    return CVK_ERR_INVALID;                          \
+  }
+
+extern "C" {
+
+const char* cvk_version(void) { return "libcvk 0.1 (sm_100a)"; }
+
+int cvk_create(int device, int precision, size_t workspace_bytes, cvk_ctx** out) {
+  if (!out) return CVK_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device || device < 0) return CVK_ERR_CUDA;   // no CPU fallback
+  if (precision != CVK_PREC_FP32 && precision != CVK_PREC_BF16) return CVK_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return CVK_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CVK_ERR_CUDA;
+  if (prop.major != 10) return CVK_ERR_CUDA;   // sm_100a only: the tcgen05/TMA kernels have no other code path
+  cvk_ctx* ctx = new cvk_ctx();
+  ctx->device = device;
+  ctx->precision = precision;
+  ctx->act_dtype = precision == CVK_PREC_BF16 ? DT_BF16 : DT_F32;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (workspace_bytes == 0) workspace_bytes = (size_t)4 << 30;
+  void* p = nullptr;
+  if (cudaMalloc(&p, workspace_bytes) != cudaSuccess) {
+    delete ctx;
+    return CVK_ERR_OOM;
+  }
+  ctx->arena.base = (char*)p;
+  ctx->arena.cap = workspace_bytes;
+  *out = ctx;
+  return CVK_OK;
+}
+
+void cvk_destroy(cvk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->raw) cudaFree(kv.second.p);
+  for (void* p : ctx->owned) cudaFree(p);
+  cudaFree(ctx->arena.base);
+  delete ctx;
+}
+
+const char* cvk_last_error(cvk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
+  CVK_API_BEGIN
+  std::string k(key ? key : "");
+  if (k == "use_tc") ctx->use_tc = value;
+  else if (k == "tc_bn256") ctx->tc_bn256 = value;
+  else throw CvkError(CVK_ERR_INVALID, "unknown option: " + k);
+  CVK_API_END
+}
+
+int cvk_set_tensor(cvk_ctx* ctx, const char* name, const float* data, int on_device, const int64_t* shape, int ndim) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(name && data && shape && ndim >= 1 && ndim <= 4, "cvk_set_tensor: bad arguments");
+  RawTensor t;
+  t.shape.assign(shape, shape + ndim);
+  size_t bytes = (size_t)t.numel() * sizeof(float);
+  CVK_CHECK_CUDA(cudaMalloc((void**)&t.p, bytes));
+  cudaError_t e = cudaMemcpy(t.p, data, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(t.p);
+    throw CvkError(CVK_ERR_CUDA, std::string("cvk_set_tensor copy: ") + cudaGetErrorString(e));
+  }
+  auto it = ctx->raw.find(name);
+  if (it != ctx->raw.end()) {
+    cudaFree(it->second.p);
+    ctx->raw.erase(it);
+  }
+  ctx->raw[name] = t;
+  CVK_API_END
+}
+
+int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg) {
+  CVK_API_BEGIN
+  std::string s(stage ? stage : "");
+  if (s == "hift") hift_build(ctx);
+  else if (s == "flow") flow_build(ctx, cfg, ncfg);
+  else if (s == "llm") llm_build(ctx, cfg, ncfg);
+  else if (s == "mel") mel_init(ctx);
+  else throw CvkError(CVK_ERR_INVALID, "unknown stage: " + s);
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  // raw tensors of this stage are no longer needed
+  std::string prefix = s + ".";
+  for (auto it = ctx->raw.begin(); it != ctx->raw.end();) {
+    if (it->first.compare(0, prefix.size(), prefix) == 0) {
+      cudaFree(it->second.p);
+      it = ctx->raw.erase(it);
+    } else ++it;
+  }
+  CVK_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- generic ops
+int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens, int B, int K, const float* w, const float* bias, int N, int taps,
+                  int dil, int shift0, int act, float* out, void* stream) {
+  CVK_API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  CVK_REQUIRE(x && lens && w && out && B > 0, "cvk_op_conv1d: bad arguments");
+  ctx->arena.reset();
+  size_t owned_mark = ctx->owned.size();
+  int gap = 32;
+  Seqs s = make_seqs(ctx, lens, B, gap, 1, 0, st);
+  ConvW W = make_conv(ctx, w, bias, N, K, taps, dil, shift0);
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());   // weight repack runs on the default stream
+  Mat a = arena_mat(ctx, ctx->act_dtype, s.R, K);
+  zero_mat(ctx, st, a);
+  pack_rows(ctx, st, x, K, s, a);
+  Mat o = arena_mat(ctx, DT_F32, s.R, N);
+  Epilogue e;
+  e.act1 = act;
+  e.act1_param = 0.1f;
+  e.row2seq = s.d_row2seq;
+  e.out = o;
+  if (a.dtype == DT_BF16 && W.w16 == nullptr) {   // K not TMA-able: fp32 path
+    Mat a32 = arena_mat(ctx, DT_F32, s.R, K);
+    zero_mat(ctx, st, a32);
+    pack_rows(ctx, st, x, K, s, a32);
+    conv_gemm_simt(ctx, st, a32, W, e);
+  } else {
+    conv_gemm(ctx, st, a, W, e);
+  }
+  unpack_rows(ctx, st, o, s, 0, out, N);
+  CVK_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = owned_mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+  ctx->owned.resize(owned_mark);
+  CVK_API_END
+}
+
+int cvk_op_attention(cvk_ctx* ctx, const float* q, const float* k, const float* v, const int* lens, int B, int H, int chunk,
+                     float scale, float* out, void* stream) {
+  CVK_API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  CVK_REQUIRE(q && k && v && out && lens && B > 0 && H > 0, "cvk_op_attention: bad arguments");
+  ctx->arena.reset();
+  Seqs s = make_seqs(ctx, lens, B, 8, 1, 0, st);
+  int C = H * 64;
+  Mat mq = arena_mat(ctx, ctx->act_dtype, s.R, C), mk = arena_mat(ctx, ctx->act_dtype, s.R, C), mv = arena_mat(ctx, ctx->act_dtype, s.R, C);
+  Mat mo = arena_mat(ctx, ctx->act_dtype, s.R, C);
+  zero_mat(ctx, st, mq); zero_mat(ctx, st, mk); zero_mat(ctx, st, mv); zero_mat(ctx, st, mo);
+  pack_rows(ctx, st, q, C, s, mq);
+  pack_rows(ctx, st, k, C, s, mk);
+  pack_rows(ctx, st, v, C, s, mv);
+  attention_fwd(ctx, st, mq, mk, mv, s, H, chunk, scale, mo);
+  unpack_rows(ctx, st, mo, s, 0, out, C);
+  CVK_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- HiFT
+int cvk_hift_f0(cvk_ctx* ctx, const float* mel, const int* lens, int B, float* f0, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(mel && lens && f0 && B > 0, "cvk_hift_f0: bad arguments");
+  hift_f0(ctx, mel, lens, B, f0, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_hift_source(cvk_ctx* ctx, const float* f0, const int* lens, int B, const float* noise, float* source, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(f0 && lens && noise && source && B > 0, "cvk_hift_source: bad arguments");
+  hift_source(ctx, f0, lens, B, noise, source, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_hift_decode(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* source, float* wav, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(mel && lens && source && wav && B > 0, "cvk_hift_decode: bad arguments");
+  hift_decode(ctx, mel, lens, B, source, wav, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_hift_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* noise, const float* cache_source,
+                       const int* cache_lens, float* wav, float* source, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(mel && lens && noise && wav && B > 0, "cvk_hift_inference: bad arguments");
+  hift_inference(ctx, mel, lens, B, noise, cache_source, cache_lens, wav, source, (cudaStream_t)stream);
+  CVK_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- flow
+int cvk_flow_encoder(cvk_ctx* ctx, const int32_t* tokens, const int* lens, int B, int streaming, int context_len, float* h, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(tokens && lens && h && B > 0 && (context_len == 0 || context_len == 3), "cvk_flow_encoder: bad arguments");
+  flow_encoder(ctx, tokens, lens, B, streaming, context_len, h, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_cfm_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
+                      int B, int streaming, float* out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(x && mu && t && spks && cond && lens && out && B > 0, "cvk_cfm_estimator: bad arguments");
+  flow_estimator(ctx, x, mu, t, spks, cond, lens, B, streaming, out, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float* cond, const int* lens, int B, const float* z,
+                  int n_timesteps, float cfg_rate, int streaming, float* out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(mu && spks && cond && lens && out && B > 0 && n_timesteps > 0, "cvk_cfm_solve: bad arguments");
+  flow_cfm_solve(ctx, mu, spks, cond, lens, B, z, n_timesteps, cfg_rate, streaming, out, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
+                       const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(tokens && token_lens && prompt_feat_lens && embedding && mel && B > 0, "cvk_flow_inference: bad arguments");
+  flow_inference(ctx, tokens, token_lens, prompt_feat, prompt_feat_lens, embedding, B, n_timesteps, streaming, finalize, mel,
+                 (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(noise_tm && T > 0, "cvk_cfm_set_noise: bad arguments");
+  flow_set_noise(ctx, noise_tm, T, on_device);
+  CVK_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- LM
+int cvk_lm_session_create(cvk_ctx* ctx, int max_batch, int max_context, cvk_lm_session** out) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(out && max_batch > 0 && max_context > 0, "cvk_lm_session_create: bad arguments");
+  *out = llm_session_create(ctx, max_batch, max_context);
+  CVK_API_END
+}
+void cvk_lm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s) {
+  if (!ctx || !s) return;
+  try { llm_session_destroy(ctx, s); } catch (...) {}
+}
+int cvk_lm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const int* text_lens, const int32_t* speech,
+                   const int* speech_lens, int B, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s && text && text_lens && speech_lens && B > 0, "cvk_lm_prefill: bad arguments");
+  llm_prefill(ctx, s, text, text_lens, speech, speech_lens, B, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
+                  int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s && uniforms && min_len && max_len && out_ids && out_count && done && n_steps > 0, "cvk_lm_decode: bad arguments");
+  llm_decode(ctx, s, n_steps, uniforms, min_len, max_len, out_ids, out_ld, out_count, done, live_host, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(embeds && lens && logp && B > 0, "cvk_lm_forward_logp: bad arguments");
+  llm_forward_logp(ctx, embeds, lens, B, logp, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
+                   const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(logp && history && hist_count && uniforms && ignore_eos && out_ids && B > 0 && V > 0, "cvk_ras_sample: bad arguments");
+  llm_ras_sample(ctx, logp, B, V, history, hist_ld, hist_count, uniforms, ignore_eos, out_ids, (cudaStream_t)stream);
+  CVK_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- mel
+int cvk_mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(wav && lens && mel && B > 0, "cvk_mel_spectrogram: bad arguments");
+  mel_spectrogram(ctx, wav, lens, B, mel, (cudaStream_t)stream);
+  CVK_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Device-side helpers shared by all kernels.
+#pragma once
+#include "cvk_internal.h"
+
+struct EpiDev {
+  const float* bias;
+  const float* rowvec;
+  int rowvec_ld;
+  int act1;
+  float act1_param;
+  const float* alpha1;
+  float scale;
+  const float* resid;
+  int resid_ld;
+  const int* row2seq;
+  int accumulate;
+  void* out;
+  int out_dtype;
+  int out_ld;
+  int act2;
+  float act2_param;
+  const float* alpha2;
+  void* out2;
+  int out2_dtype;
+  int out2_ld;
+};
+
+inline EpiDev to_dev(const Epilogue& e) {
+  EpiDev d;
+  d.bias = e.bias;
+  d.rowvec = e.rowvec;
+  d.rowvec_ld = e.rowvec_ld;
+  d.act1 = e.act1;
+  d.act1_param = e.act1_param;
+  d.alpha1 = e.alpha1;
+  d.scale = e.scale;
+  d.resid = e.resid.p ? e.resid.f32() : nullptr;
+  d.resid_ld = e.resid.ld;
+  d.row2seq = e.row2seq;
+  d.accumulate = e.accumulate;
+  d.out = e.out.p;
+  d.out_dtype = e.out.dtype;
+  d.out_ld = e.out.ld;
+  d.act2 = e.act2;
+  d.act2_param = e.act2_param;
+  d.alpha2 = e.alpha2;
+  d.out2 = e.out2.p;
+  d.out2_dtype = e.out2.dtype;
+  d.out2_ld = e.out2.ld;
+  return d;
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ld_any(const void* p, int dtype, size_t i) {
+  return dtype == DT_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
+  if (dtype == DT_F32) ((float*)p)[i] = v;
+  else ((bf16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+// torch semantics: F.gelu(approximate='none'), F.silu, F.mish (softplus threshold 20), F.elu(alpha=1),
+// F.leaky_relu(slope), Snake (transformer/activation.py:73-84), tanh
+__device__ __forceinline__ float apply_act(int act, float x, float param, float alpha) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case ACT_SILU: return x / (1.f + expf(-x));
+    case ACT_MISH: {
+      float sp = x > 20.f ? x : log1pf(expf(x));
+      return x * tanhf(sp);
+    }
+    case ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case ACT_LRELU: return x > 0.f ? x : x * param;
+    case ACT_SNAKE: {
+      float s = sinf(x * alpha);
+      return x + (1.0f / (alpha + 1e-9f)) * (s * s);
+    }
+    case ACT_TANH: return tanhf(x);
+    case ACT_ABS: return fabsf(x);
+    default: return x;
+  }
+}
+
+// One output element through the fused epilogue (see struct Epilogue in cvk_internal.h).
+__device__ __forceinline__ void epi_store(const EpiDev& e, int r, int n, float acc) {
+  int seq = 0;
+  bool valid = true;
+  if (e.row2seq) {
+    seq = e.row2seq[r];
+    valid = seq >= 0;
+  }
+  float v = acc;
+  if (e.bias) v += e.bias[n];
+  if (e.rowvec && valid) v += e.rowvec[(size_t)seq * e.rowvec_ld + n];
+  v = apply_act(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1[n] : 1.f) * e.scale;
+  if (e.resid) v += e.resid[(size_t)r * e.resid_ld + n];
+  if (!valid) v = 0.f;
+  size_t o = (size_t)r * e.out_ld + n;
+  if (e.accumulate) v += ld_any(e.out, e.out_dtype, o);
+  st_any(e.out, e.out_dtype, o, v);
+  if (e.out2) {
+    float w = valid ? apply_act(e.act2, v, e.act2_param, e.alpha2 ? e.alpha2[n] : 1.f) : 0.f;
+    st_any(e.out2, e.out2_dtype, (size_t)r * e.out2_ld + n, w);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

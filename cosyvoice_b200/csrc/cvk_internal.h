@@ -1,0 +1,219 @@
+// Internal definitions shared by the libcvk translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <unordered_map>
+#include <stdexcept>
+
+#include "../../include/cvk.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ errors
+struct CvkError : std::runtime_error {
+  int code;
+  CvkError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CVK_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw CvkError(CVK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" +     \
+                                       __FILE__ + ":" + std::to_string(__LINE__));                 \
+  } while (0)
+
+#define CVK_REQUIRE(cond, msg)                                                                     \
+  do {                                                                                             \
+    if (!(cond))                                                                                   \
+      throw CvkError(CVK_ERR_INVALID, std::string(msg) + " (" #cond ") @" + __FILE__ + ":" +       \
+                                          std::to_string(__LINE__));                               \
+  } while (0)
+
+#define CVK_LAUNCH_CHECK() CVK_CHECK_CUDA(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------------ tensors
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+
+// A 2-D row-major view [rows, cols] with row pitch ld (elements).  Activations are time-major: one row per
+// frame / token / sample-block, channels contiguous.
+struct Mat {
+  void* p = nullptr;
+  int dtype = DT_F32;
+  int rows = 0;
+  int cols = 0;
+  int ld = 0;
+  Mat() {}
+  Mat(void* p_, int dt, int r, int c, int ld_) : p(p_), dtype(dt), rows(r), cols(c), ld(ld_) {}
+  size_t esize() const { return dtype == DT_F32 ? 4 : 2; }
+  // column slice [c0, c0+n)
+  Mat slice(int c0, int n) const { return Mat((char*)p + (size_t)c0 * esize(), dtype, rows, n, ld); }
+  float* f32() const { return (float*)p; }
+  bf16* b16() const { return (bf16*)p; }
+};
+
+// Packed ragged batch geometry.  Sequence b occupies rows [start[b], start[b]+len[b]) of every activation
+// matrix at this rate; all other rows ("gap rows") hold zeros so that convolution halos read zeros
+// (the reference multiplies by the padding mask after every block, flow/decoder.py:65-78).
+struct Seqs {
+  int B = 0;
+  int R = 0;                      // total rows (multiple of 128)
+  std::vector<int> start, len;    // host copies
+  int* d_start = nullptr;         // [B]
+  int* d_len = nullptr;           // [B]
+  int* d_row2seq = nullptr;       // [R]  sequence index or -1 for gap rows
+  int max_len = 0;
+  int64_t sum_len = 0;
+};
+
+// Weight of a (dilated / causal / transposed-as-polyphase) 1-D convolution or a Linear layer, repacked to
+// [N][taps][K] (K contiguous).  out[r, n] = bias[n] + sum_j sum_k A[r + shift0 + j*dil, k] * w[n][j][k]
+struct ConvW {
+  int N = 0, K = 0, taps = 1, dil = 1, shift0 = 0;
+  float* w32 = nullptr;   // always present
+  bf16* w16 = nullptr;    // present in bf16 mode
+  float* bias = nullptr;  // [N] or null
+};
+
+enum Act {
+  ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6, ACT_TANH = 7, ACT_ABS = 8
+};
+
+// Fused epilogue of the conv-GEMM kernels:
+//   v = acc + bias[n] + rowvec[seq(r)][n]            (rowvec: per-sequence broadcast add, e.g. time-MLP)
+//   v = act1(v) * scale
+//   v = v + resid[r][n]
+//   v = valid(r) ? v : 0
+//   out  = accumulate ? out + v : v                   (fp32 or bf16)
+//   out2 = valid(r) ? act2(v) : 0                     (optional second output, e.g. next Snake-activated operand)
+struct Epilogue {
+  const float* bias = nullptr;
+  const float* rowvec = nullptr;  // [B][rowvec_ld]
+  int rowvec_ld = 0;
+  int act1 = ACT_NONE;
+  float act1_param = 0.f;          // lrelu slope
+  const float* alpha1 = nullptr;   // snake alpha per column
+  float scale = 1.f;
+  Mat resid;                       // fp32, optional
+  const int* row2seq = nullptr;    // validity mask (null = all rows valid)
+  int accumulate = 0;
+  Mat out;                         // required
+  int act2 = ACT_NONE;
+  float act2_param = 0.f;
+  const float* alpha2 = nullptr;
+  Mat out2;                        // optional
+};
+
+// ------------------------------------------------------------------------------------------------ context
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) throw CvkError(CVK_ERR_OOM, "workspace arena exhausted: need " + std::to_string(a + bytes) +
+                                                          " of " + std::to_string(cap));
+    off = a + bytes;
+    if (off > high) high = off;
+    return base + a;
+  }
+  void reset() { off = 0; }
+};
+
+struct RawTensor {
+  float* p = nullptr;  // device fp32
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct HiftModel;
+struct FlowModel;
+struct LlmModel;
+
+struct cvk_ctx {
+  int device = 0;
+  int precision = CVK_PREC_FP32;
+  int act_dtype = DT_F32;
+  int num_sms = 148;
+  std::string last_error;
+  std::map<std::string, RawTensor> raw;     // tensors handed over by cvk_set_tensor, consumed by cvk_finalize
+  std::vector<void*> owned;                 // device allocations owned by the context
+  Arena arena;
+  HiftModel* hift = nullptr;
+  FlowModel* flow = nullptr;
+  LlmModel* llm = nullptr;
+  void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
+  int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
+  int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
+  int use_tc = 1;                           // bf16 mode: route GEMMs to the tcgen05 kernel (0 = debug: SIMT on converted operands)
+
+  void* dmalloc(size_t bytes) {
+    void* p = nullptr;
+    CVK_CHECK_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    owned.push_back(p);
+    return p;
+  }
+  const RawTensor& get_raw(const std::string& name) const {
+    auto it = raw.find(name);
+    if (it == raw.end()) throw CvkError(CVK_ERR_MISSING_WEIGHT, "missing weight tensor: " + name);
+    return it->second;
+  }
+  bool has_raw(const std::string& name) const { return raw.find(name) != raw.end(); }
+};
+
+// ------------------------------------------------------------------------------------------------ shared ops
+// geometry
+Seqs make_seqs(cvk_ctx* ctx, const int* lens, int B, int gap, int scale, int extra_front, cudaStream_t st, bool with_row2seq = true);
+Seqs scale_seqs(cvk_ctx* ctx, const Seqs& s, int scale, int extra_front, cudaStream_t st, bool with_row2seq = true);
+
+// weights
+ConvW make_linear(cvk_ctx* ctx, const std::string& wname, const std::string& bname);
+ConvW make_conv(cvk_ctx* ctx, const float* w_oik /*[N][K][taps] device*/, const float* bias, int N, int K, int taps,
+                int dil, int shift0);
+ConvW make_conv_named(cvk_ctx* ctx, const std::string& wname, const std::string& bname, int dil, int shift0);
+float* fold_weight_norm(cvk_ctx* ctx, const std::string& prefix, int64_t* numel_out);
+void finish_convw(cvk_ctx* ctx, ConvW& w);   // create bf16 copy if needed
+float* dev_copy_f32(cvk_ctx* ctx, const float* src_dev, size_t n);
+
+// conv-GEMM (dispatches SIMT fp32 / tcgen05 bf16 on A.dtype)
+void conv_gemm(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
+void conv_gemm_simt(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
+void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
+
+// elementwise / normalisation (elementwise.cu)
+void zero_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& m);
+void layernorm(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const float* gamma, const float* beta, float eps, int act,
+               float post_scale, const int* row2seq, const Mat& out);
+void rmsnorm(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const float* gamma, float eps, const Mat& out);
+void act_copy(cvk_ctx* ctx, cudaStream_t st, const Mat& x, int act, float param, const float* alpha, const int* row2seq,
+              const Mat& out);
+void act_copy_scaled(cvk_ctx* ctx, cudaStream_t st, const Mat& x, float pre_scale, int act, float param, const float* alpha,
+                     const int* row2seq, const Mat& out);
+void pack_rows(cvk_ctx* ctx, cudaStream_t st, const float* dense, int C, const Seqs& s, const Mat& out);
+void unpack_rows(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Seqs& s, int skip, float* dense, int C);
+void bcast_rows(cvk_ctx* ctx, cudaStream_t st, const float* vec, int C, int vec_ld, const Seqs& s, const Mat& out);
+void convert_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Mat& out);
+
+// attention (attention.cu)
+//  q,k,v: packed [R, H*64] views (same Seqs); mask: key j visible from query i iff j < klimit(i), with
+//  klimit(i) = len (chunk<=0) or min(len, (i/chunk+1)*chunk) (block-causal, utils/mask.py:155-157)
+void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
+                   float scale, const Mat& out);
+void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Mat& pos /*[2*Tmax-1, H*64]*/,
+                          int pos_center, const float* bias_u, const float* bias_v, const Seqs& s, int H, int chunk, float scale,
+                          const Mat& out);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+inline Mat arena_mat(cvk_ctx* ctx, int dtype, int rows, int cols, int ld = 0) {
+  if (ld == 0) ld = round_up(cols, 8);
+  size_t es = dtype == DT_F32 ? 4 : 2;
+  void* p = ctx->arena.alloc((size_t)rows * ld * es);
+  return Mat(p, dtype, rows, cols, ld);
+}

@@ -1,0 +1,658 @@
+// HiFT vocoder (CosyVoice2 config): mel -> f0 -> harmonic source -> STFT -> conv / ResBlock stack -> ISTFT.
+// Follows cosyvoice/hifigan/generator.py:557-569 (inference), :507-539 (decode), :491-505 (_stft/_istft),
+// :358-375 + :233-317 (SourceModuleHnNSF / SineGen2), f0_predictor.py:56-59; hyper-parameters of
+// examples/libritts/cosyvoice2/conf/cosyvoice2.yaml:89-111.
+//
+// Layout: time-major ragged matrices at four rates (mel frame, x8, x40, x120) that share one row geometry scaled
+// by the up-sampling factor, so that ConvTranspose1d(stride s) is a 3-tap convolution producing s*Cout columns
+// whose output buffer [R, s*Cout] *is* the next level's [s*R, Cout] matrix (polyphase form, no scatter).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kUps[3] = {8, 5, 3};
+constexpr int kUpK[3] = {16, 11, 7};
+constexpr int kRbK[3] = {3, 7, 11};
+constexpr int kSrcRbK[3] = {7, 7, 11};
+constexpr int kDil[3] = {1, 3, 5};
+constexpr int kCh[4] = {512, 256, 128, 64};
+constexpr int kUpscale = 480;
+constexpr int kStftLd = 24;   // 18 STFT channels padded to 24 so that strided views keep 16-byte row pitch
+
+struct ResBlockW {
+  ConvW c1[3], c2[3];
+  float* a1[3];
+  float* a2[3];
+};
+
+}  // namespace
+
+struct HiftModel {
+  ConvW f0_conv[5];
+  ConvW f0_cls;
+  float* src_w = nullptr;   // [9]
+  float* src_b = nullptr;   // [1]
+  ConvW conv_pre, conv_post;
+  ConvW ups[3];
+  ConvW src_down[3];
+  ResBlockW src_rb[3];
+  ResBlockW rb[9];
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- weight repack
+// ConvTranspose1d weight [Cin][Cout][k] (stride s, padding p) -> polyphase conv [s*Cout][3][Cin]:
+//   out[t*s + ph, co] = sum_{m in {-1,0,1}} sum_ci x[t - m, ci] * w[ci][co][m*s + ph + p]
+// tap jt reads input row t + (jt - 1), i.e. m = 1 - jt.
+__global__ void polyphase_kernel(const float* __restrict__ w, float* __restrict__ o, int Cin, int Cout, int k, int s, int p) {
+  size_t total = (size_t)s * Cout * 3 * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ci = i % Cin;
+    int jt = (i / Cin) % 3;
+    int n = i / ((size_t)Cin * 3);
+    int ph = n / Cout, co = n % Cout;
+    int m = 1 - jt;
+    int j = m * s + ph + p;
+    o[i] = (j >= 0 && j < k) ? w[((size_t)ci * Cout + co) * k + j] : 0.f;
+  }
+}
+__global__ void repeat_bias_kernel(const float* __restrict__ b, float* __restrict__ o, int Cout, int s) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cout * s) o[i] = b[i % Cout];
+}
+// strided Conv1d weight [N][18][k] (stride s, padding p) over the STFT matrix viewed as [R/s, s*24]:
+//   level-3 row of tap j for output row r = s*r + j - (p+1)  ->  view row r + dq, view column pp*24 + c
+__global__ void strided_view_fill_kernel(const float* __restrict__ w, float* __restrict__ o, int N, int C, int k, int s, int off) {
+  int Kv = s * kStftLd;
+  size_t total = (size_t)N * C * k;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int j = i % k;
+    int c = (i / k) % C;
+    int n = i / ((size_t)C * k);
+    int jp = j - off;
+    int dq = jp >= 0 ? jp / s : -((-jp + s - 1) / s);
+    int pp = jp - dq * s;
+    o[((size_t)n * 3 + (dq + 1)) * Kv + pp * kStftLd + c] = w[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- source
+// SineGen2 phase: per (sequence, harmonic) running sum over mel frames of rad = (f0*h/24000) mod 1, then
+// (cum * 2) * pi * 480 exactly as generator.py:255-257.  torch's CPU cumsum accumulates float in double
+// (at::acc_type<float,false>), mirrored here so the parity mode tracks the CPU reference.
+__global__ void phase_kernel(const float* __restrict__ f0, int f0_ld, const int* __restrict__ start, const int* __restrict__ len,
+                             float* __restrict__ phase /*[R0][9]*/) {
+  int b = blockIdx.x;
+  int h = threadIdx.x;
+  if (h >= 9) return;
+  int s = start[b], l = len[b];
+  double cum = 0.0;
+  const float harm = (float)(h + 1);
+  const float pi_f = 3.14159265358979323846f;
+  for (int t = 0; t < l; ++t) {
+    float fn = f0[(size_t)(s + t) * f0_ld] * harm;
+    float rad = fmodf(fn / 24000.f, 1.f);
+    cum += (double)rad;
+    float c = (float)cum;
+    phase[(size_t)(s + t) * 9 + h] = ((c * 2.f) * pi_f) * 480.f;
+  }
+}
+
+// one thread per output sample: linear x480 up-sampling of the phase (F.interpolate, align_corners=False),
+// sin, voiced/unvoiced gating, additive noise, Linear(9->1) + tanh (generator.py:289-317, 358-375)
+__global__ void source_kernel(const float* __restrict__ f0, int f0_ld, const float* __restrict__ phase, const int* __restrict__ start,
+                              const int* __restrict__ len, const float* __restrict__ noise /*dense [sum 480T][9]*/,
+                              const int* __restrict__ noise_off, const float* __restrict__ lw, const float* __restrict__ lb,
+                              float* __restrict__ src /*[480*R0]*/) {
+  int b = blockIdx.y;
+  int T = len[b], s0 = start[b];
+  int L = T * kUpscale;
+  const float scale = (float)(1.0 / 480.0);
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    float srcf = scale * ((float)l + 0.5f) - 0.5f;
+    if (srcf < 0.f) srcf = 0.f;
+    int i0 = (int)srcf;
+    int i1 = i0 + (i0 < T - 1 ? 1 : 0);
+    float l1 = srcf - (float)i0, l0 = 1.f - l1;
+    int t = l / kUpscale;
+    float f = f0[(size_t)(s0 + t) * f0_ld];
+    float uv = f > 10.f ? 1.f : 0.f;
+    float noise_amp = uv * 0.003f + (1.f - uv) * 0.1f / 3.f;
+    const float* p0 = phase + (size_t)(s0 + i0) * 9;
+    const float* p1 = phase + (size_t)(s0 + i1) * 9;
+    const float* nz = noise + ((size_t)noise_off[b] * kUpscale + l) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 9; ++h) {
+      float ph = l0 * p0[h] + l1 * p1[h];
+      float sw = (sinf(ph) * 0.1f) * uv + noise_amp * nz[h];
+      acc += sw * lw[h];
+    }
+    src[(size_t)s0 * kUpscale + l] = tanhf(acc + lb[0]);
+  }
+}
+
+__global__ void cache_source_kernel(const float* __restrict__ cache, const int* __restrict__ cache_off, const int* __restrict__ cache_len,
+                                    const int* __restrict__ start, float* __restrict__ src) {
+  int b = blockIdx.y;
+  int n = cache_len[b];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    src[(size_t)start[b] * kUpscale + i] = cache[cache_off[b] + i];
+}
+
+// ---------------------------------------------------------------------------------------------- STFT / ISTFT (n_fft 16, hop 4)
+__constant__ float c_win[16];
+__constant__ float c_cos[16];   // cos(2*pi*i/16)
+__constant__ float c_sin[16];
+
+// frame f of sequence b -> 9 re + 9 im (torch.stft center=True, reflect), written to the level-3 matrix row
+// start3[b] + f, columns [0,9) re, [9,18) im, [18,24) zero.
+template <typename TO>
+__global__ void stft16_kernel(const float* __restrict__ src, const int* __restrict__ start0, const int* __restrict__ len0,
+                              const int* __restrict__ start3, TO* __restrict__ out, int ldo) {
+  int b = blockIdx.y;
+  int L = len0[b] * kUpscale;
+  int F = L / 4 + 1;
+  const float* x = src + (size_t)start0[b] * kUpscale;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+    float xv[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      int m = 4 * f + n - 8;
+      if (m < 0) m = -m;
+      if (m >= L) m = 2 * (L - 1) - m;
+      xv[n] = x[m] * c_win[n];
+    }
+    TO* op = out + (size_t)(start3[b] + f) * ldo;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float re = 0.f, im = 0.f;
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        int idx = (k * n) & 15;
+        re += xv[n] * c_cos[idx];
+        im -= xv[n] * c_sin[idx];
+      }
+      op[k] = from_f32<TO>(re);
+      op[9 + k] = from_f32<TO>(im);
+    }
+#pragma unroll
+    for (int k = 18; k < kStftLd; ++k) op[k] = from_f32<TO>(0.f);
+  }
+}
+
+// conv_post output [R3, 18] -> magnitude = min(exp(x[:9]), 100), phase = sin(x[9:]) -> irfft(16) * window,
+// overlap-add / window-envelope, trim 8, clamp +-0.99 (generator.py:533-538, torch.istft center=True).
+// Block: 512 output samples, which need frames f_base-1 .. f_base+129.
+__global__ void istft16_kernel(const float* __restrict__ xp, int ldx, const int* __restrict__ start3, const int* __restrict__ len0,
+                               const int* __restrict__ out_off, float* __restrict__ wav, float limit) {
+  __shared__ float fr[131][17];   // frames f_base-1 .. f_base+129
+  int b = blockIdx.y;
+  int L = len0[b] * kUpscale;
+  int F = L / 4 + 1;
+  int f_base = blockIdx.x * 128;          // first frame whose leading 4 samples this block emits
+  if (f_base * 4 >= L) return;
+  for (int i = threadIdx.x; i < 131; i += blockDim.x) {
+    int f = f_base - 1 + i;
+    if (f < 0 || f >= F) {
+#pragma unroll
+      for (int n = 0; n < 16; ++n) fr[i][n] = 0.f;
+      continue;
+    }
+    const float* p = xp + (size_t)(start3[b] + f) * ldx;
+    float re[9], im[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float mag = fminf(expf(p[k]), 100.f);
+      float ph = sinf(p[9 + k]);
+      re[k] = mag * cosf(ph);
+      im[k] = mag * sinf(ph);
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      float acc = re[0] + ((n & 1) ? -re[8] : re[8]);   // DC and Nyquist (imaginary parts ignored by irfft)
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        int idx = (k * n) & 15;
+        acc += 2.f * (re[k] * c_cos[idx] - im[k] * c_sin[idx]);
+      }
+      fr[i][n] = acc * (1.f / 16.f) * c_win[n];
+    }
+  }
+  __syncthreads();
+  // output sample n (after trimming 8) lives at padded position p = n + 8; frames f with 4f <= p < 4f + 16
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    int n = f_base * 4 + i;
+    if (n >= L) break;
+    int p = n + 8;
+    int f_hi = p >> 2;
+    float acc = 0.f, env = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      int f = f_hi - d;
+      if (f < 0 || f >= F) continue;
+      int m = p - 4 * f;
+      acc += fr[f - (f_base - 1)][m];
+      env += c_win[m] * c_win[m];
+    }
+    float y = acc / env;
+    wav[(size_t)out_off[b] * kUpscale + n] = fminf(fmaxf(y, -limit), limit);
+  }
+}
+
+// ReflectionPad1d((1,0)) at the last level: row start3[b] := row start3[b] + 2
+__global__ void reflect_front_kernel(float* __restrict__ x, int ld, int C, const int* __restrict__ start3) {
+  int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x[(size_t)start3[b] * ld + c] = x[(size_t)(start3[b] + 2) * ld + c];
+}
+
+bool g_consts_ready = false;
+void init_consts() {
+  if (g_consts_ready) return;
+  float win[16], cs[16], sn[16];
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < 16; ++i) {
+    win[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / 16.0));   // scipy get_window('hann', 16, fftbins=True)
+    cs[i] = (float)cos(2.0 * PI * i / 16.0);
+    sn[i] = (float)sin(2.0 * PI * i / 16.0);
+  }
+  CVK_CHECK_CUDA(cudaMemcpyToSymbol(c_win, win, sizeof(win)));
+  CVK_CHECK_CUDA(cudaMemcpyToSymbol(c_cos, cs, sizeof(cs)));
+  CVK_CHECK_CUDA(cudaMemcpyToSymbol(c_sin, sn, sizeof(sn)));
+  g_consts_ready = true;
+}
+
+// ---------------------------------------------------------------------------------------------- model build
+ConvW wn_conv(cvk_ctx* ctx, const std::string& prefix, int dil, int shift0) {
+  float* w = fold_weight_norm(ctx, prefix, nullptr);
+  const RawTensor& v = ctx->has_raw(prefix + ".parametrizations.weight.original1") ? ctx->get_raw(prefix + ".parametrizations.weight.original1")
+                                                                                     : ctx->get_raw(prefix + ".weight_v");
+  const RawTensor& b = ctx->get_raw(prefix + ".bias");
+  return make_conv(ctx, w, b.p, (int)v.shape[0], (int)v.shape[1], (int)v.shape[2], dil, shift0);
+}
+
+ResBlockW build_resblock(cvk_ctx* ctx, const std::string& p, int k) {
+  ResBlockW r;
+  for (int i = 0; i < 3; ++i) {
+    int d = kDil[i];
+    r.c1[i] = wn_conv(ctx, p + ".convs1." + std::to_string(i), d, -((k - 1) * d) / 2);
+    r.c2[i] = wn_conv(ctx, p + ".convs2." + std::to_string(i), 1, -(k - 1) / 2);
+    r.a1[i] = dev_copy_f32(ctx, ctx->get_raw(p + ".activations1." + std::to_string(i) + ".alpha").p, r.c1[i].K);
+    r.a2[i] = dev_copy_f32(ctx, ctx->get_raw(p + ".activations2." + std::to_string(i) + ".alpha").p, r.c1[i].K);
+  }
+  return r;
+}
+
+}  // namespace
+
+void hift_build(cvk_ctx* ctx) {
+  init_consts();
+  HiftModel* m = new HiftModel();
+  const std::string P = "hift.";
+  for (int i = 0; i < 5; ++i) {
+    m->f0_conv[i] = wn_conv(ctx, P + "f0_predictor.condnet." + std::to_string(2 * i), 1, -1);
+    m->f0_conv[i].w16 = nullptr;   // the f0 predictor always runs fp32 (phase accumulates f0 over the utterance)
+  }
+  m->f0_cls = make_linear(ctx, P + "f0_predictor.classifier.weight", P + "f0_predictor.classifier.bias");
+  m->f0_cls.w16 = nullptr;
+  m->src_w = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.weight").p, 9);
+  m->src_b = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.bias").p, 1);
+  m->conv_pre = wn_conv(ctx, P + "conv_pre", 1, -3);
+  m->conv_post = wn_conv(ctx, P + "conv_post", 1, -3);
+  for (int i = 0; i < 3; ++i) {
+    // polyphase transposed convolution
+    std::string pre = P + "ups." + std::to_string(i);
+    float* w = fold_weight_norm(ctx, pre, nullptr);   // [Cin][Cout][k]
+    int Cin = kCh[i], Cout = kCh[i + 1], k = kUpK[i], s = kUps[i], p = (k - s) / 2;
+    ConvW c;
+    c.N = s * Cout; c.K = Cin; c.taps = 3; c.dil = 1; c.shift0 = -1;
+    c.w32 = (float*)ctx->dmalloc((size_t)c.N * 3 * Cin * sizeof(float));
+    polyphase_kernel<<<256, 256>>>(w, c.w32, Cin, Cout, k, s, p);
+    CVK_LAUNCH_CHECK();
+    c.bias = (float*)ctx->dmalloc((size_t)c.N * sizeof(float));
+    repeat_bias_kernel<<<ceil_div(c.N, 256), 256>>>(ctx->get_raw(pre + ".bias").p, c.bias, Cout, s);
+    CVK_LAUNCH_CHECK();
+    finish_convw(ctx, c);
+    m->ups[i] = c;
+  }
+  {
+    // source_downs: strided convs over the STFT matrix, expressed on its [R/s, s*24] view
+    const int ds[3] = {15, 3, 1}, dk[3] = {30, 6, 1}, dp[3] = {7, 1, 0};
+    for (int i = 0; i < 3; ++i) {
+      std::string pre = P + "source_downs." + std::to_string(i);
+      const RawTensor& w = ctx->get_raw(pre + ".weight");
+      int N = (int)w.shape[0], C = (int)w.shape[1], k = (int)w.shape[2];
+      CVK_REQUIRE(C == 18 && k == dk[i] && N == kCh[i + 1], "unexpected source_downs shape");
+      ConvW c;
+      c.N = N;
+      c.bias = dev_copy_f32(ctx, ctx->get_raw(pre + ".bias").p, N);
+      if (ds[i] == 1) {
+        c.K = kStftLd; c.taps = 1; c.dil = 1; c.shift0 = 0;
+        c.w32 = (float*)ctx->dmalloc((size_t)N * kStftLd * sizeof(float));
+        CVK_CHECK_CUDA(cudaMemset(c.w32, 0, (size_t)N * kStftLd * sizeof(float)));
+        CVK_CHECK_CUDA(cudaMemcpy2D(c.w32, kStftLd * sizeof(float), w.p, 18 * sizeof(float), 18 * sizeof(float), N, cudaMemcpyDeviceToDevice));
+      } else {
+        c.K = ds[i] * kStftLd; c.taps = 3; c.dil = 1; c.shift0 = -1;
+        size_t n = (size_t)N * 3 * c.K;
+        c.w32 = (float*)ctx->dmalloc(n * sizeof(float));
+        CVK_CHECK_CUDA(cudaMemset(c.w32, 0, n * sizeof(float)));
+        strided_view_fill_kernel<<<64, 256>>>(w.p, c.w32, N, C, k, ds[i], dp[i] + 1);
+        CVK_LAUNCH_CHECK();
+      }
+      finish_convw(ctx, c);
+      m->src_down[i] = c;
+    }
+  }
+  for (int i = 0; i < 3; ++i) m->src_rb[i] = build_resblock(ctx, P + "source_resblocks." + std::to_string(i), kSrcRbK[i]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m->rb[i * 3 + j] = build_resblock(ctx, P + "resblocks." + std::to_string(i * 3 + j), kRbK[j]);
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  ctx->hift = m;
+}
+
+// ================================================================================================ forward pieces
+struct HiftGeom {
+  Seqs s0;      // mel rate
+  Seqs lv[3];   // x8, x40, x120(+1 front row)
+};
+
+static HiftGeom hift_geom(cvk_ctx* ctx, const int* lens, int B, cudaStream_t st) {
+  HiftGeom g;
+  g.s0 = make_seqs(ctx, lens, B, 8, 1, 0, st);
+  g.lv[0] = scale_seqs(ctx, g.s0, 8, 0, st);
+  g.lv[1] = scale_seqs(ctx, g.s0, 40, 0, st);
+  g.lv[2] = scale_seqs(ctx, g.s0, 120, 1, st);
+  return g;
+}
+
+// mel32 packed [R0,80] fp32 -> f0 [R0] (ld 1)
+static void hift_f0_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s0, const Mat& mel32, const Mat& f0) {
+  HiftModel* m = ctx->hift;
+  Mat a = arena_mat(ctx, DT_F32, s0.R, 512), b = arena_mat(ctx, DT_F32, s0.R, 512);
+  Mat cur = mel32;
+  for (int i = 0; i < 5; ++i) {
+    Epilogue e;
+    e.act1 = ACT_ELU;
+    e.row2seq = s0.d_row2seq;
+    e.out = (i & 1) ? b : a;
+    conv_gemm_simt(ctx, st, cur, m->f0_conv[i], e);
+    cur = e.out;
+  }
+  Epilogue e;
+  e.act1 = ACT_ABS;
+  e.row2seq = s0.d_row2seq;
+  e.out = f0;
+  conv_gemm_simt(ctx, st, cur, m->f0_cls, e);
+}
+
+static int* upload_ints(cvk_ctx* ctx, const std::vector<int>& v, cudaStream_t st) {
+  int* d = (int*)ctx->arena.alloc(sizeof(int) * v.size());
+  CVK_CHECK_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, st));
+  return d;
+}
+
+static std::vector<int> prefix_offsets(const int* lens, int B) {
+  std::vector<int> off(B);
+  int acc = 0;
+  for (int b = 0; b < B; ++b) { off[b] = acc; acc += lens[b]; }
+  return off;
+}
+
+// f0 [R0] -> packed source [480*R0] fp32 (zero in gaps).  noise: dense [sum 480T][9]
+static void hift_source_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s0, const int* lens, const Mat& f0, const float* noise,
+                               float* src_packed) {
+  HiftModel* m = ctx->hift;
+  float* phase = (float*)ctx->arena.alloc(sizeof(float) * 9 * (size_t)s0.R);
+  phase_kernel<<<s0.B, 32, 0, st>>>(f0.f32(), f0.ld, s0.d_start, s0.d_len, phase);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  CVK_CHECK_CUDA(cudaMemsetAsync(src_packed, 0, sizeof(float) * (size_t)s0.R * kUpscale, st));
+  int* noff = upload_ints(ctx, prefix_offsets(lens, s0.B), st);
+  int bx = ceil_div(s0.max_len * kUpscale, 256);
+  if (bx > 512) bx = 512;
+  source_kernel<<<dim3(bx, s0.B), 256, 0, st>>>(f0.f32(), f0.ld, phase, s0.d_start, s0.d_len, noise, noff, m->src_w, m->src_b, src_packed);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+static void run_resblock(cvk_ctx* ctx, cudaStream_t st, const ResBlockW& rb, const Seqs& s, const Mat& x /*fp32 input*/,
+                         const Mat& a /*act(x) with alpha a1[0], act dtype, consumed*/, const Mat& ya, const Mat& xr /*fp32 scratch*/,
+                         const Mat& final_out, int final_accumulate) {
+  for (int d = 0; d < 3; ++d) {
+    Epilogue e1;
+    e1.act1 = ACT_SNAKE;
+    e1.alpha1 = rb.a2[d];
+    e1.row2seq = s.d_row2seq;
+    e1.out = ya;
+    conv_gemm(ctx, st, a, rb.c1[d], e1);
+    Epilogue e2;
+    e2.resid = d == 0 ? x : xr;
+    e2.row2seq = s.d_row2seq;
+    if (d < 2) {
+      e2.out = xr;
+      e2.act2 = ACT_SNAKE;
+      e2.alpha2 = rb.a1[d + 1];
+      e2.out2 = a;
+    } else {
+      e2.out = final_out;
+      e2.accumulate = final_accumulate;
+    }
+    conv_gemm(ctx, st, ya, rb.c2[d], e2);
+  }
+}
+
+// mel packed + source packed -> conv_post output [R3, 18] fp32 (ld 24)
+static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat& mel32, const float* src_packed) {
+  HiftModel* m = ctx->hift;
+  const int adt = ctx->act_dtype;
+  const Seqs& s0 = g.s0;
+  // STFT of the source at the x120 rate
+  const Seqs& s3 = g.lv[2];
+  Mat stft = arena_mat(ctx, adt, s3.R, kStftLd, kStftLd);
+  zero_mat(ctx, st, stft);
+  {
+    int F = s0.max_len * 120 + 1;
+    int bx = ceil_div(F, 128);
+    if (bx > 1024) bx = 1024;
+    if (adt == DT_F32) stft16_kernel<float><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.f32(), stft.ld);
+    else stft16_kernel<bf16><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.b16(), stft.ld);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  // conv_pre (+ leaky_relu 0.1 for ups[0])
+  Mat mel_a = mel32;
+  if (adt != DT_F32) {
+    mel_a = arena_mat(ctx, adt, s0.R, 80);
+    convert_mat(ctx, st, mel32, mel_a);
+  }
+  Mat xin = arena_mat(ctx, adt, s0.R, 512);
+  {
+    Epilogue e;
+    e.act1 = ACT_LRELU;
+    e.act1_param = 0.1f;
+    e.row2seq = s0.d_row2seq;
+    e.out = xin;
+    conv_gemm(ctx, st, mel_a, m->conv_pre, e);
+  }
+  const Seqs* sin_ = &s0;
+  // ping-pong buffers for the activated level outputs, sized for the largest level (x120, 64 ch)
+  const size_t lvl_elems = (size_t)g.lv[2].R * 64 > (size_t)g.lv[1].R * 128 ? (size_t)g.lv[2].R * 64 : (size_t)g.lv[1].R * 128;
+  void* nxt_buf[2];
+  nxt_buf[0] = ctx->arena.alloc(lvl_elems * (adt == DT_F32 ? 4 : 2));
+  nxt_buf[1] = ctx->arena.alloc(lvl_elems * (adt == DT_F32 ? 4 : 2));
+  for (int i = 0; i < 3; ++i) {
+    const Seqs& sl = g.lv[i];
+    const int C = kCh[i + 1];
+    const size_t mark = ctx->arena.off;   // per-level scratch is released at the end of the level (stream-ordered reuse)
+    // transposed conv (polyphase): [R_in, s*C] == [R_out, C]
+    Mat xu_in(ctx->arena.alloc((size_t)sl.R * C * 4), DT_F32, sin_->R, kUps[i] * C, kUps[i] * C);
+    {
+      Epilogue e;
+      e.row2seq = sin_->d_row2seq;
+      e.out = xu_in;
+      conv_gemm(ctx, st, xin, m->ups[i], e);
+    }
+    Mat xu(xu_in.p, DT_F32, sl.R, C, C);
+    if (i == 2) {
+      reflect_front_kernel<<<sl.B, 64, 0, st>>>(xu.f32(), xu.ld, C, sl.d_start);
+      ctx->launches++;
+      CVK_LAUNCH_CHECK();
+    }
+    // source branch
+    Mat si = arena_mat(ctx, DT_F32, sl.R, C);
+    Mat a = arena_mat(ctx, adt, sl.R, C);
+    Mat ya = arena_mat(ctx, adt, sl.R, C);
+    Mat xr = arena_mat(ctx, DT_F32, sl.R, C);
+    {
+      const int ds[3] = {15, 3, 1};
+      Mat view(stft.p, adt, s3.R / ds[i], ds[i] * kStftLd, ds[i] * kStftLd);
+      Epilogue e;
+      e.row2seq = sl.d_row2seq;
+      e.out = si;
+      e.act2 = ACT_SNAKE;
+      e.alpha2 = m->src_rb[i].a1[0];
+      e.out2 = a;
+      conv_gemm(ctx, st, view, m->src_down[i], e);
+    }
+    run_resblock(ctx, st, m->src_rb[i], sl, si, a, ya, xr, xu, 1);   // xu += source_resblock(si)
+    // main resblocks, summed into xs
+    Mat xs = arena_mat(ctx, DT_F32, sl.R, C);
+    for (int j = 0; j < 3; ++j) {
+      const ResBlockW& rb = m->rb[i * 3 + j];
+      act_copy(ctx, st, xu, ACT_SNAKE, 0.f, rb.a1[0], sl.d_row2seq, a);
+      run_resblock(ctx, st, rb, sl, xu, a, ya, xr, xs, j > 0);
+    }
+    // x = xs / 3 ; leaky_relu (0.1 before the next ups, default 0.01 before conv_post, generator.py:513,532)
+    Mat nxt(nxt_buf[i & 1], adt, sl.R, C, C);
+    act_copy_scaled(ctx, st, xs, 1.f / 3.f, ACT_LRELU, i < 2 ? 0.1f : 0.01f, nullptr, sl.d_row2seq, nxt);
+    xin = nxt;
+    sin_ = &sl;
+    ctx->arena.off = mark;
+  }
+  Mat xp = arena_mat(ctx, DT_F32, s3.R, 18, kStftLd);
+  {
+    Epilogue e;
+    e.row2seq = s3.d_row2seq;
+    e.out = xp;
+    conv_gemm(ctx, st, xin, m->conv_post, e);
+  }
+  return xp;
+}
+
+static void hift_istft(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const int* lens, const Mat& xp, float* wav_dense) {
+  const Seqs& s0 = g.s0;
+  int* ooff = upload_ints(ctx, prefix_offsets(lens, s0.B), st);
+  int bx = ceil_div(s0.max_len * kUpscale, 512);
+  istft16_kernel<<<dim3(bx, s0.B), 128, 0, st>>>(xp.f32(), xp.ld, g.lv[2].d_start, s0.d_len, ooff, wav_dense, 0.99f);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+__global__ void gather_f0_kernel(const float* __restrict__ f0, int ld, const int* __restrict__ start, const int* __restrict__ len,
+                                 const int* __restrict__ off, float* __restrict__ out) {
+  int b = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len[b]; t += gridDim.x * blockDim.x) out[off[b] + t] = f0[(size_t)(start[b] + t) * ld];
+}
+__global__ void scatter_f0_kernel(const float* __restrict__ in, const int* __restrict__ start, const int* __restrict__ len,
+                                  const int* __restrict__ off, float* __restrict__ f0, int ld) {
+  int b = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len[b]; t += gridDim.x * blockDim.x) f0[(size_t)(start[b] + t) * ld] = in[off[b] + t];
+}
+__global__ void copy_samples_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ start,
+                                    const int* __restrict__ len, const int* __restrict__ off, int to_packed) {
+  int b = blockIdx.y;
+  int L = len[b] * kUpscale;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    size_t pi = (size_t)start[b] * kUpscale + i, di = (size_t)off[b] * kUpscale + i;
+    if (to_packed) out[pi] = in[di];
+    else out[di] = in[pi];
+  }
+}
+
+static Mat pack_mel(cvk_ctx* ctx, cudaStream_t st, const Seqs& s0, const float* mel) {
+  Mat mel32 = arena_mat(ctx, DT_F32, s0.R, 80);
+  zero_mat(ctx, st, mel32);
+  pack_rows(ctx, st, mel, 80, s0, mel32);
+  return mel32;
+}
+
+// ================================================================================================ entry points (called from api.cu)
+void hift_f0(cvk_ctx* ctx, const float* mel, const int* lens, int B, float* f0_out, cudaStream_t st) {
+  CVK_REQUIRE(ctx->hift, "hift stage not finalised");
+  ctx->arena.reset();
+  Seqs s0 = make_seqs(ctx, lens, B, 8, 1, 0, st);
+  Mat mel32 = pack_mel(ctx, st, s0, mel);
+  Mat f0 = arena_mat(ctx, DT_F32, s0.R, 1, 1);
+  hift_f0_packed(ctx, st, s0, mel32, f0);
+  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  gather_f0_kernel<<<dim3(ceil_div(s0.max_len, 128), B), 128, 0, st>>>(f0.f32(), 1, s0.d_start, s0.d_len, off, f0_out);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+void hift_source(cvk_ctx* ctx, const float* f0_dense, const int* lens, int B, const float* noise, float* source_out, cudaStream_t st) {
+  CVK_REQUIRE(ctx->hift, "hift stage not finalised");
+  ctx->arena.reset();
+  Seqs s0 = make_seqs(ctx, lens, B, 8, 1, 0, st);
+  Mat f0 = arena_mat(ctx, DT_F32, s0.R, 1, 1);
+  zero_mat(ctx, st, f0);
+  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  scatter_f0_kernel<<<dim3(ceil_div(s0.max_len, 128), B), 128, 0, st>>>(f0_dense, s0.d_start, s0.d_len, off, f0.f32(), 1);
+  ctx->launches++;
+  float* src = (float*)ctx->arena.alloc(sizeof(float) * (size_t)s0.R * kUpscale);
+  hift_source_packed(ctx, st, s0, lens, f0, noise, src);
+  copy_samples_kernel<<<dim3(256, B), 256, 0, st>>>(src, source_out, s0.d_start, s0.d_len, off, 0);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+void hift_decode(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* source, float* wav, cudaStream_t st) {
+  CVK_REQUIRE(ctx->hift, "hift stage not finalised");
+  ctx->arena.reset();
+  HiftGeom g = hift_geom(ctx, lens, B, st);
+  Mat mel32 = pack_mel(ctx, st, g.s0, mel);
+  float* src = (float*)ctx->arena.alloc(sizeof(float) * (size_t)g.s0.R * kUpscale);
+  CVK_CHECK_CUDA(cudaMemsetAsync(src, 0, sizeof(float) * (size_t)g.s0.R * kUpscale, st));
+  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  copy_samples_kernel<<<dim3(256, B), 256, 0, st>>>(source, src, g.s0.d_start, g.s0.d_len, off, 1);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  Mat xp = hift_body(ctx, st, g, mel32, src);
+  hift_istft(ctx, st, g, lens, xp, wav);
+}
+
+void hift_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, const float* noise, const float* cache_source,
+                    const int* cache_lens, float* wav, float* source_out, cudaStream_t st) {
+  CVK_REQUIRE(ctx->hift, "hift stage not finalised");
+  ctx->arena.reset();
+  HiftGeom g = hift_geom(ctx, lens, B, st);
+  Mat mel32 = pack_mel(ctx, st, g.s0, mel);
+  Mat f0 = arena_mat(ctx, DT_F32, g.s0.R, 1, 1);
+  hift_f0_packed(ctx, st, g.s0, mel32, f0);
+  float* src = (float*)ctx->arena.alloc(sizeof(float) * (size_t)g.s0.R * kUpscale);
+  hift_source_packed(ctx, st, g.s0, lens, f0, noise, src);
+  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  if (cache_source && cache_lens) {
+    std::vector<int> cl(cache_lens, cache_lens + B);
+    int mx = 0;
+    for (int b = 0; b < B; ++b) {
+      CVK_REQUIRE(cl[b] <= lens[b] * kUpscale, "cache_source longer than the utterance");
+      if (cl[b] > mx) mx = cl[b];
+    }
+    if (mx > 0) {
+      int* coff = upload_ints(ctx, prefix_offsets(cache_lens, B), st);
+      int* clen = upload_ints(ctx, cl, st);
+      cache_source_kernel<<<dim3(ceil_div(mx, 256), B), 256, 0, st>>>(cache_source, coff, clen, g.s0.d_start, src);
+      ctx->launches++;
+      CVK_LAUNCH_CHECK();
+    }
+  }
+  if (source_out) {
+    copy_samples_kernel<<<dim3(256, B), 256, 0, st>>>(src, source_out, g.s0.d_start, g.s0.d_len, off, 0);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  Mat xp = hift_body(ctx, st, g, mel32, src);
+  hift_istft(ctx, st, g, lens, xp, wav);
+}

@@ -1,0 +1,145 @@
+/* libcvk - C ABI of the B200-native CosyVoice2 hot path (LM decode -> CFM flow -> HiFT vocoder + mel frontend).
+ *
+ * This header is the drop-in boundary.  The reference is pure Python, so there is no FFI to
+ * mirror symbol-for-symbol; each entry point replaces one of the engine plug-in granularities the reference itself
+ * swaps (TensorRT estimator, vLLM LM, TorchScript encoder) or one stage-model method, cited per function as
+ * "replaces <file>:<lines>" relative to the reference tree.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in _host.  Memory is owned by the caller (PyTorch
+ *    allocates it); the library owns only its repacked weights, KV arena and workspace, all inside cvk_ctx.
+ *  - Activations cross the ABI as *ragged time-major* fp32 matrices: the B sequences are concatenated along
+ *    rows without padding, `lens_host[b]` rows each, channels contiguous ([sum(lens), C]).
+ *  - Every call takes an explicit cudaStream_t (passed as void*), never touches the default stream on its own
+ *    and never calls cudaDeviceSynchronize.  Calls on one ctx must be serialised by the caller (one workspace).
+ *  - Return value: 0 on success, a negative cvk_status otherwise; cvk_last_error(ctx) holds the message.  No C++
+ *    exception crosses the ABI.  There is NO CPU fallback: without a CUDA device cvk_create fails.
+ */
+#ifndef CVK_H_
+#define CVK_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvk_ctx cvk_ctx;
+
+typedef enum {
+  CVK_OK = 0,
+  CVK_ERR_INVALID = -1,        /* bad argument / shape (reference: AssertionError / ValueError) */
+  CVK_ERR_CUDA = -2,           /* CUDA runtime / driver error */
+  CVK_ERR_OOM = -3,            /* workspace or KV arena exhausted */
+  CVK_ERR_MISSING_WEIGHT = -4, /* a state_dict key required by cvk_finalize was not supplied */
+  CVK_ERR_STATE = -5           /* stage not finalised / session misuse */
+} cvk_status;
+
+/* arithmetic of the tensor-core stages */
+#define CVK_PREC_FP32 0 /* everything fp32 on CUDA cores: parity mode, tracks the CPU reference to ~1e-4 */
+#define CVK_PREC_BF16 1 /* dense GEMM / conv operands bf16 on tcgen05 tensor cores, fp32 accumulate + residuals */
+
+/* ---------------------------------------------------------------------------------------------- context */
+int cvk_create(int device, int precision, size_t workspace_bytes, cvk_ctx** out);
+void cvk_destroy(cvk_ctx* ctx);
+const char* cvk_last_error(cvk_ctx* ctx);
+const char* cvk_version(void);
+/* kernels launched by this library since creation (bench.py "gpu_launches") */
+int64_t cvk_launch_count(cvk_ctx* ctx);
+/* debug switch: 1 (default) = bf16 GEMMs on the tcgen05 kernel, 0 = same operands through the SIMT kernel */
+int cvk_set_option(cvk_ctx* ctx, const char* key, int value);
+
+/* ---------------------------------------------------------------------------------------------- weights
+ * replaces cosyvoice/cli/model.py:65-73 (CosyVoice2Model.load -> load_state_dict(strict=True)).
+ * `name` = "<stage>." + reference state_dict key, stage in {"llm","flow","hift"}; data fp32, C-contiguous, on the
+ * device (on_device=1) or host.  cvk_finalize(stage) folds weight-norm (g*v/||v||), repacks convolutions to
+ * [Cout][tap][Cin], builds polyphase transposed-conv weights and bf16 copies, then drops the raw tensors.
+ * cfg: hift: none; flow: {enc_blocks, enc_up_blocks, num_mid_blocks, n_blocks}; llm: {num_layers}. */
+int cvk_set_tensor(cvk_ctx* ctx, const char* name, const float* data, int on_device, const int64_t* shape, int ndim);
+int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg);
+
+/* ---------------------------------------------------------------------------------------------- generic ops
+ * exposed for per-op parity tests (tests/test_ops_gpu.py); same kernels the stages use. */
+/* out[r,n] = act(bias[n] + sum_j sum_k x[r + shift0 + j*dil, k] * w[n,k,j]) for one zero-padded sequence per
+ * entry of lens_host.  w is a torch Conv1d weight [N,K,taps] fp32 on the device. */
+int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens_host, int B, int K, const float* w, const float* bias,
+                  int N, int taps, int dil, int shift0, int act, float* out, void* stream);
+/* block-causal / full multi-head attention over ragged sequences; q,k,v,out [sum(lens), H*64] */
+int cvk_op_attention(cvk_ctx* ctx, const float* q, const float* k, const float* v, const int* lens_host, int B, int H,
+                     int chunk, float scale, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- HiFT vocoder
+ * replaces cosyvoice/hifigan/generator.py:557-569 (HiFTGenerator.inference) and its parts. */
+/* f0_predictor.py:56-59: mel [sum T,80] -> f0 [sum T] */
+int cvk_hift_f0(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, float* f0, void* stream);
+/* generator.py:560-564 + SourceModuleHnNSF/SineGen2: f0 [sum T], noise [sum 480T, 9] (standard-normal draws, the
+ * reference's randn_like) -> source [sum 480T] */
+int cvk_hift_source(cvk_ctx* ctx, const float* f0, const int* lens_host, int B, const float* noise, float* source,
+                    void* stream);
+/* generator.py:507-539 (decode): mel [sum T,80], source [sum 480T] -> wav [sum 480T] (clamped to +-0.99) */
+int cvk_hift_decode(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, const float* source, float* wav,
+                    void* stream);
+/* whole inference(); cache_source (optional, may be NULL) [sum cache_lens] overwrites the head of each source
+ * (generator.py:566-567, streaming glue).  Outputs wav [sum 480T], source [sum 480T]. */
+int cvk_hift_inference(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, const float* noise,
+                       const float* cache_source, const int* cache_lens_host, float* wav, float* source, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- flow (token -> mel)
+ * replaces cosyvoice/flow/flow.py:235-281 (CausalMaskedDiffWithXvec.inference) and the engine plug-in points
+ * flow/flow_matching.py:126-153 (forward_estimator: the TensorRT swap point) and cli/model.py:277-279 (encoder). */
+/* transformer/upsample_encoder.py:244-307 on token ids.  tokens [sum N] int32 (prompt ++ generated per sequence).
+ * context_len: 0 (finalize) or 3 (the last 3 tokens of every sequence are look-ahead context only,
+ * flow.py:259-261).  out h [sum 2*(N-context_len), 512]. */
+int cvk_flow_encoder(cvk_ctx* ctx, const int32_t* tokens, const int* lens_host, int B, int streaming, int context_len,
+                     float* h, void* stream);
+/* flow/decoder.py:405-494 (CausalConditionalDecoder.forward) - same I/O contract as the TensorRT engine:
+ * x, mu, cond [sum T,80]; t [B]; spks [B,80]; out [sum T,80]; mask = ones within each length. */
+int cvk_cfm_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond,
+                      const int* lens_host, int B, int streaming, float* out, void* stream);
+/* flow/flow_matching.py:203-227 + 71-124: fixed seed-0 noise unless z given ([sum T,80]), cosine schedule, Euler,
+ * CFG.  mu, cond [sum T,80]; spks [B,80]; out mel [sum T,80]. */
+int cvk_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float* cond, const int* lens_host, int B,
+                  const float* z, int n_timesteps, float cfg_rate, int streaming, float* out, void* stream);
+/* flow.py:235-281 end to end.  tokens [sum (P_b+N_b)] (prompt then generated), prompt_feat [sum Tp_b, 80],
+ * embedding [B,192]; finalize=0 treats the last 3 tokens as look-ahead.  out mel [sum (2*(P+N-ctx) - Tp), 80]. */
+int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens_host, const float* prompt_feat,
+                       const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming,
+                       int finalize, float* mel, void* stream);
+/* the fixed noise tensor of CausalConditionalCFM (flow_matching.py:199-200) must be supplied once: [15000,80]
+ * time-major (it is torch's seed-0 randn stream; the library does not re-implement torch's Philox/MT generator) */
+int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device);
+
+/* ---------------------------------------------------------------------------------------------- speech-token LM
+ * replaces cosyvoice/llm/llm.py:458-549 (Qwen2LM.inference / inference_wrapper; the vLLM swap point :506-534). */
+typedef struct cvk_lm_session cvk_lm_session;
+int cvk_lm_session_create(cvk_ctx* ctx, int max_batch, int max_context, cvk_lm_session** out);
+void cvk_lm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s);
+/* llm.py:474-494: assemble [sos, embed(text), task_id, speech_embedding(prompt)] for B rows and run the prefill.
+ * text [sum Nt] (prompt_text ++ text per row), speech [sum Np].  After the call the session holds the KV cache and
+ * the hidden state of the last prompt position of every row. */
+int cvk_lm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const int* text_lens_host,
+                   const int32_t* speech, const int* speech_lens_host, int B, void* stream);
+/* llm.py:536-549: run up to n_steps decode steps for all live rows: head -> log_softmax -> RAS sampling ->
+ * stop test -> next embedding.  uniforms [max_steps][B][2] (u1 nucleus draw, u2 fallback draw) indexed by the
+ * absolute step; min_len/max_len [B] (device int32).  out_ids [B][out_ld] receives the accepted ids, out_count [B]
+ * their number, done [B] (1 once a row hit a stop id or max_len).  Returns the number of live rows via
+ * *live_host after synchronising the stream when live_host != NULL. */
+int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len,
+                  const int32_t* max_len, int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host,
+                  void* stream);
+/* teacher-forced log-probs for parity tests: embeds [sum L, 896] -> logp [sum L, 6564] */
+int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens_host, int B, float* logp, void* stream);
+/* utils/common.py:138-167 + llm.py:150-160 as one kernel.  logp [B,V] (modified in place like the reference),
+ * history [B, hist_ld] with hist_count [B] valid entries, uniforms [B,2], ignore_eos [B]; out ids [B]. */
+int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
+                   const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- mel frontend
+ * replaces third_party/Matcha-TTS/matcha/utils/audio.py:45-82 with cosyvoice2.yaml:150-158 parameters.
+ * wav [sum N] (24 kHz, N multiple of 480) -> mel [sum N/480, 80] */
+int cvk_mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, float* mel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVK_H_ */
