@@ -65,6 +65,39 @@ Seqs scale_seqs(cvk_ctx* ctx, const Seqs& b, int scale, int extra_front, cudaStr
   return s;
 }
 
+// same rows, every sequence shortened by drop_tail rows at its end (flow look-ahead context, flow/flow.py:259-261)
+Seqs shrink_seqs(cvk_ctx* ctx, const Seqs& b, int drop_tail, cudaStream_t st) {
+  Seqs s;
+  s.B = b.B;
+  s.start = b.start;
+  s.len.resize(b.B);
+  for (int i = 0; i < b.B; ++i) {
+    s.len[i] = b.len[i] - drop_tail;
+    CVK_REQUIRE(s.len[i] > 0, "sequence shorter than the look-ahead context");
+    if (s.len[i] > s.max_len) s.max_len = s.len[i];
+    s.sum_len += s.len[i];
+  }
+  s.R = b.R;
+  upload_seqs(ctx, s, st, true);
+  return s;
+}
+
+// same rows, sequence b restricted to its first skip[b] rows (prompt part)
+Seqs subseqs(cvk_ctx* ctx, const Seqs& b, const int* head_host, cudaStream_t st) {
+  Seqs s;
+  s.B = b.B;
+  s.start = b.start;
+  s.len.assign(head_host, head_host + b.B);
+  for (int i = 0; i < b.B; ++i) {
+    CVK_REQUIRE(s.len[i] >= 0 && s.len[i] <= b.len[i], "prefix longer than the sequence");
+    if (s.len[i] > s.max_len) s.max_len = s.len[i];
+    s.sum_len += s.len[i];
+  }
+  s.R = b.R;
+  upload_seqs(ctx, s, st, false);
+  return s;
+}
+
 // ================================================================================================ weights
 namespace {
 // torch Conv1d weight [N][K][taps] -> [N][taps][K]
@@ -183,13 +216,14 @@ __global__ void zero_kernel(TO* __restrict__ p, int rows, int cols, int ld) {
 template <typename TO>
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int act, float post_scale, const int* __restrict__ row2seq,
-                                 TO* __restrict__ out, int ldo) {
+                                 TO* __restrict__ out, int ldo, const float* __restrict__ rowvec, int rowvec_ld) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xp = x + (size_t)warp * ldx;
   TO* op = out + (size_t)warp * ldo;
-  bool valid = !row2seq || row2seq[warp] >= 0;
+  int seq = row2seq ? row2seq[warp] : 0;
+  bool valid = seq >= 0;
   if (!valid) {
     for (int c = lane; c < C; c += 32) op[c] = from_f32<TO>(0.f);
     return;
@@ -207,6 +241,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, int rows,
     float y = (xp[c] - mean) * rstd;
     if (gamma) y = y * gamma[c] + (beta ? beta[c] : 0.f);
     y = apply_act(act, y, 0.f, 1.f) * post_scale;
+    if (rowvec) y += rowvec[(size_t)seq * rowvec_ld + c];
     op[c] = from_f32<TO>(y);
   }
 }
@@ -252,8 +287,10 @@ __global__ void pack_rows_kernel(const float* __restrict__ dense, int C, const i
 }
 template <typename TI>
 __global__ void unpack_rows_kernel(const TI* __restrict__ in, int ldi, const int* __restrict__ start, const int* __restrict__ len,
-                                   int skip, float* __restrict__ dense, int C, const int* __restrict__ dense_off) {
+                                   int skip_all, const int* __restrict__ skips, float* __restrict__ dense, int C,
+                                   const int* __restrict__ dense_off) {
   int b = blockIdx.y;
+  int skip = skips ? skips[b] : skip_all;
   int l = len[b] - skip, s = start[b] + skip;
   if (l <= 0) return;
   size_t total = (size_t)l * C;
@@ -295,14 +332,14 @@ void zero_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& m) {
 }
 
 void layernorm(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const float* gamma, const float* beta, float eps, int act,
-               float post_scale, const int* row2seq, const Mat& out) {
+               float post_scale, const int* row2seq, const Mat& out, const float* rowvec, int rowvec_ld) {
   CVK_REQUIRE(x.dtype == DT_F32, "layernorm input must be fp32");
   int rows = x.rows, C = x.cols;
   int blocks = ceil_div(rows, 8);
   if (out.dtype == DT_F32)
-    layernorm_kernel<float><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, C, gamma, beta, eps, act, post_scale, row2seq, out.f32(), out.ld);
+    layernorm_kernel<float><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, C, gamma, beta, eps, act, post_scale, row2seq, out.f32(), out.ld, rowvec, rowvec_ld);
   else
-    layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, C, gamma, beta, eps, act, post_scale, row2seq, out.b16(), out.ld);
+    layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, C, gamma, beta, eps, act, post_scale, row2seq, out.b16(), out.ld, rowvec, rowvec_ld);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }
@@ -366,8 +403,27 @@ void unpack_rows(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Seqs& s, in
   int* off = dense_offsets(ctx, s, skip, st);
   int bx = grid_for((size_t)s.max_len * C);
   if (bx > 256) bx = 256;
-  if (in.dtype == DT_F32) unpack_rows_kernel<float><<<dim3(bx, s.B), 256, 0, st>>>(in.f32(), in.ld, s.d_start, s.d_len, skip, dense, C, off);
-  else unpack_rows_kernel<bf16><<<dim3(bx, s.B), 256, 0, st>>>(in.b16(), in.ld, s.d_start, s.d_len, skip, dense, C, off);
+  if (in.dtype == DT_F32) unpack_rows_kernel<float><<<dim3(bx, s.B), 256, 0, st>>>(in.f32(), in.ld, s.d_start, s.d_len, skip, nullptr, dense, C, off);
+  else unpack_rows_kernel<bf16><<<dim3(bx, s.B), 256, 0, st>>>(in.b16(), in.ld, s.d_start, s.d_len, skip, nullptr, dense, C, off);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+void unpack_rows_skip(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Seqs& s, const int* skip_host, float* dense, int C) {
+  std::vector<int> off(s.B), sk(skip_host, skip_host + s.B);
+  int acc = 0;
+  for (int b = 0; b < s.B; ++b) {
+    off[b] = acc;
+    acc += s.len[b] - sk[b];
+  }
+  int* d_off = (int*)ctx->arena.alloc(sizeof(int) * s.B);
+  int* d_sk = (int*)ctx->arena.alloc(sizeof(int) * s.B);
+  CVK_CHECK_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int) * s.B, cudaMemcpyHostToDevice, st));
+  CVK_CHECK_CUDA(cudaMemcpyAsync(d_sk, sk.data(), sizeof(int) * s.B, cudaMemcpyHostToDevice, st));
+  int bx = grid_for((size_t)s.max_len * C);
+  if (bx > 256) bx = 256;
+  if (in.dtype == DT_F32) unpack_rows_kernel<float><<<dim3(bx, s.B), 256, 0, st>>>(in.f32(), in.ld, s.d_start, s.d_len, 0, d_sk, dense, C, d_off);
+  else unpack_rows_kernel<bf16><<<dim3(bx, s.B), 256, 0, st>>>(in.b16(), in.ld, s.d_start, s.d_len, 0, d_sk, dense, C, d_off);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

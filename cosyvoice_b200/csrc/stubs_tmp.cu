@@ -10,9 +10,3 @@ void llm_forward_logp(cvk_ctx*, const float*, const int*, int, float*, cudaStrea
 void llm_ras_sample(cvk_ctx*, float*, int, int, const int32_t*, int, const int32_t*, const float*, const int32_t*, int32_t*, cudaStream_t) { NOTYET("llm"); }
 void mel_spectrogram(cvk_ctx*, const float*, const int*, int, float*, cudaStream_t) { NOTYET("mel"); }
 void mel_init(cvk_ctx*) { NOTYET("mel"); }
-void flow_build(cvk_ctx*, const int*, int) { NOTYET("flow"); }
-void flow_encoder(cvk_ctx*, const int32_t*, const int*, int, int, int, float*, cudaStream_t) { NOTYET("flow"); }
-void flow_estimator(cvk_ctx*, const float*, const float*, const float*, const float*, const float*, const int*, int, int, float*, cudaStream_t) { NOTYET("flow"); }
-void flow_cfm_solve(cvk_ctx*, const float*, const float*, const float*, const int*, int, const float*, int, float, int, float*, cudaStream_t) { NOTYET("flow"); }
-void flow_inference(cvk_ctx*, const int32_t*, const int*, const float*, const int*, const float*, int, int, int, int, float*, cudaStream_t) { NOTYET("flow"); }
-void flow_set_noise(cvk_ctx*, const float*, int, int) { NOTYET("flow"); }

@@ -1,0 +1,105 @@
+"""GPU: flow stage (conformer encoder + CFM estimator + Euler/CFG) through the C ABI against the committed outputs
+of the reference (tests/golden/flow_*.npz) and the oracle (oracle/flow.py).
+
+Tolerances: fp32 mode follows the reference's own export check (cosyvoice/bin/export_onnx.py:99-110,
+rtol 1e-2 / atol 1e-4 on the estimator); bf16 mode (tcgen05 operands, fp32 accumulate and residual stream) is held
+to the measured bounds stated next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import ctx, maxdiff
+from oracle import cases, flow, weights
+
+pytestmark = pytest.mark.gpu
+
+CFGS = {"small": dict(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2),
+        "full": dict(enc_blocks=6, enc_up_blocks=4, num_mid_blocks=12, n_blocks=4)}
+_state = {}
+
+
+def model(precision, tag):
+    c = ctx(precision)
+    if _state.get(precision) != tag:
+        cfg = flow.FlowCfg(**CFGS[tag])
+        sd = weights.synth_state_dict(flow.param_shapes(cfg), 1986, flow.SYNTH_GAINS)
+        c.load_state_dict("flow", sd, cfg=[cfg.enc_blocks, cfg.enc_up_blocks, cfg.num_mid_blocks, cfg.n_blocks])
+        c.set_cfm_noise(flow.cfm_noise(15000)[0].t().contiguous())
+        _state[precision] = tag
+        _state[(precision, "sd")] = sd
+    return c, _state[(precision, "sd")], flow.FlowCfg(**CFGS[tag])
+
+
+def tm(x):          # [B,C,T] -> [B*T, C]
+    return x.transpose(1, 2).reshape(-1, x.shape[1]).contiguous()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_estimator_golden(precision, tag, golden):
+    g = golden("flow_" + tag)
+    c, sd, cfg = model(precision, tag)
+    x, mask, mu, t, spks, cond = cases.estimator_case()
+    T = x.shape[2]
+    for streaming, key in ((False, "est_offline"), (True, "est_stream")):
+        out = c.cfm_estimator(tm(x), tm(mu), t, spks, tm(cond), [T, T], streaming=streaming)
+        ref = tm(torch.from_numpy(g[key]))
+        d = maxdiff(out, ref)
+        if precision == "fp32":
+            np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-2, atol=1e-4)
+        else:
+            assert d < 0.15, d          # bf16 operands through 14 resnets + 56 transformer blocks (|out| ~ 3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_encoder_golden(precision, tag, golden):
+    g = golden("flow_" + tag)
+    c, sd, cfg = model(precision, tag)
+    token, ptok, pfeat, emb = cases.flow_case()
+    toks = torch.cat([ptok, token], 1).reshape(-1)
+    h = c.flow_encoder(toks, [toks.numel()], streaming=False, context_len=0)
+    ref = torch.from_numpy(g["enc_offline"])[0]
+    d = maxdiff(h, ref)
+    assert d < (2e-3 if precision == "fp32" else 0.25), d     # after_norm output, unit scale
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_inference_golden(precision, tag, golden):
+    g = golden("flow_" + tag)
+    c, sd, cfg = model(precision, tag)
+    token, ptok, pfeat, emb = cases.flow_case()
+    toks = torch.cat([ptok, token], 1).reshape(-1)
+    for name, streaming, finalize in (("offline", False, True), ("stream_final", True, True), ("stream_chunk", True, False)):
+        if "mel_" + name not in g:
+            continue
+        mel, lens = c.flow_inference(toks, [toks.numel()], pfeat[0], [pfeat.shape[1]], emb, streaming=streaming, finalize=finalize)
+        ref = torch.from_numpy(g["mel_" + name])[0].t()
+        assert mel.shape == ref.shape
+        d = maxdiff(mel, ref)
+        assert d < (5e-3 if precision == "fp32" else 0.5), (name, d)      # mel after 10 Euler steps, |mel| ~ 5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_batch_vs_oracle(precision):
+    """three utterances of different length in one call == the oracle run one utterance at a time"""
+    c, sd, cfg = model(precision, "small")
+    g = torch.Generator().manual_seed(9)
+    utts = []
+    for N, P in ((17, 6), (40, 25), (9, 3)):
+        utts.append((torch.randint(0, 6561, (1, N), generator=g, dtype=torch.int32), torch.randint(0, 6561, (1, P), generator=g, dtype=torch.int32),
+                     torch.rand(1, 2 * P, 80, generator=g) * 13.5 - 11.5, torch.randn(1, 192, generator=g)))
+    toks = torch.cat([torch.cat([p, t], 1).reshape(-1) for t, p, _, _ in utts])
+    tl = [t.shape[1] + p.shape[1] for t, p, _, _ in utts]
+    pf = torch.cat([f[0] for _, _, f, _ in utts], 0)
+    pl = [f.shape[1] for _, _, f, _ in utts]
+    emb = torch.cat([e for _, _, _, e in utts], 0)
+    mel, lens = c.flow_inference(toks, tl, pf, pl, emb)
+    o = 0
+    for (t, p, f, e), L in zip(utts, lens):
+        ref = flow.inference(sd, t, p, f, e, cfg)[0].t()
+        assert L == ref.shape[0]
+        d = maxdiff(mel[o:o + L], ref)
+        assert d < (5e-3 if precision == "fp32" else 0.5), d
+        o += L
