@@ -20,7 +20,7 @@ template <typename T, bool RELPOS>
 __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
                                                         const T* __restrict__ v, int ldv, const T* __restrict__ pos, int ldp, int pos_rows, int pos_center,
                                                         const float* __restrict__ bias_u, const float* __restrict__ bias_v,
-                                                        const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale,
+                                                        const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale, int kv_div,
                                                         T* __restrict__ out, int ldo) {
   __shared__ float Qs[BQ][HD + 1];
   __shared__ float Ks[BKEY][HD + 1];
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
       int j = e >> 6, d = e & 63;
       float kv = 0.f, vv = 0.f;
       if (j0 + j < L) {
-        kv = to_f32(k[(size_t)(s0 + j0 + j) * ldk + h * HD + d]);
-        vv = to_f32(v[(size_t)(s0 + j0 + j) * ldv + h * HD + d]);
+        kv = to_f32(k[(size_t)(s0 + j0 + j) * ldk + (h / kv_div) * HD + d]);
+        vv = to_f32(v[(size_t)(s0 + j0 + j) * ldv + (h / kv_div) * HD + d]);
       }
       Ks[j][d] = kv;
       Vs[j][d] = vv;
@@ -163,15 +163,15 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
 }  // namespace
 
 void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                   float scale, const Mat& out) {
+                   float scale, const Mat& out, int kv_div) {
   CVK_REQUIRE(q.dtype == k.dtype && q.dtype == v.dtype && q.dtype == out.dtype, "attention: mixed dtypes");
   dim3 grid(ceil_div(s.max_len, BQ), H, s.B);
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, false><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, nullptr, 0, 0, 0, nullptr, nullptr,
-                                                         s.d_start, s.d_len, chunk, scale, out.f32(), out.ld);
+                                                         s.d_start, s.d_len, chunk, scale, kv_div, out.f32(), out.ld);
   else
     attn_simt_kernel<bf16, false><<<grid, 128, 0, st>>>(q.b16(), q.ld, k.b16(), k.ld, v.b16(), v.ld, nullptr, 0, 0, 0, nullptr, nullptr,
-                                                        s.d_start, s.d_len, chunk, scale, out.b16(), out.ld);
+                                                        s.d_start, s.d_len, chunk, scale, kv_div, out.b16(), out.ld);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }
@@ -183,10 +183,10 @@ void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat
   dim3 grid(ceil_div(s.max_len, BQ), H, s.B);
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, true><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, pos.f32(), pos.ld, pos.rows, pos_center, bias_u,
-                                                        bias_v, s.d_start, s.d_len, chunk, scale, out.f32(), out.ld);
+                                                        bias_v, s.d_start, s.d_len, chunk, scale, 1, out.f32(), out.ld);
   else
     attn_simt_kernel<bf16, true><<<grid, 128, 0, st>>>(q.b16(), q.ld, k.b16(), k.ld, v.b16(), v.ld, pos.b16(), pos.ld, pos.rows, pos_center, bias_u,
-                                                       bias_v, s.d_start, s.d_len, chunk, scale, out.b16(), out.ld);
+                                                       bias_v, s.d_start, s.d_len, chunk, scale, 1, out.b16(), out.ld);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

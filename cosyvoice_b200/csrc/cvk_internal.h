@@ -150,6 +150,7 @@ struct cvk_ctx {
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
+  int use_graph = 1;                        // LM decode step replayed as a CUDA graph
   int use_tc = 1;                           // bf16 mode: route GEMMs to the tcgen05 kernel (0 = debug: SIMT on converted operands)
 
   void* dmalloc(size_t bytes) {
@@ -207,7 +208,7 @@ void convert_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Mat& out);
 //  q,k,v: packed [R, H*64] views (same Seqs); mask: key j visible from query i iff j < klimit(i), with
 //  klimit(i) = len (chunk<=0) or min(len, (i/chunk+1)*chunk) (block-causal, utils/mask.py:155-157)
 void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                   float scale, const Mat& out);
+                   float scale, const Mat& out, int kv_div = 1);
 void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Mat& pos /*[2*Tmax-1, H*64]*/,
                           int pos_center, const float* bias_u, const float* bias_v, const Seqs& s, int H, int chunk, float scale,
                           const Mat& out);

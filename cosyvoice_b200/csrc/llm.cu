@@ -1,0 +1,776 @@
+// CosyVoice2 speech-token LM: Qwen2-0.5B-shaped decoder driven through inputs_embeds, KV-cached autoregressive
+// decode, fused log-softmax + repetition-aware sampling + stop logic + next-embedding gather.
+//
+// Follows cosyvoice/llm/llm.py:458-502 (Qwen2LM.inference: prompt assembly), :536-549 (inference_wrapper decode
+// loop), :150-160 (sampling_ids), cosyvoice/utils/common.py:138-167 (ras_sampling / nucleus_sampling /
+// random_sampling).  The transformer arithmetic is transformers' Qwen2 (modeling_qwen2.py):
+// RMSNorm(1e-6) -> q/k/v (+bias) -> half-split RoPE(theta 1e6) -> GQA 14/2 x 64 -> o_proj -> +res -> RMSNorm ->
+// SwiGLU(4864) -> +res, 24 layers, final RMSNorm.
+//
+// Batched over B independent rows (the reference decodes one utterance at a time).  One decode step for all rows is
+// captured into a CUDA graph; the sampler advances per-row counters on the device, so the host only polls the
+// number of live rows every few steps - no .item() style host round trip per token (common.py:155-161 has several).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+constexpr int D = 896, NH = 14, NKV = 2, HD = 64, DFF = 4864, VOUT = 6564, EOS = 6561;
+constexpr int QKV_N = NH * HD + 2 * NKV * HD;   // 1152
+constexpr float ROPE_THETA = 1.0e6f, RMS_EPS = 1e-6f;
+constexpr int SAMPLER_THREADS = 256, TOPK = 25, WIN = 10;
+
+struct LayerW {
+  float *ln1, *ln2;
+  ConvW qkv, o, gate_up, down;
+};
+}  // namespace
+
+struct LlmModel {
+  int num_layers = 24;
+  std::vector<LayerW> layers;
+  float* final_norm = nullptr;
+  float* text_emb = nullptr;     // [151936][896]
+  float* llm_emb = nullptr;      // [2][896]  sos, task_id
+  float* speech_emb = nullptr;   // [6564][896]
+  ConvW head;                    // llm_decoder 896 -> 6564
+  float inv_freq[HD / 2];
+  float* d_inv_freq = nullptr;
+};
+
+struct cvk_lm_session {
+  int max_batch = 0, max_ctx = 0, B = 0;
+  int kv_dtype = DT_F32;
+  void* kcache = nullptr;   // [layers][max_batch][NKV][max_ctx][HD]
+  void* vcache = nullptr;
+  int* ctx_len = nullptr;   // [max_batch] cache position of the token currently being fed
+  int* base_len = nullptr;  // [max_batch] prompt length L0
+  bool fresh = false;
+  int64_t graph_kernels = 0;
+  int* count = nullptr;     // [max_batch] tokens generated so far
+  int* done = nullptr;      // [max_batch]
+  int* live = nullptr;      // [1]
+  float* x = nullptr;       // [max_batch][896] input embedding of the current step (fp32 residual stream)
+  float* hidden = nullptr;  // [max_batch][896] final-normed hidden of the last position
+  float* logits = nullptr;  // [max_batch][VOUT]
+  void* xn = nullptr;       // act [max_batch][896]
+  void* qkv = nullptr;      // act [max_batch][1152]
+  void* att = nullptr;      // act [max_batch][896]
+  void* gu = nullptr;       // act [max_batch][2*4864]
+  void* ffa = nullptr;      // act [max_batch][4864]
+  cudaGraphExec_t graph = nullptr;
+  // arguments baked into the captured graph
+  const float* g_uniforms = nullptr;
+  const int32_t *g_min = nullptr, *g_max = nullptr;
+  int32_t *g_out_ids = nullptr, *g_out_count = nullptr, *g_done = nullptr;
+  int g_out_ld = 0, g_B = 0;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+float* copy_param(cvk_ctx* ctx, const std::string& name) {
+  const RawTensor& t = ctx->get_raw(name);
+  return dev_copy_f32(ctx, t.p, (size_t)t.numel());
+}
+
+ConvW concat_linear(cvk_ctx* ctx, const std::vector<std::string>& wn, const std::vector<std::string>& bn) {
+  int K = (int)ctx->get_raw(wn[0]).shape[1], N = 0;
+  for (auto& n : wn) N += (int)ctx->get_raw(n).shape[0];
+  ConvW w;
+  w.N = N; w.K = K;
+  w.w32 = (float*)ctx->dmalloc((size_t)N * K * sizeof(float));
+  size_t off = 0;
+  for (auto& n : wn) {
+    const RawTensor& t = ctx->get_raw(n);
+    CVK_CHECK_CUDA(cudaMemcpy(w.w32 + off, t.p, (size_t)t.numel() * sizeof(float), cudaMemcpyDeviceToDevice));
+    off += t.numel();
+  }
+  if (!bn.empty()) {
+    w.bias = (float*)ctx->dmalloc((size_t)N * sizeof(float));
+    size_t bo = 0;
+    for (auto& n : bn) {
+      const RawTensor& t = ctx->get_raw(n);
+      CVK_CHECK_CUDA(cudaMemcpy(w.bias + bo, t.p, (size_t)t.numel() * sizeof(float), cudaMemcpyDeviceToDevice));
+      bo += t.numel();
+    }
+  }
+  finish_convw(ctx, w);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// lm_input rows: [sos, embed(text...), task_id, speech_embedding(prompt...)] per sequence (llm.py:485-494)
+__global__ void build_input_kernel(const int32_t* __restrict__ text, const int* __restrict__ text_off, const int* __restrict__ text_len,
+                                   const int32_t* __restrict__ speech, const int* __restrict__ sp_off, const int* __restrict__ sp_len,
+                                   const float* __restrict__ text_emb, const float* __restrict__ llm_emb, const float* __restrict__ speech_emb,
+                                   const int* __restrict__ start, float* __restrict__ out) {
+  int b = blockIdx.y;
+  int nt = text_len[b], ns = sp_len[b];
+  int L = 1 + nt + 1 + ns;
+  for (int t = blockIdx.x; t < L; t += gridDim.x) {
+    const float* src;
+    if (t == 0) src = llm_emb;
+    else if (t <= nt) src = text_emb + (size_t)text[text_off[b] + t - 1] * D;
+    else if (t == nt + 1) src = llm_emb + D;
+    else src = speech_emb + (size_t)speech[sp_off[b] + t - nt - 2] * D;
+    float* dst = out + (size_t)(start[b] + t) * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = src[c];
+  }
+}
+
+// half-split RoPE (modeling_qwen2.py rotate_half) on the q and k parts of a fused qkv row, in place; position =
+// pos0[seq] + t.  Also appends k, v to the cache at that position.
+template <typename T>
+__global__ void rope_append_kernel(T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len,
+                                   const int* __restrict__ pos0, const float* __restrict__ inv_freq, T* __restrict__ kc, T* __restrict__ vc,
+                                   int max_ctx, int rows_are_seqs) {
+  int b = blockIdx.y;
+  int L = rows_are_seqs ? 1 : len[b];
+  int base = rows_are_seqs ? b : start[b];
+  for (int t = blockIdx.x; t < L; t += gridDim.x) {
+    int pos = (pos0 ? pos0[b] : 0) + t;
+    T* row = qkv + (size_t)(base + t) * ld;
+    // 16 heads to rotate (14 q + 2 k), 32 pairs each
+    for (int e = threadIdx.x; e < (NH + NKV) * (HD / 2); e += blockDim.x) {
+      int h = e / (HD / 2), i = e % (HD / 2);
+      float fr = (float)pos * inv_freq[i];
+      float c = cosf(fr), s = sinf(fr);
+      T* p = row + h * HD;
+      float x1 = to_f32(p[i]), x2 = to_f32(p[i + HD / 2]);
+      p[i] = from_f32<T>(x1 * c - x2 * s);
+      p[i + HD / 2] = from_f32<T>(x2 * c + x1 * s);
+    }
+    __syncthreads();
+    if (pos < max_ctx) {
+      for (int e = threadIdx.x; e < NKV * HD; e += blockDim.x) {
+        int h = e / HD, d = e % HD;
+        size_t ci = (((size_t)b * NKV + h) * max_ctx + pos) * HD + d;
+        kc[ci] = row[NH * HD + e];
+        vc[ci] = row[NH * HD + NKV * HD + e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// decode attention: one warp per (row, query head); keys 0..ctx_len[b] (the new token was appended already)
+template <typename T>
+__global__ void decode_attn_kernel(const T* __restrict__ qkv, int ld, const T* __restrict__ kc, const T* __restrict__ vc,
+                                   const int* __restrict__ ctx_len, int max_ctx, T* __restrict__ out, int ldo) {
+  int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kvh = h / (NH / NKV);
+  int L = min(ctx_len[b] + 1, max_ctx);
+  const T* q = qkv + (size_t)b * ld + h * HD;
+  float q0 = to_f32(q[lane]), q1 = to_f32(q[lane + 32]);
+  const T* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
+  const T* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < L; ++j) {
+    float s = q0 * to_f32(kb[(size_t)j * HD + lane]) + q1 * to_f32(kb[(size_t)j * HD + lane + 32]);
+    s = warp_sum(s) * 0.125f;
+    float mn = fmaxf(m, s);
+    float corr = expf(m - mn), p = expf(s - mn);
+    l = l * corr + p;
+    o0 = o0 * corr + p * to_f32(vb[(size_t)j * HD + lane]);
+    o1 = o1 * corr + p * to_f32(vb[(size_t)j * HD + lane + 32]);
+    m = mn;
+  }
+  T* op = out + (size_t)b * ldo + h * HD;
+  op[lane] = from_f32<T>(o0 / l);
+  op[lane + 32] = from_f32<T>(o1 / l);
+}
+
+// SwiGLU: silu(gate) * up; gu = [gate(4864) | up(4864)]
+template <typename T>
+__global__ void swiglu_kernel(const T* __restrict__ gu, int ld, int rows, T* __restrict__ out, int ldo) {
+  size_t total = (size_t)rows * DFF;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int r = i / DFF, c = i % DFF;
+    float g = to_f32(gu[(size_t)r * ld + c]), u = to_f32(gu[(size_t)r * ld + DFF + c]);
+    out[(size_t)r * ldo + c] = from_f32<T>(g / (1.f + expf(-g)) * u);
+  }
+}
+
+__global__ void gather_last_kernel(const float* __restrict__ x, const int* __restrict__ start, const int* __restrict__ len,
+                                   float* __restrict__ out) {
+  int b = blockIdx.x;
+  const float* src = x + (size_t)(start[b] + len[b] - 1) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) out[(size_t)b * D + c] = src[c];
+}
+
+// ---- block-wide helpers for the sampler (256 threads, contiguous segments of `per` entries per thread) ----
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < SAMPLER_THREADS / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+// float32 sum in the oracle's order (oracle/sampling.py hsum): per-thread contiguous segment left to right, then the
+// 256 partials left to right by one thread.
+__device__ __forceinline__ float block_hsum(float seg, float* part, float* total) {
+  __syncthreads();
+  part[threadIdx.x] = seg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < SAMPLER_THREADS; ++i) t += part[i];
+    *total = t;
+  }
+  __syncthreads();
+  return *total;
+}
+
+// Fused head epilogue: [optional log-softmax of logits] -> eos mask -> softmax -> nucleus (top-p 0.8 / top-k 25,
+// stable order) -> inverse-CDF draw on u1 -> repetition window test (win 10, tau_r 0.1) -> fallback draw on u2 from
+// the full distribution with the repeated id removed -> stop / length logic -> append id, gather next embedding.
+// Bit-for-bit restatement: oracle/sampling.py (ras_sample, nucleus_select, draw_index, softmax_f32).
+// standalone mode (cvk_ras_sample): `scores` already holds log-probs, history given explicitly, no state update.
+__global__ void __launch_bounds__(SAMPLER_THREADS)
+ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const float* __restrict__ uniforms /*[..][B][2]*/, int B,
+                   const int32_t* __restrict__ min_len, const int32_t* __restrict__ max_len, int32_t* __restrict__ out_ids, int out_ld,
+                   int32_t* __restrict__ out_count, int32_t* __restrict__ done, int* __restrict__ ctx_len, const int* __restrict__ base_len,
+                   int* __restrict__ live,
+                   const float* __restrict__ speech_emb, float* __restrict__ next_x,
+                   const int32_t* __restrict__ history, int hist_ld, const int32_t* __restrict__ hist_count,
+                   const int32_t* __restrict__ ignore_eos_in, int32_t* __restrict__ ids_out) {
+  extern __shared__ float sp[];            // V probabilities
+  __shared__ float red[SAMPLER_THREADS / 32];
+  __shared__ float part[SAMPLER_THREADS];
+  __shared__ float tot;
+  __shared__ float bv[SAMPLER_THREADS / 32];
+  __shared__ int bi[SAMPLER_THREADS / 32];
+  __shared__ float kept_p[TOPK];
+  __shared__ int kept_i[TOPK];
+  __shared__ int s_n, s_top, s_seg;
+  __shared__ float s_thr, s_cum;
+
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool standalone = ids_out != nullptr;
+  if (!standalone && done[b]) return;
+  float* x = scores + (size_t)b * V;
+  const int per = (V + SAMPLER_THREADS - 1) / SAMPLER_THREADS;
+  const int lo = tid * per, hi = min(lo + per, V);
+  const int cnt = standalone ? hist_count[b] : out_count[b];
+  const bool ignore_eos = standalone ? (ignore_eos_in[b] != 0) : (cnt < min_len[b]);
+  const float u1 = standalone ? uniforms[b * 2] : uniforms[((size_t)cnt * B + b) * 2];
+  const float u2 = standalone ? uniforms[b * 2 + 1] : uniforms[((size_t)cnt * B + b) * 2 + 1];
+
+  // (1) log-softmax of the head output (llm.py:542): (x - max) - log(hsum(exp(x - max)))
+  if (from_logits) {
+    float mx = -INFINITY;
+    for (int i = lo; i < hi; ++i) mx = fmaxf(mx, x[i]);
+    mx = block_max(mx, red);
+    float seg = 0.f;
+    for (int i = lo; i < hi; ++i) seg += expf(x[i] - mx);
+    float s = block_hsum(seg, part, &tot);
+    float ls = logf(s);
+    for (int i = lo; i < hi; ++i) x[i] = (x[i] - mx) - ls;
+    __syncthreads();
+  }
+  // (2) eos mask before min_len (llm.py:157-158: only index speech_token_size is masked)
+  if (ignore_eos && tid == 0) x[EOS] = -INFINITY;
+  __syncthreads();
+  // (3) softmax of the scores
+  float mx = -INFINITY;
+  for (int i = lo; i < hi; ++i) mx = fmaxf(mx, x[i]);
+  mx = block_max(mx, red);
+  {
+    float seg = 0.f;
+    for (int i = lo; i < hi; ++i) {
+      float e = x[i] == -INFINITY ? 0.f : expf(x[i] - mx);
+      sp[i] = e;
+      seg += e;
+    }
+    float s = block_hsum(seg, part, &tot);
+    for (int i = lo; i < hi; ++i) sp[i] = sp[i] / s;
+  }
+  if (tid == 0) { s_n = 0; s_cum = 0.f; }
+  __syncthreads();
+  // (4) nucleus: repeatedly take the largest remaining probability (ties -> lowest index == stable sort)
+  float lbest = -1.f;
+  int lidx = -1;
+  for (int i = lo; i < hi; ++i)
+    if (sp[i] > lbest) { lbest = sp[i]; lidx = i; }
+  for (int round = 0; round < TOPK; ++round) {
+    if (!(s_cum < 0.8f)) break;           // block-uniform (shared)
+    float v = lbest;
+    int ix = lidx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+      if (ov > v || (ov == v && oi >= 0 && (ix < 0 || oi < ix))) { v = ov; ix = oi; }
+    }
+    if ((tid & 31) == 0) { bv[tid >> 5] = v; bi[tid >> 5] = ix; }
+    __syncthreads();
+    if (tid == 0) {
+      float gv = bv[0];
+      int gi = bi[0];
+      for (int w = 1; w < SAMPLER_THREADS / 32; ++w)
+        if (bv[w] > gv || (bv[w] == gv && bi[w] >= 0 && (gi < 0 || bi[w] < gi))) { gv = bv[w]; gi = bi[w]; }
+      kept_p[s_n] = gv;
+      kept_i[s_n] = gi;
+      s_n = s_n + 1;
+      s_cum = s_cum + gv;
+      s_top = gi;
+    }
+    __syncthreads();
+    int taken = s_top;
+    if (taken >= lo && taken < hi) {      // owner removes it and rescans its segment
+      sp[taken] = -2.f;
+      lbest = -1.f;
+      lidx = -1;
+      for (int i = lo; i < hi; ++i)
+        if (sp[i] > lbest) { lbest = sp[i]; lidx = i; }
+    }
+    __syncthreads();
+  }
+  // (5) inverse-CDF draw over the kept (unnormalised) probabilities
+  if (tid == 0) {
+    int n = s_n;
+    float total = 0.f;
+    for (int i = 0; i < n; ++i) total += kept_p[i];
+    float thr = u1 * total, acc = 0.f;
+    int pick = -1, last = -1;
+    for (int i = 0; i < n; ++i) {
+      if (kept_p[i] > 0.f) last = i;
+      acc += kept_p[i];
+      if (pick < 0 && acc > thr && kept_p[i] > 0.f) pick = i;
+    }
+    if (pick < 0) pick = last;
+    int top = kept_i[pick];
+    // (6) repetition-aware fallback (common.py:140-143): count of top in the last WIN outputs >= WIN*tau_r = 1
+    int rep = 0;
+    const int32_t* hist = standalone ? history + (size_t)b * hist_ld : out_ids + (size_t)b * out_ld;
+    for (int i = max(0, cnt - WIN); i < cnt; ++i) rep += hist[i] == top;
+    s_top = top;
+    s_n = rep >= 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_n) {
+    int top = s_top;
+    if (tid == 0) x[top] = -INFINITY;
+    __syncthreads();
+    float m3 = -INFINITY;
+    for (int i = lo; i < hi; ++i) m3 = fmaxf(m3, x[i]);
+    m3 = block_max(m3, red);
+    float seg = 0.f;
+    for (int i = lo; i < hi; ++i) {
+      float e = x[i] == -INFINITY ? 0.f : expf(x[i] - m3);
+      sp[i] = e;
+      seg += e;
+    }
+    float s = block_hsum(seg, part, &tot);
+    seg = 0.f;
+    for (int i = lo; i < hi; ++i) {
+      sp[i] = sp[i] / s;
+      seg += sp[i];
+    }
+    // hierarchical inverse CDF (oracle draw_index): segment sums -> sequential prefix -> walk inside the segment
+    __syncthreads();
+    part[tid] = seg;
+    __syncthreads();
+    if (tid == 0) {
+      float pre = 0.f;
+      for (int i = 0; i < SAMPLER_THREADS; ++i) pre += part[i];
+      float thr = u2 * pre;
+      float acc = 0.f;
+      int segi = -1, lastseg = -1;
+      float segbase = 0.f;
+      for (int i = 0; i < SAMPLER_THREADS; ++i) {
+        if (part[i] > 0.f) {
+          lastseg = i;
+          if (acc + part[i] > thr) { segi = i; segbase = acc; break; }
+        }
+        acc += part[i];
+      }
+      // walk (the oracle keeps scanning later segments if rounding leaves the chosen one without a hit)
+      int pick = -1, last = -1;
+      if (segi < 0) segi = lastseg;
+      float a = segbase;
+      for (int sg = segi; sg < SAMPLER_THREADS && pick < 0; ++sg) {
+        if (sg > segi) {
+          if (!(part[sg] > 0.f)) continue;
+          // prefix[sg+1] > thr holds trivially once an earlier segment already exceeded it
+        }
+        int l2 = sg * per, h2 = min(l2 + per, V);
+        for (int i = l2; i < h2; ++i) {
+          if (sp[i] > 0.f) last = i;
+          a += sp[i];
+          if (a > thr && sp[i] > 0.f) { pick = i; break; }
+        }
+      }
+      if (pick < 0) pick = last;
+      s_top = pick;
+    }
+    __syncthreads();
+  }
+  const int top = s_top;
+  if (standalone) {
+    if (tid == 0) ids_out[b] = top;
+    return;
+  }
+  // (7) stop / length logic (llm.py:544-549)
+  const bool stop = top >= EOS && top <= EOS + 2;
+  if (!stop) {
+    for (int c = tid; c < D; c += SAMPLER_THREADS) next_x[(size_t)b * D + c] = speech_emb[(size_t)top * D + c];
+  }
+  if (tid == 0) {
+    bool fin = stop;
+    if (!stop) {
+      out_ids[(size_t)b * out_ld + cnt] = top;
+      out_count[b] = cnt + 1;
+      ctx_len[b] = base_len[b] + cnt;   // cache position of the token that is fed next
+      if (cnt + 1 >= max_len[b]) fin = true;
+    }
+    if (fin) {
+      done[b] = 1;
+      atomicSub(live, 1);
+    }
+  }
+}
+
+__global__ void logsoftmax_rows_kernel(float* __restrict__ x, int V) {
+  __shared__ float red[SAMPLER_THREADS / 32];
+  __shared__ float part[SAMPLER_THREADS];
+  __shared__ float tot;
+  float* row = x + (size_t)blockIdx.x * V;
+  const int per = (V + SAMPLER_THREADS - 1) / SAMPLER_THREADS;
+  const int lo = threadIdx.x * per, hi = min(lo + per, V);
+  float mx = -INFINITY;
+  for (int i = lo; i < hi; ++i) mx = fmaxf(mx, row[i]);
+  mx = block_max(mx, red);
+  float seg = 0.f;
+  for (int i = lo; i < hi; ++i) seg += expf(row[i] - mx);
+  float s = block_hsum(seg, part, &tot);
+  float ls = logf(s);
+  for (int i = lo; i < hi; ++i) row[i] = (row[i] - mx) - ls;
+}
+
+__global__ void init_state_kernel(const int* __restrict__ len, int B, int* ctx_len, int* base_len, int* live) {
+  int b = threadIdx.x;
+  if (b < B) {
+    ctx_len[b] = len[b];
+    base_len[b] = len[b];
+  }
+  if (b == 0) *live = B;
+}
+
+int* upload(cvk_ctx* ctx, const std::vector<int>& v, cudaStream_t st) {
+  int* d = (int*)ctx->arena.alloc(sizeof(int) * (v.size() ? v.size() : 1));
+  if (!v.empty()) CVK_CHECK_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, st));
+  return d;
+}
+std::vector<int> prefix(const int* lens, int B) {
+  std::vector<int> off(B);
+  int a = 0;
+  for (int b = 0; b < B; ++b) { off[b] = a; a += lens[b]; }
+  return off;
+}
+
+// one transformer layer on `rows` rows.  prefill: seqs geometry + causal attention over the qkv buffer;
+// decode: rows == sequences, attention against the cache.
+void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, const Mat& x, const Mat& xn, const Mat& qkv, const Mat& att,
+                   const Mat& gu, const Mat& ffa, const Seqs* s, cvk_lm_session* sess, bool decode) {
+  const LayerW& w = m->layers[li];
+  const int rows = x.rows;
+  rmsnorm(ctx, st, x, w.ln1, RMS_EPS, xn);
+  {
+    Epilogue e;
+    e.out = qkv;
+    conv_gemm(ctx, st, xn, w.qkv, e);
+  }
+  size_t es = qkv.dtype == DT_F32 ? 4 : 2;
+  void* kc = sess ? (char*)sess->kcache + (size_t)li * sess->max_batch * NKV * sess->max_ctx * HD * es : nullptr;
+  void* vc = sess ? (char*)sess->vcache + (size_t)li * sess->max_batch * NKV * sess->max_ctx * HD * es : nullptr;
+  if (decode) {
+    if (qkv.dtype == DT_F32) {
+      rope_append_kernel<float><<<dim3(1, rows), 128, 0, st>>>(qkv.f32(), qkv.ld, nullptr, nullptr, sess->ctx_len, m->d_inv_freq, (float*)kc,
+                                                               (float*)vc, sess->max_ctx, 1);
+      decode_attn_kernel<float><<<rows, NH * 32, 0, st>>>(qkv.f32(), qkv.ld, (const float*)kc, (const float*)vc, sess->ctx_len, sess->max_ctx,
+                                                          att.f32(), att.ld);
+    } else {
+      rope_append_kernel<bf16><<<dim3(1, rows), 128, 0, st>>>(qkv.b16(), qkv.ld, nullptr, nullptr, sess->ctx_len, m->d_inv_freq, (bf16*)kc,
+                                                              (bf16*)vc, sess->max_ctx, 1);
+      decode_attn_kernel<bf16><<<rows, NH * 32, 0, st>>>(qkv.b16(), qkv.ld, (const bf16*)kc, (const bf16*)vc, sess->ctx_len, sess->max_ctx,
+                                                         att.b16(), att.ld);
+    }
+    ctx->launches += 2;
+    CVK_LAUNCH_CHECK();
+  } else {
+    int bx = s->max_len < 256 ? s->max_len : 256;
+    // without a session (teacher-forced parity path) the cache pointers are null: append is skipped via max_ctx = 0
+    int mc = sess ? sess->max_ctx : 0;
+    if (qkv.dtype == DT_F32)
+      rope_append_kernel<float><<<dim3(bx, s->B), 128, 0, st>>>(qkv.f32(), qkv.ld, s->d_start, s->d_len, nullptr, m->d_inv_freq, (float*)kc,
+                                                                (float*)vc, mc, 0);
+    else
+      rope_append_kernel<bf16><<<dim3(bx, s->B), 128, 0, st>>>(qkv.b16(), qkv.ld, s->d_start, s->d_len, nullptr, m->d_inv_freq, (bf16*)kc,
+                                                               (bf16*)vc, mc, 0);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    // causal == block-causal with chunk 1; 7 query heads per kv head
+    attention_fwd(ctx, st, qkv.slice(0, NH * HD), qkv.slice(NH * HD, NKV * HD), qkv.slice(NH * HD + NKV * HD, NKV * HD), *s, NH, 1, 0.125f,
+                  att, NH / NKV);
+  }
+  {
+    Epilogue e;
+    e.resid = x;
+    e.out = x;
+    conv_gemm(ctx, st, att, w.o, e);
+  }
+  rmsnorm(ctx, st, x, w.ln2, RMS_EPS, xn);
+  {
+    Epilogue e;
+    e.out = gu;
+    conv_gemm(ctx, st, xn, w.gate_up, e);
+  }
+  {
+    size_t total = (size_t)rows * DFF;
+    int g = (int)((total + 255) / 256);
+    if (g > 148 * 8) g = 148 * 8;
+    if (gu.dtype == DT_F32) swiglu_kernel<float><<<g, 256, 0, st>>>(gu.f32(), gu.ld, rows, ffa.f32(), ffa.ld);
+    else swiglu_kernel<bf16><<<g, 256, 0, st>>>(gu.b16(), gu.ld, rows, ffa.b16(), ffa.ld);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  {
+    Epilogue e;
+    e.resid = x;
+    e.out = x;
+    conv_gemm(ctx, st, ffa, w.down, e);
+  }
+}
+
+void head_logits(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, const Mat& hidden_f32, const Mat& xn_act, const Mat& logits) {
+  rmsnorm(ctx, st, hidden_f32, m->final_norm, RMS_EPS, xn_act);
+  Epilogue e;
+  e.out = logits;
+  conv_gemm(ctx, st, xn_act, m->head, e);
+}
+
+}  // namespace
+
+// ================================================================================================ build / session
+void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
+  LlmModel* m = new LlmModel();
+  if (ncfg >= 1) m->num_layers = cfg[0];
+  const std::string P = "llm.";
+  m->text_emb = copy_param(ctx, P + "llm.model.model.embed_tokens.weight");
+  m->llm_emb = copy_param(ctx, P + "llm_embedding.weight");
+  m->speech_emb = copy_param(ctx, P + "speech_embedding.weight");
+  m->head = make_linear(ctx, P + "llm_decoder.weight", P + "llm_decoder.bias");
+  m->final_norm = copy_param(ctx, P + "llm.model.model.norm.weight");
+  for (int i = 0; i < m->num_layers; ++i) {
+    std::string L = P + "llm.model.model.layers." + std::to_string(i);
+    LayerW w;
+    w.ln1 = copy_param(ctx, L + ".input_layernorm.weight");
+    w.ln2 = copy_param(ctx, L + ".post_attention_layernorm.weight");
+    w.qkv = concat_linear(ctx, {L + ".self_attn.q_proj.weight", L + ".self_attn.k_proj.weight", L + ".self_attn.v_proj.weight"},
+                          {L + ".self_attn.q_proj.bias", L + ".self_attn.k_proj.bias", L + ".self_attn.v_proj.bias"});
+    w.o = make_linear(ctx, L + ".self_attn.o_proj.weight", "");
+    w.gate_up = concat_linear(ctx, {L + ".mlp.gate_proj.weight", L + ".mlp.up_proj.weight"}, {});
+    w.down = make_linear(ctx, L + ".mlp.down_proj.weight", "");
+    m->layers.push_back(w);
+  }
+  for (int i = 0; i < HD / 2; ++i) m->inv_freq[i] = 1.0f / powf(ROPE_THETA, (float)(2 * i) / (float)HD);
+  m->d_inv_freq = (float*)ctx->dmalloc(sizeof(m->inv_freq));
+  CVK_CHECK_CUDA(cudaMemcpy(m->d_inv_freq, m->inv_freq, sizeof(m->inv_freq), cudaMemcpyHostToDevice));
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  ctx->llm = m;
+}
+
+cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context) {
+  CVK_REQUIRE(ctx->llm, "llm stage not finalised");
+  cvk_lm_session* s = new cvk_lm_session();
+  s->max_batch = max_batch;
+  s->max_ctx = max_context;
+  s->kv_dtype = ctx->act_dtype;
+  size_t es = s->kv_dtype == DT_F32 ? 4 : 2;
+  auto alloc = [&](size_t bytes) {
+    void* p = nullptr;
+    CVK_CHECK_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    CVK_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    s->owned.push_back(p);
+    return p;
+  };
+  size_t cache = (size_t)ctx->llm->num_layers * max_batch * NKV * max_context * HD * es;
+  s->kcache = alloc(cache);
+  s->vcache = alloc(cache);
+  s->ctx_len = (int*)alloc(sizeof(int) * max_batch);
+  s->base_len = (int*)alloc(sizeof(int) * max_batch);
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT * (int)sizeof(float)));
+  s->count = (int*)alloc(sizeof(int) * max_batch);
+  s->done = (int*)alloc(sizeof(int) * max_batch);
+  s->live = (int*)alloc(sizeof(int));
+  s->x = (float*)alloc(sizeof(float) * max_batch * D);
+  s->hidden = (float*)alloc(sizeof(float) * max_batch * D);
+  s->logits = (float*)alloc(sizeof(float) * (size_t)max_batch * VOUT);
+  s->xn = alloc(es * max_batch * D);
+  s->qkv = alloc(es * max_batch * QKV_N);
+  s->att = alloc(es * max_batch * D);
+  s->gu = alloc(es * (size_t)max_batch * 2 * DFF);
+  s->ffa = alloc(es * (size_t)max_batch * DFF);
+  return s;
+}
+
+void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s) {
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (s->graph) cudaGraphExecDestroy(s->graph);
+  for (void* p : s->owned) cudaFree(p);
+  delete s;
+}
+
+// ================================================================================================ prefill
+// full causal forward over packed rows; if sess != null also fills the KV cache
+static Mat forward_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& x, cvk_lm_session* sess) {
+  const LlmModel* m = ctx->llm;
+  const int adt = ctx->act_dtype;
+  Mat xn = arena_mat(ctx, adt, s.R, D), qkv = arena_mat(ctx, adt, s.R, QKV_N), att = arena_mat(ctx, adt, s.R, D),
+      gu = arena_mat(ctx, adt, s.R, 2 * DFF), ffa = arena_mat(ctx, adt, s.R, DFF);
+  zero_mat(ctx, st, att);
+  for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, &s, sess, false);
+  return x;
+}
+
+void llm_prefill(cvk_ctx* ctx, cvk_lm_session* sess, const int32_t* text, const int* text_lens, const int32_t* speech,
+                 const int* speech_lens, int B, cudaStream_t st) {
+  const LlmModel* m = ctx->llm;
+  CVK_REQUIRE(m, "llm stage not finalised");
+  CVK_REQUIRE(B <= sess->max_batch, "batch larger than the session");
+  ctx->arena.reset();
+  std::vector<int> lens(B);
+  for (int b = 0; b < B; ++b) {
+    lens[b] = 1 + text_lens[b] + 1 + speech_lens[b];
+    CVK_REQUIRE(lens[b] < sess->max_ctx, "prompt longer than the session context");
+  }
+  Seqs s = make_seqs(ctx, lens.data(), B, 0, 1, 0, st);
+  Mat x = arena_mat(ctx, DT_F32, s.R, D, D);
+  zero_mat(ctx, st, x);
+  int* toff = upload(ctx, prefix(text_lens, B), st);
+  int* tlen = upload(ctx, std::vector<int>(text_lens, text_lens + B), st);
+  int* soff = upload(ctx, prefix(speech_lens, B), st);
+  int* slen = upload(ctx, std::vector<int>(speech_lens, speech_lens + B), st);
+  int bx = s.max_len < 512 ? s.max_len : 512;
+  build_input_kernel<<<dim3(bx, B), 128, 0, st>>>(text, toff, tlen, speech, soff, slen, m->text_emb, m->llm_emb, m->speech_emb, s.d_start, x.f32());
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  if (sess->graph) {   // a new batch invalidates the captured decode graph (row count / output pointers may change)
+    cudaGraphExecDestroy(sess->graph);
+    sess->graph = nullptr;
+  }
+  forward_packed(ctx, st, s, x, sess);
+  // the first decode step consumes the hidden state of the last prompt position: keep its pre-norm residual in x
+  gather_last_kernel<<<B, 128, 0, st>>>(x.f32(), s.d_start, s.d_len, sess->hidden);
+  CVK_REQUIRE(sess->max_batch <= 1024, "max_batch > 1024");
+  init_state_kernel<<<1, sess->max_batch < 32 ? 32 : round_up(sess->max_batch, 32), 0, st>>>(s.d_len, B, sess->ctx_len, sess->base_len, sess->live);
+  sess->fresh = true;
+  ctx->launches += 2;
+  CVK_LAUNCH_CHECK();
+  sess->B = B;
+}
+
+// ================================================================================================ decode
+// One device step = head + sampler on the current hidden state (emits token k, gathers its embedding into x), then the
+// 24 layers on x (position base_len + k) leaving the next hidden state.  The reference's loop (llm.py:538-549) is the
+// same sequence rotated by half a step: its first iteration is the prefill.
+static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
+  const LlmModel* m = ctx->llm;
+  const int adt = s->kv_dtype;
+  const int B = s->g_B;
+  Mat hid(s->hidden, DT_F32, B, D, D), x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N),
+      att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, VOUT, VOUT);
+  head_logits(ctx, st, m, hid, xn, logits);
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
+                                                                       s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
+                                                                       m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
+  CVK_CHECK_CUDA(cudaMemcpyAsync(s->hidden, s->x, sizeof(float) * (size_t)B * D, cudaMemcpyDeviceToDevice, st));
+}
+
+void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
+                int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, cudaStream_t st) {
+  const LlmModel* m = ctx->llm;
+  CVK_REQUIRE(m && s->B > 0, "cvk_lm_prefill must run before cvk_lm_decode");
+  const int B = s->B;
+  if (s->fresh) {
+    CVK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * B, st));
+    CVK_CHECK_CUDA(cudaMemsetAsync(done, 0, sizeof(int32_t) * B, st));
+    s->fresh = false;
+  }
+  bool same = s->g_out_count == out_count && s->g_done == done && s->g_out_ids == out_ids && s->g_uniforms == uniforms &&
+              s->g_min == min_len && s->g_max == max_len && s->g_out_ld == out_ld && s->g_B == B;
+  if (!same) {
+    if (s->graph) {
+      cudaGraphExecDestroy(s->graph);
+      s->graph = nullptr;
+    }
+    s->g_out_count = out_count; s->g_done = done; s->g_out_ids = out_ids; s->g_uniforms = uniforms; s->g_min = min_len; s->g_max = max_len;
+    s->g_out_ld = out_ld; s->g_B = B;
+  }
+  const bool can_graph = ctx->use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;   // capture is illegal on the default streams
+  if (can_graph && !s->graph) {
+    int64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CVK_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      decode_step(ctx, st, s);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CVK_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
+    CVK_CHECK_CUDA(cudaGraphInstantiate(&s->graph, graph, 0));
+    cudaGraphDestroy(graph);
+    s->graph_kernels = ctx->launches - before;
+    ctx->launches = before;
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    if (can_graph && s->graph) {
+      CVK_CHECK_CUDA(cudaGraphLaunch(s->graph, st));
+      ctx->launches += s->graph_kernels;
+    } else {
+      decode_step(ctx, st, s);
+    }
+  }
+  if (live_host) {
+    CVK_CHECK_CUDA(cudaMemcpyAsync(live_host, s->live, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CVK_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+// teacher-forced log-probs for every position (parity tests)
+void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, cudaStream_t st) {
+  const LlmModel* m = ctx->llm;
+  CVK_REQUIRE(m, "llm stage not finalised");
+  ctx->arena.reset();
+  Seqs s = make_seqs(ctx, lens, B, 0, 1, 0, st);
+  Mat x = arena_mat(ctx, DT_F32, s.R, D, D);
+  zero_mat(ctx, st, x);
+  pack_rows(ctx, st, embeds, D, s, x);
+  forward_packed(ctx, st, s, x, nullptr);
+  Mat xn = arena_mat(ctx, ctx->act_dtype, s.R, D), logits = arena_mat(ctx, DT_F32, s.R, VOUT, VOUT);
+  head_logits(ctx, st, m, x, xn, logits);
+  logsoftmax_rows_kernel<<<s.R, SAMPLER_THREADS, 0, st>>>(logits.f32(), VOUT);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  unpack_rows(ctx, st, logits, s, 0, logp, VOUT);
+}
+
+void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
+                    const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st) {
+  CVK_REQUIRE(V > EOS + 2 && V * sizeof(float) <= 200 * 1024, "vocabulary size out of range");
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (int)sizeof(float)));
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, V * sizeof(float), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                                                    nullptr, nullptr, nullptr, nullptr, history, hist_ld, hist_count, ignore_eos,
+                                                                    out_ids);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}

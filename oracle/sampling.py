@@ -53,16 +53,36 @@ def draw_index(w, u):
     return last
 
 
+def hsum(w):
+    """float32 sum in the kernel's order: SEG contiguous segments summed left to right, then the SEG partial
+    sums left to right."""
+    w = np.asarray(w, dtype=np.float32)
+    n = w.shape[0]
+    per = (n + SEG - 1) // SEG
+    tot = np.float32(0)
+    for s in range(SEG):
+        acc = np.float32(0)
+        for i in range(s * per, min((s + 1) * per, n)):
+            acc = np.float32(acc + w[i])
+        tot = np.float32(tot + acc)
+    return tot
+
+
 def softmax_f32(x):
-    """float32 softmax with -inf support: exp(x - max) / sum (sequential float32 sum)."""
+    """float32 softmax with -inf support: exp(x - max) / hsum."""
     x = np.asarray(x, dtype=np.float32)
     m = np.max(x)
     e = np.exp((x - m).astype(np.float32)).astype(np.float32)
     e[np.isneginf(x)] = 0
-    s = np.float32(0)
-    for v in e:
-        s = np.float32(s + v)
-    return (e / s).astype(np.float32)
+    return (e / hsum(e)).astype(np.float32)
+
+
+def log_softmax_f32(x):
+    """float32 log-softmax the way the decode kernel forms it: (x - max) - log(hsum(exp(x - max)))."""
+    x = np.asarray(x, dtype=np.float32)
+    m = np.max(x)
+    d = (x - m).astype(np.float32)
+    return (d - np.log(hsum(np.exp(d).astype(np.float32))).astype(np.float32)).astype(np.float32)
 
 
 def nucleus_select(prob):

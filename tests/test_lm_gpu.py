@@ -1,0 +1,148 @@
+"""GPU: speech-token LM through the C ABI - sampler bit-exactness, teacher-forced log-probs, KV-cached decode loop.
+
+The sampler is integer bookkeeping over float32 probabilities: given identical log-probs and identical uniforms the
+ids must be IDENTICAL to the reference's (tests/golden/sampling.npz, produced by cosyvoice/utils/common.py:138-167
+with Tensor.multinomial fed from the same uniforms).  The decode loop in fp32 mode reproduces the reference's ids
+token for token; in bf16 mode the log-probs are held to a stated bound instead (free-running ids legitimately
+diverge once two candidates are within the bf16 noise)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import ctx, maxdiff
+from oracle import cases, lm, sampling
+
+pytestmark = pytest.mark.gpu
+_state = {}
+
+
+def model(precision, NL):
+    c = ctx(precision)
+    if _state.get(precision) != NL:
+        sd = lm.synth_state_dict(NL)
+        c.load_state_dict("llm", sd, cfg=[NL])
+        _state[precision] = NL
+        _state[(precision, "sd")] = sd
+    return c, _state[(precision, "sd")]
+
+
+def test_sampler_matches_reference_ids(golden):
+    g = golden("sampling")
+    logp, hist, U, ignore = cases.sampling_case()
+    c = ctx("fp32")
+    cnt = torch.full((logp.shape[0],), hist.shape[1], dtype=torch.int32)
+    ids = c.ras_sample(logp, hist, cnt, U, ignore.int())
+    assert ids.cpu().tolist() == g["ids"].tolist()
+
+
+def test_sampler_edge_cases():
+    c = ctx("fp32")
+    V = 6564
+    lp = torch.full((4, V), -float("inf"))
+    lp[:, 7] = 0.0
+    lp[:, 9] = -20.0
+    lp[2:, :] = -30.0
+    lp[2:, 6561] = 0.0
+    lp[2:, 5] = -1.0
+    hist = torch.zeros(4, 12, dtype=torch.int32)
+    hist[1, 0] = 7
+    cnt = torch.tensor([0, 1, 0, 0], dtype=torch.int32)
+    U = torch.tensor([[0.3, 0.3], [0.3, 0.3], [0.0, 0.0], [0.0, 0.0]])
+    ign = torch.tensor([0, 0, 1, 0], dtype=torch.int32)
+    ids = c.ras_sample(lp, hist, cnt, U, ign).cpu().tolist()
+    exp = [sampling.ras_sample(lp[i].numpy(), hist[i, :cnt[i]].tolist(), float(U[i, 0]), float(U[i, 1]), bool(ign[i])) for i in range(4)]
+    assert ids == exp == [7, 9, 5, 6561]
+
+
+@pytest.mark.parametrize("precision,NL", [("fp32", 2), ("bf16", 2), ("fp32", 24), ("bf16", 24)])
+def test_teacher_forced_logp(precision, NL, golden):
+    g = golden(f"lm_l{NL}")
+    c, sd = model(precision, NL)
+    text, ptext, ptok, U = cases.lm_case()
+    lm_in = lm.build_lm_input(sd, text, ptext, ptok)
+    ids = torch.from_numpy(g["ids"][:16]).long()
+    full = torch.cat([lm_in, torch.nn.functional.embedding(ids[None], sd["speech_embedding.weight"])], 1)[0]
+    logp = c.lm_forward_logp(full, [full.shape[0]])
+    ref_rows = torch.from_numpy(g["logp_rows"])                      # reference HF model, last 4 positions, every 41st column
+    d = maxdiff(logp[-4:, ::41], ref_rows)
+    assert d < (2e-3 if precision == "fp32" else 0.25), d
+    # ragged batch of two copies with different lengths == single
+    two = c.lm_forward_logp(torch.cat([full, full[:11]], 0), [full.shape[0], 11])
+    assert maxdiff(two[:full.shape[0]], logp) < 1e-4
+    assert maxdiff(two[full.shape[0]:], logp[:11]) < (1e-3 if precision == "fp32" else 0.1)
+
+
+def _decode(c, text, ptext, ptok, U, max_ratio=20.0, min_ratio=2.0, steps_per_call=16):
+    """batch of rows -> list of id lists.  text/ptext/ptok: lists of [1,n] tensors; U [max_len, B, 2]"""
+    B = len(text)
+    tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(text, ptext)]
+    sl = [int(s.shape[1]) for s in ptok]
+    tt = torch.cat([torch.cat([p, t], 1).reshape(-1) for t, p in zip(text, ptext)])
+    ss = torch.cat([s.reshape(-1) for s in ptok])
+    min_len = torch.tensor([int(t.shape[1] * min_ratio) for t in text], dtype=torch.int32, device=c.device)
+    max_len = torch.tensor([int(t.shape[1] * max_ratio) for t in text], dtype=torch.int32, device=c.device)
+    mx = int(max_len.max())
+    sess = c.lm_session(B, max(tl) + max(sl) + 2 + mx + 8)
+    out_ids = torch.zeros(B, mx + 1, dtype=torch.int32, device=c.device)
+    out_count = torch.zeros(B, dtype=torch.int32, device=c.device)
+    done = torch.zeros(B, dtype=torch.int32, device=c.device)
+    Ud = U.to(c.device).float().contiguous()
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        c.lm_prefill(sess, tt, tl, ss, sl)
+        n = 0
+        while True:
+            live = c.lm_decode(sess, steps_per_call, Ud, min_len, max_len, out_ids, out_count, done)
+            n += steps_per_call
+            if live == 0 or n > mx + steps_per_call:
+                break
+    torch.cuda.synchronize()
+    c.lm_session_destroy(sess)
+    cnt = out_count.cpu().tolist()
+    return [out_ids[b, :cnt[b]].cpu().tolist() for b in range(B)]
+
+
+@pytest.mark.parametrize("NL", [2, 24])
+def test_decode_ids_match_reference_fp32(NL, golden):
+    g = golden(f"lm_l{NL}")
+    c, sd = model("fp32", NL)
+    text, ptext, ptok, U = cases.lm_case()
+    ids = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    assert ids == g["ids"].tolist()
+
+
+def test_decode_graph_equals_eager():
+    c, sd = model("fp32", 2)
+    text, ptext, ptok, U = cases.lm_case()
+    a = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    c.set_option("use_graph", 0)
+    try:
+        b = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    finally:
+        c.set_option("use_graph", 1)
+    assert a == b
+
+
+def test_decode_ragged_batch_fp32():
+    """three rows with different prompts/lengths decode together == the oracle one row at a time"""
+    c, sd = model("fp32", 2)
+    g = torch.Generator().manual_seed(21)
+    rows = []
+    for nt, npt, nps in ((5, 3, 7), (9, 4, 12), (3, 2, 0)):
+        rows.append((torch.randint(0, 151643, (1, nt), generator=g, dtype=torch.int32), torch.randint(0, 151643, (1, npt), generator=g, dtype=torch.int32),
+                     torch.randint(0, 6561, (1, nps), generator=g, dtype=torch.int32)))
+    U = torch.rand(200, 3, 2, generator=g)
+    got = _decode(c, [r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], U, max_ratio=6.0)
+    for b, (t, p, s) in enumerate(rows):
+        exp = lm.inference(sd, t, p, s, U[:, b], 2, max_ratio=6.0)
+        assert got[b] == exp, b
+
+
+def test_decode_bf16_runs_and_first_token_matches(golden):
+    g = golden("lm_l24")
+    c, sd = model("bf16", 24)
+    text, ptext, ptok, U = cases.lm_case()
+    ids = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    assert len(ids) == len(g["ids"]) and all(0 <= i < 6561 for i in ids)
+    assert ids[0] == int(g["ids"][0])
