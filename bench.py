@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the CosyVoice2-0.5B hot path (LM decode -> CFM flow -> HiFT vocoder) on B200.
+
+Metric (BASELINE.json): audio-sec/s, CosyVoice2-0.5B zero-shot batch-32, NFE=10 - synthetic data (random-init weights of
+the reference architecture, random token / prompt tensors of the Z10 shape).  One *step* = one pass of
+the whole pipeline over one batch of 32 ragged utterances per GPU.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3            # ours (default)
+  python bench.py --impl reference --steps 1 --warmup 0    # the reference's algorithm on the host CPU cores
+  torchrun --nnodes=1 --nproc-per-node N bench.py --gpus N ...   (N > 1: one rank per GPU, weak scaling)
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = device-resident throughput, e2e = the same
+metric through the public API with host buffers (H2D of the request tensors, D2H of the waveforms inside the timed
+region), roofline = the dominant kernel family against the measured peaks, cpu_baseline = the oracle port on CPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+TOKEN_RATIO = 5.0          # min_token_text_ratio == max_token_text_ratio => exactly 5 * n_text speech tokens
+METRIC = "audio-sec/s, CosyVoice2-0.5B zero-shot batch-32, NFE=10"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ================================================================================================ reference arm (CPU)
+def cpu_reference_sample(full=True, threads=None):
+    """The reference's algorithm (oracle port, CPU fp32 torch) on ONE Z10 utterance of the batch-32 workload: LM decode of
+    5*n_text tokens with KV cache + RAS sampling, flow (NFE 10, CFG), HiFT.  Returns (audio_seconds, wall_seconds, info)."""
+    import torch
+    from oracle import flow as oflow, hift as ohift, lm as olm, weights as oweights
+    from cosyvoice_b200 import synth
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    NL = 24 if full else 2
+    fcfg = oflow.FlowCfg() if full else oflow.FlowCfg(2, 1, 2, 2)
+    lsd = olm.synth_state_dict(NL)
+    lsd["llm_decoder.bias"][6561:6564] = -1e4
+    fsd = oweights.synth_state_dict(oflow.param_shapes(fcfg), 1986, oflow.SYNTH_GAINS)
+    hsd = oweights.synth_state_dict(ohift.param_shapes(), 1986, ohift.SYNTH_GAINS)
+    utt = synth.z10_utterance(0, 50)
+    g = torch.Generator().manual_seed(0)
+    n_tok = int(50 * TOKEN_RATIO)
+    U = torch.rand(n_tok + 1, 2, generator=g)
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        ids = olm.inference(lsd, utt["text"], utt["prompt_text"], utt["llm_prompt_speech_token"], U, NL, min_ratio=TOKEN_RATIO, max_ratio=TOKEN_RATIO)
+        t1 = time.perf_counter()
+        mel = oflow.inference(fsd, torch.tensor([ids], dtype=torch.int32), utt["flow_prompt_speech_token"], utt["prompt_speech_feat"],
+                              utt["flow_embedding"], fcfg)
+        t2 = time.perf_counter()
+        noise = torch.randn(1, mel.shape[2] * 480, 9, generator=g)
+        wav, _ = ohift.inference(hsd, mel, noise)
+        t3 = time.perf_counter()
+    audio_s = wav.shape[1] / 24000.0
+    info = dict(tokens=len(ids), lm_s=t1 - t0, flow_s=t2 - t1, hift_s=t3 - t2)
+    return audio_s, t3 - t0, info
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_sample(full=not args.small, threads=cores)
+    info = {}
+    for _ in range(max(args.steps, 1)):
+        a, w, info = cpu_reference_sample(full=not args.small, threads=cores)
+        vals.append((a, w))
+    audio = sum(a for a, _ in vals)
+    wall = sum(w for _, w in vals)
+    v = audio / wall
+    sample = "1 of the 32 Z10 utterances (50 text tokens -> 250 speech tokens, 10 s of audio) per step: " \
+             f"LM {info['lm_s']:.1f}s + flow {info['flow_s']:.1f}s + HiFT {info['hift_s']:.1f}s"
+    line = {"metric": METRIC, "value": v, "unit": "audio-sec/s", "n_gpus": 0, "steps": max(args.steps, 1), "warmup": args.warmup,
+            "ms_per_step": 1000 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "CosyVoice2-0.5B zero-shot batch-32 NFE=10 (bounded sample: one utterance per step)",
+                       "reference_impl": "oracle port of cosyvoice/{llm,flow,hifigan} (torch CPU fp32; /root/reference is absent on the GPU box)"},
+            "cpu_baseline": {"value": v, "unit": "audio-sec/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ================================================================================================ our arm (GPU)
+def run_ours(args):
+    import torch
+    rank, world, local = dist_env()
+    n_gpus = args.gpus
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+    from cosyvoice_b200 import synth
+    from cosyvoice_b200.model import B200CosyVoice2Model
+    from cosyvoice_b200.parallel import broadcast_state_dicts, gather_waveforms
+    dev = torch.device("cuda", local)
+    full = not args.small
+    nl, fcfg = (24, (6, 4, 12, 4)) if full else (2, (2, 1, 2, 2))
+    # weights: rank 0 draws them, NCCL broadcast to the other ranks (the only weight traffic of the job)
+    sds = synth.cosyvoice2_state_dicts(dev, 1986, nl, fcfg) if rank == 0 else None
+    sds = broadcast_state_dicts(sds, dev, synth.llm_shapes(nl), synth.flow_shapes(*fcfg), synth.hift_shapes(), dist)
+    model = B200CosyVoice2Model(precision=args.precision, device=local, workspace_gb=args.workspace_gb)
+    model.load_state_dicts(*sds)
+    del sds
+    torch.cuda.empty_cache()
+    model.min_token_text_ratio = model.max_token_text_ratio = TOKEN_RATIO
+    batch = args.batch
+    inputs = synth.batch32_zero_shot(batch, base=rank * batch)              # weak scaling: every rank its own 32 requests
+    h2d = sum(sum(v.numel() * v.element_size() for v in i.values()) for i in inputs)
+
+    def to_dev(i):
+        return {k: v.to(dev) for k, v in i.items()}
+    inputs_dev = [to_dev(i) for i in inputs]
+    pinned = [{k: v.pin_memory() for k, v in i.items()} for i in inputs]
+
+    def step_device():
+        return model.tts_batch(inputs_dev, to_host=False, return_stats=True)
+
+    def step_e2e():
+        return model.tts_batch(pinned, to_host=True, return_stats=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    # ---- timed region 1: device-resident inputs, waveforms left in HBM
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = model.ctx.launch_count()
+    model.ctx.profile(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(model.stream)
+    audio_s, stats = 0.0, None
+    for _ in range(args.steps):
+        wavs, stats = step_device()
+        audio_s += sum(w.shape[-1] for w in wavs) / 24000.0
+    e1.record(model.stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    wall_ms = 1000 * (time.perf_counter() - t0)
+    launches = model.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = [model.ctx.profile_read(f) for f in range(3)]
+    model.ctx.profile(0)
+    # ---- timed region 2: end to end through the public API (pinned host inputs in, waveforms out to host)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(model.stream)
+    audio_e2e, d2h = 0.0, 0
+    for _ in range(args.steps):
+        wavs, _ = step_e2e()
+        audio_e2e += sum(w.shape[-1] for w in wavs) / 24000.0
+        d2h = sum(w.numel() * 4 for w in wavs)
+        if dist is not None:
+            gather_waveforms(wavs, dist, dev)                                # NCCL gather of the results on rank 0
+    f1.record(model.stream)
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), 1000 * (time.perf_counter() - t0))
+    # ---- max over ranks, totals over ranks
+    tt = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    aa = torch.tensor([audio_s, audio_e2e, float(launches)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(aa, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = tt.tolist()
+    audio_s, audio_e2e, launches = aa.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = audio_s / (dev_ms / 1000.0)
+    e2e_v = audio_e2e / (e2e_ms / 1000.0)
+    # dominant kernel family = the one with the largest share of device time
+    fam_names = ["conv_gemm_tc (tcgen05 bf16)", "conv_gemm_simt (fp32 CUDA cores)", "attention (fp32 math flash kernel)"]
+    dom = max(range(3), key=lambda f: prof[f]["ms"])
+    p = prof[dom]
+    if dom == 0:
+        ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+    else:
+        # CUDA-core kernels: report against the tensor roof they should be moved to (frac shows the gap)
+        ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+    roof.update({"traffic": None, "kernel": fam_names[dom], "launches": p["launches"], "avg_launch_ms": p["ms"] / max(p["launches"], 1),
+                 "share_of_step": p["ms"] / dev_ms, "peak_source": pk["source"],
+                 "families_ms": {fam_names[f]: prof[f]["ms"] for f in range(3)}})
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        a, w, info = cpu_reference_sample(full=full)
+        cpu = {"value": a / w, "unit": "audio-sec/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"1 of the {batch} utterances (250 speech tokens, 10 s audio): LM {info['lm_s']:.1f}s flow {info['flow_s']:.1f}s HiFT {info['hift_s']:.1f}s"}
+    line = {"metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"CosyVoice2-0.5B zero-shot batch-{batch} per GPU, NFE=10, ragged Z10 requests (40-60 text tokens -> 200-300 speech tokens, "
+                                   "75 prompt tokens / 150 prompt mel frames)" + ("" if full else " [SMALL DEBUG MODEL]"),
+                       "batch_per_gpu": batch, "nfe": 10, "l2": "working set (1.3 GB weights + GBs of activations) exceeds the 126 MB L2",
+                       "parallelism": f"dp{n_gpus} (independent utterances, weights broadcast once over NCCL, waveforms gathered)",
+                       "stage_ms_last_step": {k: stats[k] for k in ("lm_ms", "flow_ms", "hift_ms")}, "rtf": 1.0 / value},
+            "e2e": {"value": e2e_v, "unit": "audio-sec/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_ms_per_step": wall_ms / args.steps}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--small", action="store_true", help="debug: 2-layer LM / reduced flow (NOT the benchmark config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workspace-gb", type=float, default=40.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,31 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   CVK_API_END
 }
 
+int cvk_profile(cvk_ctx* ctx, int enable) {
+  CVK_API_BEGIN
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : ctx->prof) { ctx->event_pool.push_back(r.a); ctx->event_pool.push_back(r.b); }
+  ctx->prof.clear();
+  ctx->prof_on = enable;
+  CVK_API_END
+}
+
+int cvk_profile_read(cvk_ctx* ctx, int family, double* ms, double* flops, double* bytes, int64_t* launches) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(family >= 0 && family < FAM_COUNT && ms && flops && bytes && launches, "cvk_profile_read: bad arguments");
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  double t = 0, w = 0, by = 0;
+  int64_t n = 0;
+  for (auto& r : ctx->prof) {
+    if (r.family != family) continue;
+    float e = 0.f;
+    CVK_CHECK_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e; w += r.work; by += r.bytes; ++n;
+  }
+  *ms = t; *flops = w; *bytes = by; *launches = n;
+  CVK_API_END
+}
+
 int cvk_set_tensor(cvk_ctx* ctx, const char* name, const float* data, int on_device, const int64_t* shape, int ndim) {
   CVK_API_BEGIN
   CVK_REQUIRE(name && data && shape && ndim >= 1 && ndim <= 4, "cvk_set_tensor: bad arguments");

@@ -131,6 +131,15 @@ struct RawTensor {
   int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
 };
 
+// optional per-kernel-family timing (bench.py roofline): CUDA events around every launch of a family
+enum ProfFamily { FAM_GEMM_TC = 0, FAM_GEMM_SIMT = 1, FAM_ATTN = 2, FAM_COUNT = 3 };
+struct ProfRec {
+  cudaEvent_t a, b;
+  int family;
+  double work;    // algorithmic FLOPs of the launch
+  double bytes;   // algorithmic bytes of the launch
+};
+
 struct HiftModel;
 struct FlowModel;
 struct LlmModel;
@@ -147,9 +156,14 @@ struct cvk_ctx {
   HiftModel* hift = nullptr;
   FlowModel* flow = nullptr;
   LlmModel* llm = nullptr;
+  void* mel_model = nullptr;
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
+  int prof_on = 0;
+  int in_capture = 0;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
   int use_graph = 1;                        // LM decode step replayed as a CUDA graph
   int use_tc = 1;                           // bf16 mode: route GEMMs to the tcgen05 kernel (0 = debug: SIMT on converted operands)
 
@@ -212,6 +226,29 @@ void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, co
 void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Mat& pos /*[2*Tmax-1, H*64]*/,
                           int pos_center, const float* bias_u, const float* bias_v, const Seqs& s, int H, int chunk, float scale,
                           const Mat& out);
+
+struct ProfScope {
+  cvk_ctx* ctx;
+  cudaStream_t st;
+  ProfRec rec;
+  bool on;
+  ProfScope(cvk_ctx* c, cudaStream_t s, int family, double work, double bytes) : ctx(c), st(s), on(c->prof_on && !c->in_capture) {
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    rec.a = get(); rec.b = get(); rec.family = family; rec.work = work; rec.bytes = bytes;
+    cudaEventRecord(rec.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.b, st);
+    ctx->prof.push_back(rec);
+  }
+};
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

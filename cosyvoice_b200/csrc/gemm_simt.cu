@@ -90,6 +90,8 @@ void conv_gemm_simt(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W,
   dim3 grid(ceil_div(W.N, BN), ceil_div(rowsOut, BM));
   EpiDev e = to_dev(ep);
   if (!e.bias) e.bias = W.bias;
+  ProfScope ps(ctx, st, FAM_GEMM_SIMT, 2.0 * rowsOut * (double)W.N * W.K * W.taps,
+               (double)rowsOut * W.K * A.esize() + (double)W.N * W.K * W.taps * 4 + (double)rowsOut * W.N * ep.out.esize());
   if (A.dtype == DT_F32) {
     conv_gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(A.f32(), A.ld, A.rows, W.w32, W.N, W.K, W.taps, W.dil, W.shift0,
                                                               rowsOut, e);

@@ -719,9 +719,12 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     int64_t before = ctx->launches;
     cudaGraph_t graph = nullptr;
     CVK_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    ctx->in_capture = 1;
     try {
       decode_step(ctx, st, s);
+      ctx->in_capture = 0;
     } catch (...) {
+      ctx->in_capture = 0;
       cudaStreamEndCapture(st, &graph);
       if (graph) cudaGraphDestroy(graph);
       throw;

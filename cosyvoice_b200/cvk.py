@@ -29,6 +29,9 @@ SIGNATURES = {
     "cvk_version": (ctypes.c_char_p, []),
     "cvk_launch_count": (ctypes.c_int64, [_vp]),
     "cvk_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
+    "cvk_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cvk_profile_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "cvk_set_tensor": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "cvk_finalize": (ctypes.c_int, [_vp, ctypes.c_char_p, _c_int_p, ctypes.c_int]),
     "cvk_op_conv1d": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int,
@@ -150,6 +153,14 @@ class Context:
 
     def set_option(self, key, value):
         self._check(self.lib.cvk_set_option(self.h, key.encode(), int(value)))
+
+    def profile(self, enable):
+        self._check(self.lib.cvk_profile(self.h, int(enable)))
+
+    def profile_read(self, family):
+        ms, fl, by, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self._check(self.lib.cvk_profile_read(self.h, family, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by), ctypes.byref(n)))
+        return dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
 
     def launch_count(self):
         return int(self.lib.cvk_launch_count(self.h))

@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference pipeline orchestrator, over libcvk.
+
+``B200CosyVoice2Model`` exposes the constructor / ``load`` / ``tts`` / ``token2wav`` surface and the session attributes
+of ``cosyvoice.cli.model.CosyVoice2Model`` (cosyvoice/cli/model.py:245-394) so it can be dropped in behind
+``cosyvoice.cli.cosyvoice.CosyVoice2`` (``cosyvoice.model = B200CosyVoice2Model(...)``), plus
+``tts_batch`` for the batch-32 metric (the reference has no batched API; its batch is a Python loop).
+
+All arithmetic happens in libcvk (hand-written sm_100a kernels); torch provides device memory, streams and the two
+random streams the reference draws from the global RNG (sampling uniforms, SineGen noise).  No CPU fallback.
+"""
+import threading
+import time
+import uuid
+from contextlib import nullcontext
+
+import numpy as np
+import torch
+
+from . import cvk
+
+TOKEN_MEL_RATIO = 2          # cosyvoice2.yaml:14
+PRE_LOOKAHEAD = 3            # cosyvoice2.yaml:46
+SAMPLES_PER_FRAME = 480
+
+
+def _count(keys, prefix):
+    idx = set()
+    for k in keys:
+        if k.startswith(prefix):
+            idx.add(int(k[len(prefix):].split(".")[0]))
+    return len(idx)
+
+
+def infer_cfgs(llm_sd, flow_sd):
+    """layer counts from state_dict keys (the reference builds these from yaml; cosyvoice2.yaml:23-87)"""
+    nl = _count(llm_sd.keys(), "llm.model.model.layers.")
+    fk = list(flow_sd.keys())
+    flow_cfg = [_count(fk, "encoder.encoders."), _count(fk, "encoder.up_encoders."), _count(fk, "decoder.estimator.mid_blocks."),
+                _count(fk, "decoder.estimator.down_blocks.0.1.")]
+    return [nl], flow_cfg
+
+
+def _state_dict(m):
+    return m if isinstance(m, dict) else m.state_dict()
+
+
+def cfm_rand_noise():
+    """CausalConditionalCFM.rand_noise (flow/flow_matching.py:199-200): seed-0 torch.randn([1,80,15000]), time-major."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(0)
+    return torch.randn([1, 80, 50 * 300], generator=g)[0].t().contiguous()
+
+
+class B200CosyVoice2Model:
+    def __init__(self, llm=None, flow=None, hift=None, fp16=False, precision="bf16", device=0, workspace_gb=24.0):
+        # attribute names follow cli/model.py:245-275
+        self.device = torch.device("cuda", device)
+        self.llm, self.flow, self.hift = llm, flow, hift
+        self.fp16 = fp16
+        self.token_hop_len = 25
+        self.token_max_hop_len = 4 * self.token_hop_len
+        self.stream_scale_factor = 2
+        self.mel_cache_len = 8
+        self.source_cache_len = int(self.mel_cache_len * 480)
+        self.speech_window = np.hamming(2 * self.source_cache_len)
+        self.lock = threading.Lock()
+        self.tts_speech_token_dict = {}
+        self.llm_end_dict = {}
+        self.hift_cache_dict = {}
+        self.silent_tokens = []
+        self.ctx = cvk.Context(device, precision, workspace_gb)
+        self.stream = torch.cuda.Stream(self.device)     # every library call of this model runs on this stream
+        self.generator = torch.Generator(device=self.device)
+        self.generator.manual_seed(1986)
+        self._sessions = {}
+        self._window = torch.from_numpy(self.speech_window).float().to(self.device)
+        self.n_timesteps = 10
+        self.min_token_text_ratio, self.max_token_text_ratio = 2.0, 20.0
+        self.timings = {}
+        # test hooks: explicit random streams instead of the device generator (the reference uses the global torch RNG)
+        self.uniforms_override = None        # tensor [steps, B, 2]
+        self.noise_fn = None                 # callable(n_samples) -> [n_samples, 9]
+        if llm is not None and flow is not None and hift is not None:
+            self.load_state_dicts(_state_dict(llm), _state_dict(flow), _state_dict(hift))
+
+    # ---------------------------------------------------------------- weights (cli/model.py:65-73)
+    def load(self, llm_model, flow_model, hift_model):
+        llm_sd = torch.load(llm_model, map_location="cpu", weights_only=True)
+        flow_sd = torch.load(flow_model, map_location="cpu", weights_only=True)
+        hift_sd = {k.replace("generator.", ""): v for k, v in torch.load(hift_model, map_location="cpu", weights_only=True).items()}
+        self.load_state_dicts(llm_sd, flow_sd, hift_sd)
+
+    def load_state_dicts(self, llm_sd, flow_sd, hift_sd):
+        llm_cfg, flow_cfg = infer_cfgs(llm_sd, flow_sd)
+        self.ctx.load_state_dict("llm", llm_sd, llm_cfg)
+        self.ctx.load_state_dict("flow", flow_sd, flow_cfg)
+        self.ctx.load_state_dict("hift", hift_sd)
+        self.ctx.set_cfm_noise(cfm_rand_noise())
+        self.ctx.finalize("mel")
+
+    # engine swap points of the reference are meaningless here; kept so that CosyVoice2.__init__ flags fail loudly
+    def load_jit(self, *a, **k):
+        raise RuntimeError("B200CosyVoice2Model has no TorchScript path (cli/model.py:277-279 swap point is replaced by libcvk)")
+
+    def load_trt(self, *a, **k):
+        raise RuntimeError("B200CosyVoice2Model has no TensorRT path (the estimator runs in libcvk)")
+
+    def load_vllm(self, *a, **k):
+        raise RuntimeError("B200CosyVoice2Model has no vLLM path (the LM runs in libcvk)")
+
+    # ---------------------------------------------------------------- LM (llm/llm.py:458-549), batched
+    def _session(self, B, ctx_len):
+        key = (B, (ctx_len + 255) // 256 * 256)
+        if key not in self._sessions:
+            self._sessions[key] = self.ctx.lm_session(key[0], key[1])
+        return self._sessions[key]
+
+    def lm_generate(self, texts, prompt_texts, prompt_speech_tokens, uniforms=None, steps_per_sync=32, on_progress=None):
+        """texts/prompt_texts/prompt_speech_tokens: lists of int32 tensors [1,n].  Returns a list of python id lists."""
+        B = len(texts)
+        tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(texts, prompt_texts)]
+        sl = [int(s.shape[1]) for s in prompt_speech_tokens]
+        tt = torch.cat([torch.cat([p.reshape(-1), t.reshape(-1)]) for t, p in zip(texts, prompt_texts)]).to(torch.int32)
+        ss = torch.cat([s.reshape(-1) for s in prompt_speech_tokens]).to(torch.int32) if sum(sl) else torch.zeros(1, dtype=torch.int32)
+        mins = [int(t.shape[1] * self.min_token_text_ratio) for t in texts]      # llm.py:497-498
+        maxs = [int(t.shape[1] * self.max_token_text_ratio) for t in texts]
+        mx = max(maxs)
+        with torch.cuda.stream(self.stream):
+            min_len = torch.tensor(mins, dtype=torch.int32, device=self.device)
+            max_len = torch.tensor(maxs, dtype=torch.int32, device=self.device)
+            sess = self._session(B, max(a + b for a, b in zip(tl, sl)) + 2 + mx + 8)
+            out_ids = torch.zeros(B, mx + 1, dtype=torch.int32, device=self.device)
+            out_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+            done = torch.zeros(B, dtype=torch.int32, device=self.device)
+            if uniforms is None and self.uniforms_override is not None:
+                uniforms = self.uniforms_override
+            if uniforms is None:
+                uniforms = torch.rand(mx + 1, B, 2, device=self.device, generator=self.generator)
+            uniforms = uniforms.to(self.device).float().contiguous()
+            with self.ctx.lock:
+                self.ctx.lm_prefill(sess, tt.to(self.device), tl, ss.to(self.device), sl)
+            n = 0
+            while True:
+                with self.ctx.lock:
+                    live = self.ctx.lm_decode(sess, steps_per_sync, uniforms, min_len, max_len, out_ids, out_count, done)
+                n += steps_per_sync
+                if on_progress is not None:
+                    on_progress(out_ids, out_count, live)
+                if live == 0 or n > mx + steps_per_sync:
+                    break
+            cnt = out_count.cpu().tolist()
+            ids = out_ids.cpu()
+        return [ids[b, :cnt[b]].tolist() for b in range(B)]
+
+    # ---------------------------------------------------------------- flow + vocoder
+    def flow_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True):
+        """lists per utterance: tokens [1,N] int, prompt_tokens [1,P], prompt_feats [1,Tp,80], embeddings [1,192]
+        -> (mel [sum T,80] time-major on the device, lens)"""
+        toks = torch.cat([torch.cat([p.reshape(-1), t.reshape(-1)]) for t, p in zip(tokens, prompt_tokens)]).to(torch.int32)
+        tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(tokens, prompt_tokens)]
+        pl = [int(f.shape[1]) for f in prompt_feats]
+        pf = torch.cat([f[0] for f in prompt_feats], 0) if sum(pl) else None
+        emb = torch.cat([e.reshape(1, -1) for e in embeddings], 0)
+        with torch.cuda.stream(self.stream), self.ctx.lock:
+            return self.ctx.flow_inference(toks, tl, pf, pl, emb, n_timesteps=self.n_timesteps, streaming=streaming, finalize=finalize)
+
+    def hift_batch(self, mel_tm, lens, cache_source=None, cache_lens=None, noise=None):
+        with torch.cuda.stream(self.stream), self.ctx.lock:
+            if noise is None and self.noise_fn is not None:
+                noise = self.noise_fn(sum(lens) * SAMPLES_PER_FRAME)
+            if noise is None:
+                noise = torch.randn(sum(lens) * SAMPLES_PER_FRAME, 9, device=self.device, generator=self.generator)
+            return self.ctx.hift_inference(mel_tm, lens, noise, cache_source, cache_lens)
+
+    def tts_batch(self, inputs, uniforms=None, noise=None, return_stats=False, to_host=True):
+        """inputs: list of dicts with the kwargs of tts() (text, prompt_text, llm_prompt_speech_token,
+        flow_prompt_speech_token, prompt_speech_feat, flow_embedding).  Returns a list of waveforms [1,N]
+        (CPU tensors, or views of one device buffer when to_host=False)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(self.stream):
+            ev[0].record()
+        ids = self.lm_generate([i["text"] for i in inputs], [i["prompt_text"] for i in inputs],
+                               [i["llm_prompt_speech_token"] for i in inputs], uniforms)
+        with torch.cuda.stream(self.stream):
+            ev[1].record()
+        toks = [torch.tensor(x, dtype=torch.int32).unsqueeze(0) for x in ids]
+        keep = [b for b, x in enumerate(ids) if len(x) > 0]
+        mel, lens = self.flow_batch([toks[b] for b in keep], [inputs[b]["flow_prompt_speech_token"] for b in keep],
+                                    [inputs[b]["prompt_speech_feat"] for b in keep], [inputs[b]["flow_embedding"] for b in keep])
+        with torch.cuda.stream(self.stream):
+            ev[2].record()
+        wav, _ = self.hift_batch(mel, lens, noise=noise)
+        with torch.cuda.stream(self.stream):
+            ev[3].record()
+            host = wav.cpu() if to_host else wav          # one D2H for the whole batch
+        self.stream.synchronize()
+        out, o = [torch.zeros(1, 0) for _ in inputs], 0
+        for b, L in zip(keep, lens):
+            out[b] = host[o:o + L * SAMPLES_PER_FRAME].unsqueeze(0)
+            o += L * SAMPLES_PER_FRAME
+        self.timings = {"lm_ms": ev[0].elapsed_time(ev[1]), "flow_ms": ev[1].elapsed_time(ev[2]), "hift_ms": ev[2].elapsed_time(ev[3]),
+                        "tokens": [len(x) for x in ids], "mel_frames": lens}
+        return (out, dict(self.timings)) if return_stats else out
+
+    # ---------------------------------------------------------------- reference-shaped single-request API
+    def _fade_in_out(self, fade_in, fade_out):
+        """utils/common.py:170-178 without the CPU round trip."""
+        n = self.source_cache_len
+        fade_in = fade_in.clone()
+        fade_in[..., :n] = fade_in[..., :n] * self._window[:n] + fade_out[..., -n:] * self._window[n:]
+        return fade_in
+
+    def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0):
+        """cli/model.py:292-326"""
+        mel, lens = self.flow_batch([token.to(torch.int32)], [prompt_token], [prompt_feat], [embedding], streaming=stream, finalize=finalize)
+        with torch.cuda.stream(self.stream):
+            tts_mel = mel[token_offset * TOKEN_MEL_RATIO:]
+            cache = self.hift_cache_dict[uuid]
+            cache_source, cache_lens = None, None
+            if cache is not None:
+                tts_mel = torch.cat([cache["mel"], tts_mel], 0)
+                cache_source, cache_lens = cache["source"], [cache["source"].shape[0]]
+            if finalize is False:
+                wav, src = self.hift_batch(tts_mel.contiguous(), [tts_mel.shape[0]], cache_source, cache_lens)
+                if cache is not None:
+                    wav = self._fade_in_out(wav, cache["speech"])
+                self.hift_cache_dict[uuid] = {"mel": tts_mel[-self.mel_cache_len:].clone(), "source": src[-self.source_cache_len:].clone(),
+                                              "speech": wav[-self.source_cache_len:].clone()}
+                wav = wav[:-self.source_cache_len]
+            else:
+                if speed != 1.0:
+                    assert cache is None, "speed change only support non-stream inference mode"
+                    m = torch.nn.functional.interpolate(tts_mel.t().unsqueeze(0), size=int(tts_mel.shape[0] / speed), mode="linear")
+                    tts_mel = m[0].t()
+                wav, src = self.hift_batch(tts_mel.contiguous(), [tts_mel.shape[0]], cache_source, cache_lens)
+                if cache is not None:
+                    wav = self._fade_in_out(wav, cache["speech"])
+        return wav.unsqueeze(0)
+
+    def llm_job(self, text, prompt_text, llm_prompt_speech_token, llm_embedding, uuid):
+        """cli/model.py:101-129 (non-generator text).  Tokens are appended to the session list as they arrive."""
+        def progress(out_ids, out_count, live):
+            n = int(out_count[0].item())
+            have = len(self.tts_speech_token_dict[uuid])
+            if n > have:
+                self.tts_speech_token_dict[uuid].extend(out_ids[0, have:n].tolist())
+        self.lm_generate([text], [prompt_text], [llm_prompt_speech_token], steps_per_sync=8, on_progress=progress)
+        self.llm_end_dict[uuid] = True
+
+    def vc_job(self, source_speech_token, uuid):
+        self.tts_speech_token_dict[uuid] = source_speech_token.flatten().tolist()
+        self.llm_end_dict[uuid] = True
+
+    def tts(self, text=torch.zeros(1, 0, dtype=torch.int32), flow_embedding=torch.zeros(0, 192), llm_embedding=torch.zeros(0, 192),
+            prompt_text=torch.zeros(1, 0, dtype=torch.int32), llm_prompt_speech_token=torch.zeros(1, 0, dtype=torch.int32),
+            flow_prompt_speech_token=torch.zeros(1, 0, dtype=torch.int32), prompt_speech_feat=torch.zeros(1, 0, 80),
+            source_speech_token=torch.zeros(1, 0, dtype=torch.int32), stream=False, speed=1.0, **kwargs):
+        """cli/model.py:328-394: same signature, same yielded dicts ({'tts_speech': float32 CPU [1,N]})."""
+        this_uuid = str(uuid.uuid1())
+        with self.lock:
+            self.tts_speech_token_dict[this_uuid], self.llm_end_dict[this_uuid] = [], False
+            self.hift_cache_dict[this_uuid] = None
+        if source_speech_token.shape[1] == 0:
+            p = threading.Thread(target=self.llm_job, args=(text, prompt_text, llm_prompt_speech_token, llm_embedding, this_uuid))
+        else:
+            p = threading.Thread(target=self.vc_job, args=(source_speech_token, this_uuid))
+        p.start()
+        if stream is True:
+            token_offset = 0
+            P = flow_prompt_speech_token.shape[1]
+            prompt_token_pad = int(np.ceil(P / self.token_hop_len) * self.token_hop_len - P)
+            while True:
+                time.sleep(0.005)
+                this_hop = self.token_hop_len + prompt_token_pad if token_offset == 0 else self.token_hop_len
+                toks = self.tts_speech_token_dict[this_uuid]
+                if len(toks) - token_offset >= this_hop + PRE_LOOKAHEAD:
+                    this_tok = torch.tensor(toks[:token_offset + this_hop + PRE_LOOKAHEAD]).unsqueeze(0)
+                    speech = self.token2wav(this_tok, flow_prompt_speech_token, prompt_speech_feat, flow_embedding, token_offset,
+                                            this_uuid, stream=True, finalize=False)
+                    token_offset += this_hop
+                    self.token_hop_len = min(self.token_max_hop_len, self.token_hop_len * self.stream_scale_factor)
+                    yield {"tts_speech": speech.cpu()}
+                if self.llm_end_dict[this_uuid] is True and len(self.tts_speech_token_dict[this_uuid]) - token_offset < this_hop + PRE_LOOKAHEAD:
+                    break
+            p.join()
+            this_tok = torch.tensor(self.tts_speech_token_dict[this_uuid]).unsqueeze(0)
+            speech = self.token2wav(this_tok, flow_prompt_speech_token, prompt_speech_feat, flow_embedding, token_offset, this_uuid,
+                                    finalize=True)
+            yield {"tts_speech": speech.cpu()}
+        else:
+            p.join()
+            this_tok = torch.tensor(self.tts_speech_token_dict[this_uuid]).unsqueeze(0)
+            speech = self.token2wav(this_tok, flow_prompt_speech_token, prompt_speech_feat, flow_embedding, 0, this_uuid, finalize=True,
+                                    speed=speed)
+            yield {"tts_speech": speech.cpu()}
+        with self.lock:
+            self.tts_speech_token_dict.pop(this_uuid)
+            self.llm_end_dict.pop(this_uuid)
+            self.hift_cache_dict.pop(this_uuid)
+        self.stream.synchronize()

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: the path shards by utterance - one process per GPU, a full weight replica each.
+
+Only two collectives exist, both outside the compute kernels (no exchange step inside LM -> flow -> HiFT):
+  * broadcast of the weights from rank 0 at load time,
+  * gather of the finished waveforms (lengths, then padded samples) to rank 0.
+`torch.distributed` is the transport (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from collections import OrderedDict
+
+import torch
+
+
+def shard_lpt(costs, world):
+    """Longest-processing-time assignment of utterances to ranks (cost = expected speech tokens).
+    Returns a list of index lists, one per rank; deterministic, every rank computes the same plan."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0] * world
+    plan = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        plan[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(p) for p in plan]
+
+
+def broadcast_state_dicts(sds, device, llm_shapes, flow_shapes, hift_shapes, dist):
+    """rank 0 holds (llm, flow, hift) state dicts; every other rank receives them.  One flat fp32 buffer per stage."""
+    if dist is None or dist.get_world_size() == 1:
+        return sds
+    out = []
+    for k, shapes in enumerate((llm_shapes, flow_shapes, hift_shapes)):
+        n = sum(int(torch.Size(s).numel()) for s in shapes.values())
+        if dist.get_rank() == 0:
+            flat = torch.cat([sds[k][key].reshape(-1).to(device=device, dtype=torch.float32) for key in shapes])
+        else:
+            flat = torch.empty(n, device=device, dtype=torch.float32)
+        dist.broadcast(flat, src=0)
+        sd, o = OrderedDict(), 0
+        for key, s in shapes.items():
+            m = int(torch.Size(s).numel())
+            sd[key] = flat[o:o + m].view(s)
+            o += m
+        out.append(sd)
+    return tuple(out)
+
+
+def gather_waveforms(wavs, dist, device):
+    """wavs: list of [1,N_i] tensors of this rank.  Returns on rank 0 a list (per rank) of lists of CPU waveforms, else None."""
+    if dist is None or dist.get_world_size() == 1:
+        return [wavs]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lens = torch.tensor([w.shape[-1] for w in wavs], dtype=torch.int64, device=device)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = len(wavs)
+    dist.all_reduce(counts)
+    maxn = int(counts.max())
+    lens_p = torch.zeros(maxn, dtype=torch.int64, device=device)
+    lens_p[:len(wavs)] = lens
+    all_lens = [torch.zeros(maxn, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_lens, lens_p)
+    total = max(int(l.sum()) for l in all_lens)
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    if wavs:
+        cat = torch.cat([w.reshape(-1).to(device) for w in wavs])
+        flat[:cat.numel()] = cat
+    bufs = [torch.zeros(total, dtype=torch.float32, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(flat, bufs, dst=0)
+    if rank != 0:
+        return None
+    out = []
+    for r in range(world):
+        o, lst = 0, []
+        for i in range(int(counts[r])):
+            n = int(all_lens[r][i])
+            lst.append(bufs[r][o:o + n].cpu().unsqueeze(0))
+            o += n
+        out.append(lst)
+    return out

@@ -49,6 +49,12 @@ int64_t cvk_launch_count(cvk_ctx* ctx);
 /* debug switch: 1 (default) = bf16 GEMMs on the tcgen05 kernel, 0 = same operands through the SIMT kernel */
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value);
 
+/* Per-kernel-family device timing for the roofline report of bench.py: CUDA events are recorded around every launch
+ * of a family while enabled (family 0 = tcgen05 conv-GEMM, 1 = CUDA-core conv-GEMM, 2 = attention).  Launches inside
+ * the captured LM decode graph are not instrumented.  cvk_profile_read sums elapsed ms, algorithmic FLOPs and bytes. */
+int cvk_profile(cvk_ctx* ctx, int enable);
+int cvk_profile_read(cvk_ctx* ctx, int family, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------- weights
  * replaces cosyvoice/cli/model.py:65-73 (CosyVoice2Model.load -> load_state_dict(strict=True)).
  * `name` = "<stage>." + reference state_dict key, stage in {"llm","flow","hift"}; data fp32, C-contiguous, on the
