@@ -95,6 +95,7 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   if (k == "use_tc") ctx->use_tc = value;
   else if (k == "tc_bn256") ctx->tc_bn256 = value;
   else if (k == "use_graph") ctx->use_graph = value;
+  else if (k == "use_tc_attn") ctx->use_tc_attn = value;
   else throw CvkError(CVK_ERR_INVALID, "unknown option: " + k);
   CVK_API_END
 }

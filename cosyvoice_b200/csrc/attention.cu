@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
 
 }  // namespace
 
+void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
+                      float scale, const Mat& out, int kv_div);
+
 void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
                    float scale, const Mat& out, int kv_div) {
   CVK_REQUIRE(q.dtype == k.dtype && q.dtype == v.dtype && q.dtype == out.dtype, "attention: mixed dtypes");
@@ -169,6 +172,10 @@ void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, co
   double fl = 0;
   for (int b = 0; b < s.B; ++b) fl += 4.0 * (double)s.len[b] * s.len[b] * 64 * H * (chunk > 0 ? 0.5 : 1.0);
   ProfScope ps(ctx, st, FAM_ATTN, fl, (double)s.sum_len * H * 64 * 4 * q.esize());
+  if (q.dtype == DT_BF16 && ctx->use_tc_attn) {
+    attention_fwd_tc(ctx, st, q, k, v, s, H, chunk, scale, out, kv_div);
+    return;
+  }
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, false><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, nullptr, 0, 0, 0, nullptr, nullptr,
                                                          s.d_start, s.d_len, chunk, scale, kv_div, out.f32(), out.ld);

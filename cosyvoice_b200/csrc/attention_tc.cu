@@ -1,0 +1,295 @@
+// bf16 self-attention on tcgen05 tensor cores for the flow estimator (matcha transformer.py:243-316 via diffusers
+// Attention; flow/decoder.py:439-449): head_dim 64, ragged sequences, full or block-causal (chunk) masking.
+//
+// One CTA = 128 queries of one (sequence, head).  S = Q K^T and O += P V are tcgen05.mma with accumulators in TMEM
+// (S: 128 columns, O: 64 columns); Q/K/V tiles arrive by TMA (SWIZZLE_128B) straight out of the fused QKV activation
+// matrix; V is consumed MN-major so no transpose is ever materialised; the mask is a predicate on (query, key) indices.
+// Softmax is two-pass (pass 1: row maxima from S tiles, pass 2: P = exp2(S - max) and O accumulation) so O is never
+// read-modify-written: exp throughput, not the tensor pipe, bounds this kernel, and the extra Q K^T costs ~1/4 of it.
+// Warps 0-3: softmax (one query row per thread, TMEM lane == row), warp 4: TMA producer, warp 5: MMA issuer.
+// Two CTAs are co-resident per SM (TMEM 2 x 256 columns, smem 2 x ~112 KB) so one CTA's exps overlap the other's MMAs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int AT_BQ = 128, AT_BK = 128, AT_HD = 64;
+constexpr int AT_THREADS = 192;
+constexpr uint32_t Q_BYTES = AT_BQ * AT_HD * 2;        // 16 KB
+constexpr uint32_t K_BYTES = AT_BK * AT_HD * 2;        // 16 KB
+constexpr uint32_t V_BYTES = AT_BK * AT_HD * 2;        // 16 KB
+constexpr uint32_t P_BYTES = AT_BQ * AT_BK * 2;        // 32 KB (two 128x64 SW128 tiles)
+constexpr uint32_t KV_STAGE = K_BYTES + V_BYTES;
+constexpr uint32_t AT_SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) break;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// SWIZZLE_128B operand descriptor; identical fields for a K-major tile (rows of 64 K-elements) and an MN-major tile
+// (rows of 64 MN-elements, 8-row K groups 1024 B apart): start>>4 | LBO 1 | SBO 1024>>4 | version 1 | layout 2
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const __grid_constant__ CUtensorMap tmv,
+               const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale_log2e, int kv_div,
+               bf16* __restrict__ out, int ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_s, bar_p, bar_o;
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int L = len[b], s0 = start[b];
+  const int i0 = blockIdx.x * AT_BQ;
+  if (i0 >= L) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sKV = base + Q_BYTES, sP = sKV + 2 * KV_STAGE;
+  // keys visible to this query tile: all of the sequence, or up to the end of the last query's chunk
+  const int i_last = min(i0 + AT_BQ, L) - 1;
+  const int kmax = chunk > 0 ? min(L, (i_last / chunk + 1) * chunk) : L;
+  const int ntiles = (kmax + AT_BK - 1) / AT_BK;
+  const int iters = 2 * ntiles;
+
+  // instruction descriptors: D=f32, A=B=bf16, M=128;  S: N=128, both K-major;  O: N=64, B (=V) MN-major
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+  constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar_q), 1);
+    mbar_init(smem_u32(&bar_s), 1);
+    mbar_init(smem_u32(&bar_p), 128);
+    mbar_init(smem_u32(&bar_o), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tS = tmem_slot, tO = tmem_slot + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
+      tma_load_2d(sQ, &tmq, smem_u32(&bar_q), h * AT_HD, s0 + i0);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it & 1;
+        const uint32_t round = (uint32_t)(it >> 1);
+        const int tile = it < ntiles ? it : it - ntiles;
+        const bool pass2 = it >= ntiles;
+        mbar_wait(smem_u32(&bar_empty[st]), (round & 1u) ^ 1u);
+        const uint32_t fb = smem_u32(&bar_full[st]);
+        mbar_expect_tx(fb, pass2 ? KV_STAGE : K_BYTES);
+        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, s0 + tile * AT_BK);
+        if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, s0 + tile * AT_BK);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bar_q), 0);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it & 1;
+        const uint32_t round = (uint32_t)(it >> 1);
+        const bool pass2 = it >= ntiles;
+        const int tile = pass2 ? it - ntiles : it;
+        mbar_wait(smem_u32(&bar_full[st]), round & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sK = sKV + st * KV_STAGE, sV = sK + K_BYTES;
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) umma(tS, desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&bar_s));
+        mbar_wait(smem_u32(&bar_p), (uint32_t)(it & 1));     // softmax threads are done with S (and wrote P in pass 2)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (pass2) {
+#pragma unroll
+          for (int k = 0; k < AT_BK / 16; ++k) {
+            // A = P: two K-major 128x64 tiles (16 KB each), 32 B per 16-key step inside a tile
+            // B = V: MN-major, 16 keys = 16 rows of 128 B = 2048 B per step
+            const uint32_t pa = sP + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32;
+            umma(tO, desc_sw128(pa), desc_sw128(sV + k * 2048), IDESC_O, (tile > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[st]));
+      }
+      umma_commit(smem_u32(&bar_o));
+    }
+  } else {
+    // softmax warps: thread <-> query row
+    const int row = warp * 32 + lane;
+    const int i = i0 + row;
+    const int klim = i < L ? (chunk > 0 ? min(L, (i / chunk + 1) * chunk) : L) : 0;
+    const uint32_t trow = ((uint32_t)(warp * 32) << 16);
+    float m = -INFINITY;
+    for (int it = 0; it < ntiles; ++it) {
+      mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int j0 = it * AT_BK;
+#pragma unroll 1
+      for (int c = 0; c < AT_BK; c += 16) {
+        float v[16];
+        tmem_ld16(tS + trow + (uint32_t)c, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (j0 + c + e < klim) m = fmaxf(m, v[e]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&bar_p));
+    }
+    const float mneg = (m == -INFINITY) ? 0.f : -m * scale_log2e;
+    float lsum = 0.f;
+    const uint32_t prow = sP + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    for (int t = 0; t < ntiles; ++t) {
+      const int it = ntiles + t;
+      mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int j0 = t * AT_BK;
+#pragma unroll 1
+      for (int c = 0; c < AT_BK; c += 16) {
+        float v[16];
+        tmem_ld16(tS + trow + (uint32_t)c, v);
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float p0 = (j0 + c + e < klim) ? exp2f(fmaf(v[e], scale_log2e, mneg)) : 0.f;
+          float p1 = (j0 + c + e + 1 < klim) ? exp2f(fmaf(v[e + 1], scale_log2e, mneg)) : 0.f;
+          lsum += p0 + p1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        // keys c..c+15 -> 16-B chunks (c/8) and (c/8+1) of sub-tile c/64, XOR-swizzled by (row & 7)
+        const uint32_t sub = prow + (uint32_t)(c >> 6) * (AT_BQ * 128);
+        const uint32_t ch = (uint32_t)((c & 63) >> 3);
+        const uint32_t a0 = sub + (((ch) ^ (uint32_t)(row & 7)) << 4);
+        const uint32_t a1 = sub + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P stores -> visible to the tensor (async) proxy
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&bar_p));
+    }
+    mbar_wait(smem_u32(&bar_o), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < AT_HD; c += 16) {
+      float v[16];
+      tmem_ld16(tO + trow + (uint32_t)c, v);
+      if (i < L) {
+        __align__(16) bf16 t[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) t[e] = __float2bfloat16_rn(v[e] * inv);
+        bf16* op = out + (size_t)(s0 + i) * ldo + h * AT_HD + c;
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(t);
+        *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(t + 8);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void make_map(cvk_ctx* ctx, CUtensorMap* m, const Mat& x, int box_rows) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CVK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    CVK_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    ctx->encode_tiled = fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)x.cols, (cuuint64_t)x.rows};
+  cuuint64_t strides[1] = {(cuuint64_t)x.ld * 2};
+  cuuint32_t box[2] = {AT_HD, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CVK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(attention) failed: " + std::to_string((int)r));
+}
+
+}  // namespace
+
+void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
+                      float scale, const Mat& out, int kv_div) {
+  CVK_REQUIRE(q.dtype == DT_BF16 && out.dtype == DT_BF16, "attention_fwd_tc: bf16 only");
+  CVK_REQUIRE(q.ld % 8 == 0 && k.ld % 8 == 0 && v.ld % 8 == 0 && out.ld % 8 == 0, "attention_fwd_tc: 16-byte row pitch required");
+  CVK_REQUIRE((((uintptr_t)q.p | (uintptr_t)k.p | (uintptr_t)v.p | (uintptr_t)out.p) & 15) == 0, "attention_fwd_tc: 16-byte alignment required");
+  CUtensorMap tq, tk, tv;
+  make_map(ctx, &tq, q, AT_BQ);
+  make_map(ctx, &tk, k, AT_BK);
+  make_map(ctx, &tv, v, AT_BK);
+  static bool attr = false;
+  if (!attr) {
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    attr = true;
+  }
+  dim3 grid(ceil_div(s.max_len, AT_BQ), H, s.B);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}

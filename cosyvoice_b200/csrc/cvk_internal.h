@@ -164,6 +164,7 @@ struct cvk_ctx {
   int in_capture = 0;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
+  int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)
   int use_graph = 1;                        // LM decode step replayed as a CUDA graph
   int use_tc = 1;                           // bf16 mode: route GEMMs to the tcgen05 kernel (0 = debug: SIMT on converted operands)
 

@@ -334,9 +334,9 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
   EpiDev e = to_dev(ep);
   if (!e.bias) e.bias = W.bias;
   int rowsOut = ep.out.rows;
-  CVK_REQUIRE(ep.out.ld % 8 == 0 && ((uintptr_t)ep.out.p & 15) == 0, "conv_gemm_tc: output must be 16-byte aligned with ld % 8 == 0");
+  CVK_REQUIRE((ep.out.ld * ep.out.esize()) % 16 == 0 && ((uintptr_t)ep.out.p & 15) == 0, "conv_gemm_tc: output rows must be 16-byte aligned");
   CVK_REQUIRE(!ep.resid.p || (ep.resid.ld % 4 == 0 && ((uintptr_t)ep.resid.p & 15) == 0), "conv_gemm_tc: residual alignment");
-  CVK_REQUIRE(!ep.out2.p || (ep.out2.ld % 8 == 0 && ((uintptr_t)ep.out2.p & 15) == 0), "conv_gemm_tc: out2 alignment");
+  CVK_REQUIRE(!ep.out2.p || ((ep.out2.ld * ep.out2.esize()) % 16 == 0 && ((uintptr_t)ep.out2.p & 15) == 0), "conv_gemm_tc: out2 alignment");
   const double flops = 2.0 * rowsOut * (double)W.N * W.K * W.taps;
   const double bytes = (double)rowsOut * W.K * 2 + (double)W.N * W.K * W.taps * 2 + (double)rowsOut * W.N * ep.out.esize();
   ProfScope ps(ctx, st, FAM_GEMM_TC, flops, bytes);

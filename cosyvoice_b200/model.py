@@ -120,12 +120,15 @@ class B200CosyVoice2Model:
         B = len(texts)
         tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(texts, prompt_texts)]
         sl = [int(s.shape[1]) for s in prompt_speech_tokens]
-        tt = torch.cat([torch.cat([p.reshape(-1), t.reshape(-1)]) for t, p in zip(texts, prompt_texts)]).to(torch.int32)
-        ss = torch.cat([s.reshape(-1) for s in prompt_speech_tokens]).to(torch.int32) if sum(sl) else torch.zeros(1, dtype=torch.int32)
         mins = [int(t.shape[1] * self.min_token_text_ratio) for t in texts]      # llm.py:497-498
         maxs = [int(t.shape[1] * self.max_token_text_ratio) for t in texts]
         mx = max(maxs)
+        d = self.device
         with torch.cuda.stream(self.stream):
+            tt = torch.cat([torch.cat([p.reshape(-1).to(d, non_blocking=True), t.reshape(-1).to(d, non_blocking=True)])
+                            for t, p in zip(texts, prompt_texts)]).to(torch.int32)
+            ss = torch.cat([s.reshape(-1).to(d, non_blocking=True) for s in prompt_speech_tokens]).to(torch.int32) if sum(sl) \
+                else torch.zeros(1, dtype=torch.int32, device=d)
             min_len = torch.tensor(mins, dtype=torch.int32, device=self.device)
             max_len = torch.tensor(maxs, dtype=torch.int32, device=self.device)
             sess = self._session(B, max(a + b for a, b in zip(tl, sl)) + 2 + mx + 8)
@@ -156,12 +159,14 @@ class B200CosyVoice2Model:
     def flow_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True):
         """lists per utterance: tokens [1,N] int, prompt_tokens [1,P], prompt_feats [1,Tp,80], embeddings [1,192]
         -> (mel [sum T,80] time-major on the device, lens)"""
-        toks = torch.cat([torch.cat([p.reshape(-1), t.reshape(-1)]) for t, p in zip(tokens, prompt_tokens)]).to(torch.int32)
+        d = self.device
         tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(tokens, prompt_tokens)]
         pl = [int(f.shape[1]) for f in prompt_feats]
-        pf = torch.cat([f[0] for f in prompt_feats], 0) if sum(pl) else None
-        emb = torch.cat([e.reshape(1, -1) for e in embeddings], 0)
         with torch.cuda.stream(self.stream), self.ctx.lock:
+            toks = torch.cat([torch.cat([p.reshape(-1).to(d, non_blocking=True), t.reshape(-1).to(d, non_blocking=True)])
+                              for t, p in zip(tokens, prompt_tokens)]).to(torch.int32)
+            pf = torch.cat([f[0].to(d, non_blocking=True) for f in prompt_feats], 0) if sum(pl) else None
+            emb = torch.cat([e.reshape(1, -1).to(d, non_blocking=True) for e in embeddings], 0)
             return self.ctx.flow_inference(toks, tl, pf, pl, emb, n_timesteps=self.n_timesteps, streaming=streaming, finalize=finalize)
 
     def hift_batch(self, mel_tm, lens, cache_source=None, cache_lens=None, noise=None):

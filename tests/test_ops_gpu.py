@@ -100,3 +100,23 @@ def test_attention(precision, chunk):
     out = ctx(precision).attention(q, k, v, lens, H, chunk, 0.125)
     torch.cuda.synchronize()
     assert maxdiff(out, ref) < (2e-5 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("chunk", [0, 50])
+def test_attention_tcgen05_long_ragged(chunk):
+    """bf16 mode runs the tcgen05 attention kernel: multi-tile sequences, ragged lengths, block-causal mask."""
+    g = torch.Generator().manual_seed(13)
+    lens, H = [650, 129, 300, 7], 8
+    q, k, v = (torch.randn(sum(lens), H * 64, generator=g) for _ in range(3))
+    q = q * 1.5
+    ref = _ref_attention(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), lens, H, chunk, 0.125)
+    c = ctx("bf16")
+    out = c.attention(q, k, v, lens, H, chunk, 0.125)
+    c.set_option("use_tc_attn", 0)
+    try:
+        simt = c.attention(q, k, v, lens, H, chunk, 0.125)
+    finally:
+        c.set_option("use_tc_attn", 1)
+    torch.cuda.synchronize()
+    assert maxdiff(simt, ref) < 2e-2
+    assert maxdiff(out, ref) < 2e-2, maxdiff(out, ref)      # P rounded to bf16 before P.V
