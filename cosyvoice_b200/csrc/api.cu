@@ -96,6 +96,14 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   else if (k == "tc_bn256") ctx->tc_bn256 = value;
   else if (k == "use_graph") ctx->use_graph = value;
   else if (k == "use_tc_attn") ctx->use_tc_attn = value;
+  else if (k == "use_skinny") ctx->use_skinny = value;
+  else if (k == "debug_timeline") {
+    if (value && !ctx->dbg) {
+      ctx->dbg = ctx->dmalloc(1024 * sizeof(long long));
+      CVK_CHECK_CUDA(cudaMemset(ctx->dbg, 0, 1024 * sizeof(long long)));
+    }
+    if (!value) ctx->dbg = nullptr;
+  }
   else throw CvkError(CVK_ERR_INVALID, "unknown option: " + k);
   CVK_API_END
 }
@@ -197,6 +205,43 @@ int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens, int B, int K, c
   }
   unpack_rows(ctx, st, o, s, 0, out, N);
   CVK_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = owned_mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+  ctx->owned.resize(owned_mark);
+  CVK_API_END
+}
+
+// out[b, n] = sum_k x[b,k] w[n,k] (+bias) through the LM decode weight-streaming kernel (bf16 mode, rows <= 64)
+int cvk_op_linear_small(cvk_ctx* ctx, const float* x, int rows, int K, const float* w, const float* bias, int N, float* out, int iters,
+                        float* ms_out, long long* timeline_host, void* stream) {
+  CVK_API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  CVK_REQUIRE(x && w && out && rows > 0 && rows <= 64 && ctx->precision == CVK_PREC_BF16, "cvk_op_linear_small: bf16 context, rows <= 64");
+  ctx->arena.reset();
+  size_t owned_mark = ctx->owned.size();
+  ConvW W = make_conv(ctx, w, bias, N, K, 1, 1, 0);
+  skinny_tiled_weights(ctx, W);
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  Mat a32((void*)x, DT_F32, rows, K, K);
+  Mat a = arena_mat(ctx, DT_BF16, rows, K);
+  convert_mat(ctx, st, a32, a);
+  Mat o(out, DT_F32, rows, N, N);
+  size_t sf = skinny_scratch_floats(rows, N);
+  float* scratch = (float*)ctx->arena.alloc(sf * sizeof(float));
+  Epilogue e;
+  e.out = o;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  conv_gemm_skinny(ctx, st, a, W, e, scratch, sf);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) conv_gemm_skinny(ctx, st, a, W, e, scratch, sf);
+  cudaEventRecord(e1, st);
+  CVK_CHECK_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  if (timeline_host && ctx->dbg) CVK_CHECK_CUDA(cudaMemcpy(timeline_host, ctx->dbg, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->tiled.erase(W.w16);
   for (size_t i = owned_mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
   ctx->owned.resize(owned_mark);
   CVK_API_END

@@ -160,10 +160,13 @@ struct cvk_ctx {
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
+  void* dbg = nullptr;                      // device int64[1024] timeline buffer (debug option)
   int prof_on = 0;
   int in_capture = 0;
   std::vector<ProfRec> prof;
+  std::unordered_map<const void*, void*> tiled;   // bf16 weight -> streaming (pre-tiled, pre-swizzled) copy for the skinny GEMM
   std::vector<cudaEvent_t> event_pool;
+  int use_skinny = 1;                       // LM decode GEMMs on the weight-streaming split-K kernel
   int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)
   int use_graph = 1;                        // LM decode step replayed as a CUDA graph
   int use_tc = 1;                           // bf16 mode: route GEMMs to the tcgen05 kernel (0 = debug: SIMT on converted operands)
@@ -200,6 +203,9 @@ float* dev_copy_f32(cvk_ctx* ctx, const float* src_dev, size_t n);
 void conv_gemm(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
 void conv_gemm_simt(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
 void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
+size_t skinny_scratch_floats(int rows, int maxN);
+const bf16* skinny_tiled_weights(cvk_ctx* ctx, const ConvW& W);
+void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats);
 
 // elementwise / normalisation (elementwise.cu)
 void zero_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& m);

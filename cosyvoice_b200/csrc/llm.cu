@@ -63,6 +63,8 @@ struct cvk_lm_session {
   const int32_t *g_min = nullptr, *g_max = nullptr;
   int32_t *g_out_ids = nullptr, *g_out_count = nullptr, *g_done = nullptr;
   int g_out_ld = 0, g_B = 0;
+  float* scratch = nullptr;      // split-K partial sums of the weight-streaming GEMM
+  size_t scratch_floats = 0;
   std::vector<void*> owned;
 };
 
@@ -153,31 +155,88 @@ __global__ void rope_append_kernel(T* __restrict__ qkv, int ld, const int* __res
   }
 }
 
-// decode attention: one warp per (row, query head); keys 0..ctx_len[b] (the new token was appended already)
+// decode attention: one CTA per (row, kv head), one warp per query head of the group (7 warps).  Phase A: one key per
+// lane (full 64-dim dot product from a 128-byte cache row), scores to shared memory; softmax over the warp; phase B: one
+// pair of output dims per lane, keys streamed with coalesced 128-byte rows.  Keys 0..ctx_len[b] (new token included).
 template <typename T>
-__global__ void decode_attn_kernel(const T* __restrict__ qkv, int ld, const T* __restrict__ kc, const T* __restrict__ vc,
-                                   const int* __restrict__ ctx_len, int max_ctx, T* __restrict__ out, int ldo) {
-  int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int kvh = h / (NH / NKV);
-  int L = min(ctx_len[b] + 1, max_ctx);
+__global__ void __launch_bounds__((NH / NKV) * 32)
+decode_attn_kernel(const T* __restrict__ qkv, int ld, const T* __restrict__ kc, const T* __restrict__ vc,
+                   const int* __restrict__ ctx_len, int max_ctx, T* __restrict__ out, int ldo) {
+  extern __shared__ float sc_all[];            // [7][max_ctx]
+  const int b = blockIdx.x, kvh = blockIdx.y;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = kvh * (NH / NKV) + w;
+  const int L = min(ctx_len[b] + 1, max_ctx);
+  float* sc = sc_all + (size_t)w * max_ctx;
   const T* q = qkv + (size_t)b * ld + h * HD;
-  float q0 = to_f32(q[lane]), q1 = to_f32(q[lane + 32]);
   const T* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
   const T* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
-  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < L; ++j) {
-    float s = q0 * to_f32(kb[(size_t)j * HD + lane]) + q1 * to_f32(kb[(size_t)j * HD + lane + 32]);
-    s = warp_sum(s) * 0.125f;
-    float mn = fmaxf(m, s);
-    float corr = expf(m - mn), p = expf(s - mn);
-    l = l * corr + p;
-    o0 = o0 * corr + p * to_f32(vb[(size_t)j * HD + lane]);
-    o1 = o1 * corr + p * to_f32(vb[(size_t)j * HD + lane + 32]);
-    m = mn;
+  float qr[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) qr[d] = to_f32(q[d]) * 0.125f;
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    const T* kr = kb + (size_t)j * HD;
+    float s = 0.f;
+    if (sizeof(T) == 2) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(kr);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u = k4[c];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          s = fmaf(qr[c * 8 + 2 * e], f.x, s);
+          s = fmaf(qr[c * 8 + 2 * e + 1], f.y, s);
+        }
+      }
+    } else {
+      const float4* k4 = reinterpret_cast<const float4*>(kr);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 f = k4[c];
+        s = fmaf(qr[c * 4], f.x, s);
+        s = fmaf(qr[c * 4 + 1], f.y, s);
+        s = fmaf(qr[c * 4 + 2], f.z, s);
+        s = fmaf(qr[c * 4 + 3], f.w, s);
+      }
+    }
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    float p = expf(sc[j] - m);
+    sc[j] = p;
+    l += p;
+  }
+  l = warp_sum(l);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  int j = 0;
+  for (; j + 4 <= L; j += 4) {
+    float p0 = sc[j], p1 = sc[j + 1], p2 = sc[j + 2], p3 = sc[j + 3];
+    const T* v0 = vb + (size_t)j * HD;
+    float a0 = to_f32(v0[lane]), a1 = to_f32(v0[lane + 32]);
+    float b0 = to_f32(v0[HD + lane]), b1 = to_f32(v0[HD + lane + 32]);
+    float c0 = to_f32(v0[2 * HD + lane]), c1 = to_f32(v0[2 * HD + lane + 32]);
+    float d0 = to_f32(v0[3 * HD + lane]), d1 = to_f32(v0[3 * HD + lane + 32]);
+    o0 = fmaf(p0, a0, o0); o1 = fmaf(p0, a1, o1);
+    o0 = fmaf(p1, b0, o0); o1 = fmaf(p1, b1, o1);
+    o0 = fmaf(p2, c0, o0); o1 = fmaf(p2, c1, o1);
+    o0 = fmaf(p3, d0, o0); o1 = fmaf(p3, d1, o1);
+  }
+  for (; j < L; ++j) {
+    float p = sc[j];
+    o0 = fmaf(p, to_f32(vb[(size_t)j * HD + lane]), o0);
+    o1 = fmaf(p, to_f32(vb[(size_t)j * HD + lane + 32]), o1);
   }
   T* op = out + (size_t)b * ldo + h * HD;
-  op[lane] = from_f32<T>(o0 / l);
-  op[lane + 32] = from_f32<T>(o1 / l);
+  float inv = 1.f / l;
+  op[lane] = from_f32<T>(o0 * inv);
+  op[lane + 32] = from_f32<T>(o1 * inv);
 }
 
 // SwiGLU: silu(gate) * up; gu = [gate(4864) | up(4864)]
@@ -471,6 +530,14 @@ std::vector<int> prefix(const int* lens, int B) {
   return off;
 }
 
+// GEMM of the LM: the weight-streaming split-K kernel when there are at most 64 activation rows (decode), else the tiled kernel
+void lm_gemm(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& e, cvk_lm_session* sess) {
+  if (sess && A.dtype == DT_BF16 && ctx->use_tc && ctx->use_skinny && e.out.rows <= 64 && W.w16)
+    conv_gemm_skinny(ctx, st, A, W, e, sess->scratch, sess->scratch_floats);
+  else
+    conv_gemm(ctx, st, A, W, e);
+}
+
 // one transformer layer on `rows` rows.  prefill: seqs geometry + causal attention over the qkv buffer;
 // decode: rows == sequences, attention against the cache.
 void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, const Mat& x, const Mat& xn, const Mat& qkv, const Mat& att,
@@ -481,7 +548,7 @@ void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, con
   {
     Epilogue e;
     e.out = qkv;
-    conv_gemm(ctx, st, xn, w.qkv, e);
+    lm_gemm(ctx, st, xn, w.qkv, e, decode ? sess : nullptr);
   }
   size_t es = qkv.dtype == DT_F32 ? 4 : 2;
   void* kc = sess ? (char*)sess->kcache + (size_t)li * sess->max_batch * NKV * sess->max_ctx * HD * es : nullptr;
@@ -490,12 +557,12 @@ void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, con
     if (qkv.dtype == DT_F32) {
       rope_append_kernel<float><<<dim3(1, rows), 128, 0, st>>>(qkv.f32(), qkv.ld, nullptr, nullptr, sess->ctx_len, m->d_inv_freq, (float*)kc,
                                                                (float*)vc, sess->max_ctx, 1);
-      decode_attn_kernel<float><<<rows, NH * 32, 0, st>>>(qkv.f32(), qkv.ld, (const float*)kc, (const float*)vc, sess->ctx_len, sess->max_ctx,
+      decode_attn_kernel<float><<<dim3(rows, NKV), (NH / NKV) * 32, (NH / NKV) * sess->max_ctx * sizeof(float), st>>>(qkv.f32(), qkv.ld, (const float*)kc, (const float*)vc, sess->ctx_len, sess->max_ctx,
                                                           att.f32(), att.ld);
     } else {
       rope_append_kernel<bf16><<<dim3(1, rows), 128, 0, st>>>(qkv.b16(), qkv.ld, nullptr, nullptr, sess->ctx_len, m->d_inv_freq, (bf16*)kc,
                                                               (bf16*)vc, sess->max_ctx, 1);
-      decode_attn_kernel<bf16><<<rows, NH * 32, 0, st>>>(qkv.b16(), qkv.ld, (const bf16*)kc, (const bf16*)vc, sess->ctx_len, sess->max_ctx,
+      decode_attn_kernel<bf16><<<dim3(rows, NKV), (NH / NKV) * 32, (NH / NKV) * sess->max_ctx * sizeof(float), st>>>(qkv.b16(), qkv.ld, (const bf16*)kc, (const bf16*)vc, sess->ctx_len, sess->max_ctx,
                                                          att.b16(), att.ld);
     }
     ctx->launches += 2;
@@ -520,13 +587,13 @@ void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, con
     Epilogue e;
     e.resid = x;
     e.out = x;
-    conv_gemm(ctx, st, att, w.o, e);
+    lm_gemm(ctx, st, att, w.o, e, decode ? sess : nullptr);
   }
   rmsnorm(ctx, st, x, w.ln2, RMS_EPS, xn);
   {
     Epilogue e;
     e.out = gu;
-    conv_gemm(ctx, st, xn, w.gate_up, e);
+    lm_gemm(ctx, st, xn, w.gate_up, e, decode ? sess : nullptr);
   }
   {
     size_t total = (size_t)rows * DFF;
@@ -541,15 +608,16 @@ void layer_forward(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, int li, con
     Epilogue e;
     e.resid = x;
     e.out = x;
-    conv_gemm(ctx, st, ffa, w.down, e);
+    lm_gemm(ctx, st, ffa, w.down, e, decode ? sess : nullptr);
   }
 }
 
-void head_logits(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, const Mat& hidden_f32, const Mat& xn_act, const Mat& logits) {
+void head_logits(cvk_ctx* ctx, cudaStream_t st, const LlmModel* m, const Mat& hidden_f32, const Mat& xn_act, const Mat& logits,
+                 cvk_lm_session* sess = nullptr) {
   rmsnorm(ctx, st, hidden_f32, m->final_norm, RMS_EPS, xn_act);
   Epilogue e;
   e.out = logits;
-  conv_gemm(ctx, st, xn_act, m->head, e);
+  lm_gemm(ctx, st, xn_act, m->head, e, sess);
 }
 
 }  // namespace
@@ -564,6 +632,7 @@ void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
   m->speech_emb = copy_param(ctx, P + "speech_embedding.weight");
   m->head = make_linear(ctx, P + "llm_decoder.weight", P + "llm_decoder.bias");
   m->final_norm = copy_param(ctx, P + "llm.model.model.norm.weight");
+  if (ctx->precision == CVK_PREC_BF16) skinny_tiled_weights(ctx, m->head);
   for (int i = 0; i < m->num_layers; ++i) {
     std::string L = P + "llm.model.model.layers." + std::to_string(i);
     LayerW w;
@@ -574,6 +643,9 @@ void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
     w.o = make_linear(ctx, L + ".self_attn.o_proj.weight", "");
     w.gate_up = concat_linear(ctx, {L + ".mlp.gate_proj.weight", L + ".mlp.up_proj.weight"}, {});
     w.down = make_linear(ctx, L + ".mlp.down_proj.weight", "");
+    if (ctx->precision == CVK_PREC_BF16) {
+      skinny_tiled_weights(ctx, w.qkv); skinny_tiled_weights(ctx, w.o); skinny_tiled_weights(ctx, w.gate_up); skinny_tiled_weights(ctx, w.down);
+    }
     m->layers.push_back(w);
   }
   for (int i = 0; i < HD / 2; ++i) m->inv_freq[i] = 1.0f / powf(ROPE_THETA, (float)(2 * i) / (float)HD);
@@ -603,6 +675,9 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->ctx_len = (int*)alloc(sizeof(int) * max_batch);
   s->base_len = (int*)alloc(sizeof(int) * max_batch);
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT * (int)sizeof(float)));
+  CVK_REQUIRE((NH / NKV) * max_context * sizeof(float) <= 200 * 1024, "session context too long for the decode attention kernel");
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
   s->count = (int*)alloc(sizeof(int) * max_batch);
   s->done = (int*)alloc(sizeof(int) * max_batch);
   s->live = (int*)alloc(sizeof(int));
@@ -614,6 +689,8 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->att = alloc(es * max_batch * D);
   s->gu = alloc(es * (size_t)max_batch * 2 * DFF);
   s->ffa = alloc(es * (size_t)max_batch * DFF);
+  s->scratch_floats = skinny_scratch_floats(max_batch, 2 * DFF);
+  s->scratch = (float*)alloc(s->scratch_floats * sizeof(float));
   return s;
 }
 
@@ -684,7 +761,7 @@ static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
   const int B = s->g_B;
   Mat hid(s->hidden, DT_F32, B, D, D), x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N),
       att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, VOUT, VOUT);
-  head_logits(ctx, st, m, hid, xn, logits);
+  head_logits(ctx, st, m, hid, xn, logits, s);
   ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
                                                                        s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
                                                                        m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr);

@@ -36,6 +36,8 @@ SIGNATURES = {
     "cvk_finalize": (ctypes.c_int, [_vp, ctypes.c_char_p, _c_int_p, ctypes.c_int]),
     "cvk_op_conv1d": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "cvk_op_linear_small": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_longlong), _vp]),
     "cvk_op_attention": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, _vp, _vp]),
     "cvk_hift_f0": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
     "cvk_hift_source": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp, _vp]),
@@ -176,6 +178,16 @@ class Context:
         self._check(self.lib.cvk_op_conv1d(self.h, _ptr(x), _ints(lens), len(lens), K, _ptr(w), _ptr(b), N, taps, dil, shift0,
                                            ACT[act], _ptr(out), _stream()))
         return out
+
+    def linear_small(self, x, w, bias=None, iters=0, timeline=False):
+        x, w = _f32(x, self.device), _f32(w, self.device)
+        b = _f32(bias, self.device) if bias is not None else None
+        out = torch.empty(x.shape[0], w.shape[0], device=self.device)
+        ms = ctypes.c_float(0)
+        tl = (ctypes.c_longlong * 128)() if timeline else None
+        self._check(self.lib.cvk_op_linear_small(self.h, _ptr(x), x.shape[0], x.shape[1], _ptr(w), _ptr(b), w.shape[0], _ptr(out), iters,
+                                                 ctypes.byref(ms), tl, _stream()))
+        return out, ms.value, (list(tl) if timeline else None)
 
     def attention(self, q, k, v, lens, heads, chunk=0, scale=0.125):
         q, k, v = (_f32(t, self.device) for t in (q, k, v))

@@ -70,6 +70,11 @@ int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg);
  * entry of lens_host.  w is a torch Conv1d weight [N,K,taps] fp32 on the device. */
 int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens_host, int B, int K, const float* w, const float* bias,
                   int N, int taps, int dil, int shift0, int act, float* out, void* stream);
+/* out[b,n] = bias[n] + sum_k x[b,k] w[n,k] through the LM decode weight-streaming kernel (bf16 context, rows <= 64);
+ * runs it `iters` more times and reports the mean device time; timeline_host (optional, 128 int64) receives the clock64
+ * stamps of CTA 0 when the "debug_timeline" option is on. */
+int cvk_op_linear_small(cvk_ctx* ctx, const float* x, int rows, int K, const float* w, const float* bias, int N, float* out, int iters,
+                        float* ms_out, long long* timeline_host, void* stream);
 /* block-causal / full multi-head attention over ragged sequences; q,k,v,out [sum(lens), H*64] */
 int cvk_op_attention(cvk_ctx* ctx, const float* q, const float* k, const float* v, const int* lens_host, int B, int H,
                      int chunk, float scale, float* out, void* stream);

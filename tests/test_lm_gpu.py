@@ -146,3 +146,18 @@ def test_decode_bf16_runs_and_first_token_matches(golden):
     ids = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
     assert len(ids) == len(g["ids"]) and all(0 <= i < 6561 for i in ids)
     assert ids[0] == int(g["ids"][0])
+
+
+def test_decode_weight_streaming_gemm_vs_tiled_bf16():
+    """bf16 decode: the split-K weight-streaming GEMM and the tiled tcgen05 GEMM see the same operands; the sampled ids
+    agree until fp32 summation-order noise meets a near-tie (the first tokens are required to agree)."""
+    c, sd = model("bf16", 2)
+    text, ptext, ptok, U = cases.lm_case()
+    a = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    c.set_option("use_skinny", 0)
+    try:
+        b = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    finally:
+        c.set_option("use_skinny", 1)
+    n = min(len(a), len(b), 8)
+    assert n >= 6 and a[:n] == b[:n], (a[:16], b[:16])
