@@ -6,14 +6,15 @@
 // matrix; V is consumed MN-major so no transpose is ever materialised; the mask is a predicate on (query, key) indices.
 // Softmax is two-pass (pass 1: row maxima from S tiles, pass 2: P = exp2(S - max) and O accumulation) so O is never
 // read-modify-written: exp throughput, not the tensor pipe, bounds this kernel, and the extra Q K^T costs ~1/4 of it.
-// Warps 0-3: softmax (one query row per thread, TMEM lane == row), warp 4: TMA producer, warp 5: MMA issuer.
+// Warps 0-7: softmax (two threads per query row, one per 64-key half; TMEM lane == row), warp 8: TMA producer,
+// warp 9: MMA issuer.
 // Two CTAs are co-resident per SM (TMEM 2 x 256 columns, smem 2 x ~112 KB) so one CTA's exps overlap the other's MMAs.
 #include "common.cuh"
 
 namespace {
 
 constexpr int AT_BQ = 128, AT_BK = 128, AT_HD = 64;
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;   // warps 0-7 softmax (2 threads per query row: key halves), warp 8 TMA, warp 9 MMA
 constexpr uint32_t Q_BYTES = AT_BQ * AT_HD * 2;        // 16 KB
 constexpr uint32_t K_BYTES = AT_BK * AT_HD * 2;        // 16 KB
 constexpr uint32_t V_BYTES = AT_BK * AT_HD * 2;        // 16 KB
@@ -89,6 +90,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_q, bar_s, bar_p, bar_o;
   __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][AT_BQ];   // row max / row sum exchange between the two threads of a row
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int L = len[b], s0 = start[b];
@@ -110,7 +112,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar_q), 1);
     mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
+    mbar_init(smem_u32(&bar_p), 256);
     mbar_init(smem_u32(&bar_o), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -118,7 +120,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -127,7 +129,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tS = tmem_slot, tO = tmem_slot + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
       tma_load_2d(sQ, &tmq, smem_u32(&bar_q), h * AT_HD, s0 + i0);
@@ -143,7 +145,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, s0 + tile * AT_BK);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       mbar_wait(smem_u32(&bar_q), 0);
       for (int it = 0; it < iters; ++it) {
@@ -173,53 +175,69 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       umma_commit(smem_u32(&bar_o));
     }
   } else {
-    // softmax warps: thread <-> query row
-    const int row = warp * 32 + lane;
+    // softmax warps: two threads per query row (key halves [0,64) and [64,128) of every tile)
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
     const int i = i0 + row;
     const int klim = i < L ? (chunk > 0 ? min(L, (i / chunk + 1) * chunk) : L) : 0;
-    const uint32_t trow = ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = ((uint32_t)(q4 * 32) << 16);
+    const int cbase = half * 64;
     float m = -INFINITY;
     for (int it = 0; it < ntiles; ++it) {
       mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int j0 = it * AT_BK;
+      const int j0 = it * AT_BK + cbase;
+      const bool full = j0 + 64 <= klim;
 #pragma unroll 1
-      for (int c = 0; c < AT_BK; c += 16) {
+      for (int c = 0; c < 64; c += 16) {
         float v[16];
-        tmem_ld16(tS + trow + (uint32_t)c, v);
+        tmem_ld16(tS + trow + (uint32_t)(cbase + c), v);
+        if (full) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (j0 + c + e < klim) m = fmaxf(m, v[e]);
+          for (int e = 0; e < 16; ++e) m = fmaxf(m, v[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (j0 + c + e < klim) m = fmaxf(m, v[e]);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&bar_p));
     }
+    xch[half][row] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(xch[0][row], xch[1][row]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const float mneg = (m == -INFINITY) ? 0.f : -m * scale_log2e;
     float lsum = 0.f;
-    const uint32_t prow = sP + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const uint32_t prow = sP + (uint32_t)half * (AT_BQ * 128) + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
     for (int t = 0; t < ntiles; ++t) {
       const int it = ntiles + t;
       mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int j0 = t * AT_BK;
+      const int j0 = t * AT_BK + cbase;
+      const bool full = j0 + 64 <= klim;
 #pragma unroll 1
-      for (int c = 0; c < AT_BK; c += 16) {
+      for (int c = 0; c < 64; c += 16) {
         float v[16];
-        tmem_ld16(tS + trow + (uint32_t)c, v);
+        tmem_ld16(tS + trow + (uint32_t)(cbase + c), v);
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-          float p0 = (j0 + c + e < klim) ? exp2f(fmaf(v[e], scale_log2e, mneg)) : 0.f;
-          float p1 = (j0 + c + e + 1 < klim) ? exp2f(fmaf(v[e + 1], scale_log2e, mneg)) : 0.f;
+          float p0 = fast_ex2(fmaf(v[e], scale_log2e, mneg));
+          float p1 = fast_ex2(fmaf(v[e + 1], scale_log2e, mneg));
+          if (!full) {
+            if (j0 + c + e >= klim) p0 = 0.f;
+            if (j0 + c + e + 1 >= klim) p1 = 0.f;
+          }
           lsum += p0 + p1;
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        // keys c..c+15 -> 16-B chunks (c/8) and (c/8+1) of sub-tile c/64, XOR-swizzled by (row & 7)
-        const uint32_t sub = prow + (uint32_t)(c >> 6) * (AT_BQ * 128);
-        const uint32_t ch = (uint32_t)((c & 63) >> 3);
-        const uint32_t a0 = sub + (((ch) ^ (uint32_t)(row & 7)) << 4);
-        const uint32_t a1 = sub + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
+        // keys c..c+15 of this half -> 16-B chunks (c/8) and (c/8+1), XOR-swizzled by (row & 7)
+        const uint32_t ch = (uint32_t)(c >> 3);
+        const uint32_t a0 = prow + (((ch) ^ (uint32_t)(row & 7)) << 4);
+        const uint32_t a1 = prow + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       }
@@ -227,11 +245,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&bar_p));
     }
+    xch[half][row] = lsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    lsum = xch[0][row] + xch[1][row];
     mbar_wait(smem_u32(&bar_o), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
 #pragma unroll 1
-    for (int c = 0; c < AT_HD; c += 16) {
+    for (int c = half * 32; c < half * 32 + 32; c += 16) {
       float v[16];
       tmem_ld16(tO + trow + (uint32_t)c, v);
       if (i < L) {
@@ -246,7 +267,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
   }
 }

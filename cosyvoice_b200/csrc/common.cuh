@@ -86,7 +86,54 @@ __device__ __forceinline__ float apply_act(int act, float x, float param, float 
   }
 }
 
+// bf16-mode variants: hardware approximations (ex2.approx / tanh.approx / sin.approx, fast division).  Their error
+// (<= ~1e-6 absolute on O(1) values) is two orders below the bf16 rounding of the stored result.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return fast_ex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float apply_act_fast(int act, float x, float param, float alpha) {
+  switch (act) {
+    case ACT_GELU: {
+      // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z)
+      float z = fabsf(x) * 0.70710678118654752440f;
+      float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+      float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+      float erfz = 1.f - poly * fast_exp(-z * z);
+      return 0.5f * x * (1.f + copysignf(erfz, x));
+    }
+    case ACT_SILU: return __fdividef(x, 1.f + fast_exp(-x));
+    case ACT_MISH: {
+      // x * tanh(log(1 + e^x)) = x * e(e+2) / (e(e+2) + 2)
+      float e = fast_exp(fminf(x, 20.f));
+      float n = e * (e + 2.f);
+      return x > 20.f ? x : x * __fdividef(n, n + 2.f);
+    }
+    case ACT_ELU: return x > 0.f ? x : fast_exp(x) - 1.f;
+    case ACT_LRELU: return x > 0.f ? x : x * param;
+    case ACT_SNAKE: {
+      float s = __sinf(x * alpha);
+      return fmaf(__fdividef(1.f, alpha + 1e-9f), s * s, x);
+    }
+    case ACT_TANH: return fast_tanh(x);
+    case ACT_ABS: return fabsf(x);
+    default: return x;
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float act_sel(int act, float x, float param, float alpha) {
+  return FAST ? apply_act_fast(act, x, param, alpha) : apply_act(act, x, param, alpha);
+}
+
 // One output element through the fused epilogue (see struct Epilogue in cvk_internal.h).
+template <bool FAST = false>
 __device__ __forceinline__ void epi_store(const EpiDev& e, int r, int n, float acc) {
   int seq = 0;
   bool valid = true;
@@ -97,14 +144,14 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, int r, int n, float a
   float v = acc;
   if (e.bias) v += e.bias[n];
   if (e.rowvec && valid) v += e.rowvec[(size_t)seq * e.rowvec_ld + n];
-  v = apply_act(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1[n] : 1.f) * e.scale;
+  v = act_sel<FAST>(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1[n] : 1.f) * e.scale;
   if (e.resid) v += e.resid[(size_t)r * e.resid_ld + n];
   if (!valid) v = 0.f;
   size_t o = (size_t)r * e.out_ld + n;
   if (e.accumulate) v += ld_any(e.out, e.out_dtype, o);
   st_any(e.out, e.out_dtype, o, v);
   if (e.out2) {
-    float w = valid ? apply_act(e.act2, v, e.act2_param, e.alpha2 ? e.alpha2[n] : 1.f) : 0.f;
+    float w = valid ? act_sel<FAST>(e.act2, v, e.act2_param, e.alpha2 ? e.alpha2[n] : 1.f) : 0.f;
     st_any(e.out2, e.out2_dtype, (size_t)r * e.out2_ld + n, w);
   }
 }

@@ -3,8 +3,8 @@
 //   out[r, n] = epilogue( sum_{j<taps} sum_{k<K} A[r + shift0 + j*dil, k] * W[n][j][k] ),  fp32 accumulate
 //
 // One CTA computes a 128 x BN output tile.  Warp 0 is the TMA producer, warp 1 allocates TMEM and issues the
-// MMAs (single elected lane), warps 2-5 run the fused epilogue straight out of TMEM (one accumulator row per
-// thread).  A convolution tap is just a row-shifted TMA box of the time-major activation matrix; rows outside the
+// MMAs (single elected lane), warps 2-9 run the fused epilogue straight out of TMEM (one accumulator row per
+// thread, two warps per 32-row lane quarter splitting the columns).  A convolution tap is just a row-shifted TMA box of the time-major activation matrix; rows outside the
 // matrix and the K tail are zero-filled by the TMA unit, gap rows between ragged sequences hold zeros in memory.
 // Two CTAs are co-resident per SM (3 stages x 32 KB each) so one CTA's epilogue overlaps the other's main loop.
 //
@@ -18,7 +18,7 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quarter, half the columns each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -88,7 +88,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // 16 consecutive columns of one row through the fused epilogue (vector fast path + scalar tail).
 __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int N, const float* acc) {
   if (n0 + 16 > N) {
-    for (int i = 0; i < 16 && n0 + i < N; ++i) epi_store(e, r, n0 + i, acc[i]);
+    for (int i = 0; i < 16 && n0 + i < N; ++i) epi_store<true>(e, r, n0 + i, acc[i]);
     return;
   }
   int seq = 0;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
   }
   if (e.act1 != ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act1, v[i], e.act1_param, e.alpha1 ? e.alpha1[n0 + i] : 1.f);
+    for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act1, v[i], e.act1_param, e.alpha1 ? e.alpha1[n0 + i] : 1.f);
   }
   if (e.scale != 1.f) {
 #pragma unroll
@@ -160,7 +160,7 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
     float w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      w[i] = valid ? apply_act(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
+      w[i] = valid ? apply_act_fast(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
     size_t o2 = (size_t)r * e.out2_ld + n0;
     if (e.out2_dtype == DT_F32) {
       float* op = (float*)e.out2 + o2;
@@ -256,12 +256,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     mbar_wait(smem_u32(&bar_acc), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int r = r0 + q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
+    for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
       if (n0 + c >= N) break;   // warp-uniform
       float acc[16];
       tmem_ld16(trow + (uint32_t)c, acc);
