@@ -88,15 +88,19 @@ void cvk_destroy(cvk_ctx* ctx) {
 
 const char* cvk_last_error(cvk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double cvk_last_op_ms(cvk_ctx* ctx) { return ctx ? ctx->op_ms : 0.0; }
 
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   CVK_API_BEGIN
   std::string k(key ? key : "");
   if (k == "use_tc") ctx->use_tc = value;
   else if (k == "tc_bn256") ctx->tc_bn256 = value;
+  else if (k == "tc_epi") ctx->tc_epi = value;
+  else if (k == "op_iters") ctx->op_iters = value;
   else if (k == "use_graph") ctx->use_graph = value;
   else if (k == "use_tc_attn") ctx->use_tc_attn = value;
   else if (k == "use_skinny") ctx->use_skinny = value;
+  else if (k == "lm_fused") ctx->lm_fused = value;
   else if (k == "debug_timeline") {
     if (value && !ctx->dbg) {
       ctx->dbg = ctx->dmalloc(1024 * sizeof(long long));
@@ -202,6 +206,18 @@ int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens, int B, int K, c
     conv_gemm_simt(ctx, st, a32, W, e);
   } else {
     conv_gemm(ctx, st, a, W, e);
+    if (ctx->op_iters > 0) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+      for (int i = 0; i < ctx->op_iters; ++i) conv_gemm(ctx, st, a, W, e);
+      cudaEventRecord(e1, st);
+      CVK_CHECK_CUDA(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ctx->op_ms = ms / ctx->op_iters;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
   }
   unpack_rows(ctx, st, o, s, 0, out, N);
   CVK_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -239,7 +255,7 @@ int cvk_op_linear_small(cvk_ctx* ctx, const float* x, int rows, int K, const flo
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
-  if (timeline_host && ctx->dbg) CVK_CHECK_CUDA(cudaMemcpy(timeline_host, ctx->dbg, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (timeline_host && ctx->dbg) CVK_CHECK_CUDA(cudaMemcpy(timeline_host, ctx->dbg, 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   ctx->tiled.erase(W.w16);
   for (size_t i = owned_mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);

@@ -159,6 +159,9 @@ struct cvk_ctx {
   void* mel_model = nullptr;
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
+  int op_iters = 0;                         // cvk_op_conv1d: repeat the GEMM launch this many times and time it
+  double op_ms = 0.0;
+  int tc_epi = 2;                           // tcgen05 GEMM epilogue: 2 = smem-staged TMA stores, 0 = direct stores, 1 = direct + prefetch
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
   void* dbg = nullptr;                      // device int64[1024] timeline buffer (debug option)
   int prof_on = 0;
@@ -166,6 +169,7 @@ struct cvk_ctx {
   std::vector<ProfRec> prof;
   std::unordered_map<const void*, void*> tiled;   // bf16 weight -> streaming (pre-tiled, pre-swizzled) copy for the skinny GEMM
   std::vector<cudaEvent_t> event_pool;
+  int lm_fused = 1;                         // LM decode: fused finish+rmsnorm / rope+attention / SwiGLU-epilogue kernels
   int use_skinny = 1;                       // LM decode GEMMs on the weight-streaming split-K kernel
   int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)
   int use_graph = 1;                        // LM decode step replayed as a CUDA graph
@@ -205,6 +209,9 @@ void conv_gemm_simt(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W,
 void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep);
 size_t skinny_scratch_floats(int rows, int maxN);
 const bf16* skinny_tiled_weights(cvk_ctx* ctx, const ConvW& W);
+void skinny_set_carveout();
+int conv_gemm_skinny_ex(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats,
+                        int mode);
 void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats);
 
 // elementwise / normalisation (elementwise.cu)

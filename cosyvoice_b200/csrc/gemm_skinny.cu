@@ -103,8 +103,11 @@ __global__ void tile_weights_kernel(const bf16* __restrict__ w, bf16* __restrict
 template <int BPAD>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUtensorMap tmap_x, int N, int K, int rows,
-                   int chunks_per_split, float* __restrict__ partial /*[splits][rows][N] or null*/, EpiDev ep, long long* __restrict__ dbg) {
+                   int chunks_per_split, float* __restrict__ partial /*[splits][rows][N] or null*/, EpiDev ep, int swiglu,
+                   long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
+  long long t_entry = 0;
+  if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_entry));
   __shared__ __align__(8) uint64_t bar_full[SK_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[SK_STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
@@ -141,6 +144,13 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
   const uint32_t tmem = tmem_slot;
   const bool trace = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (trace && threadIdx.x == 0) dbg[0] = clock64();
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  if (dbg && threadIdx.x == 0 && cta_lin < 200) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    dbg[128 + cta_lin * 4 + 0] = t_entry;
+    dbg[128 + cta_lin * 4 + 1] = t;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -173,8 +183,15 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     }
   } else {
     const int q = warp & 3;
+    const int n_pre = n0 + q * 32 + lane;
+    const float bias_n = (!partial && !swiglu && ep.bias && n_pre < N) ? ep.bias[n_pre] : 0.f;   // fetched while the weights stream
     mbar_wait(smem_u32(&bar_acc), 0);
     if (trace && threadIdx.x == 64) dbg[1] = clock64();
+    if (dbg && threadIdx.x == 64 && cta_lin < 200) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      dbg[128 + cta_lin * 4 + 2] = t;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int n = n0 + q * 32 + lane;          // this thread's output feature
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
@@ -182,21 +199,43 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     for (int c = 0; c < BPAD; c += 16) {
       float acc[16];
       tmem_ld16(trow + (uint32_t)c, acc);
-      if (n < N) {
+      if (trace && threadIdx.x == 64) dbg[3 + (c >> 4)] = clock64();
+      if (swiglu) {
+        // rows of W are interleaved (2i = gate_i, 2i+1 = up_i): lanes pair up, the even lane emits silu(g) * u
+        // (Qwen2 MLP act_fn(gate_proj(x)) * up_proj(x), modeling_qwen2.py:46-48) into column n/2
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float other = __shfl_xor_sync(0xffffffffu, acc[e], 1);
+          const int b = c + e;
+          if (!(lane & 1) && n + 1 < N && b < rows) {
+            const float g = acc[e];
+            st_any(ep.out, ep.out_dtype, (size_t)b * ep.out_ld + (n >> 1), __fdividef(g, 1.f + fast_exp(-g)) * other);
+          }
+        }
+      } else if (n < N) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int b = c + e;
           if (b < rows) {
             if (partial) partial[((size_t)blockIdx.y * rows + b) * N + n] = acc[e];
+            else if (ep.act1 == ACT_NONE && !ep.resid && !ep.rowvec && !ep.row2seq && !ep.accumulate && !ep.out2 && ep.scale == 1.f)
+              st_any(ep.out, ep.out_dtype, (size_t)b * ep.out_ld + n, acc[e] + bias_n);   // plain Linear (+bias): no loads in the store loop
             else epi_store(ep, b, n, acc[e]);
           }
         }
       }
     }
   }
+  if (trace && threadIdx.x == 64) dbg[5] = clock64();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (trace && threadIdx.x == 64) dbg[6] = clock64();
   if (trace && threadIdx.x == 0) dbg[2] = clock64();
+  if (dbg && threadIdx.x == 0 && cta_lin < 200) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    dbg[128 + cta_lin * 4 + 3] = t;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(BPAD < 32 ? 32 : BPAD)) : "memory");
   }
@@ -218,14 +257,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 template <int BPAD>
 void launch(cudaStream_t st, dim3 grid, const bf16* tw, const CUtensorMap& tx, const ConvW& W, int rows, int cps, float* partial,
-            const EpiDev& e, long long* dbg) {
+            const EpiDev& e, int swiglu, long long* dbg) {
   constexpr size_t smem = (size_t)SK_STAGES * (SK_BM * SK_BK * 2 + BPAD * SK_BK * 2) + 1024;
   static bool attr = false;
   if (!attr) {
     CVK_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  skinny_gemm_kernel<BPAD><<<grid, SK_THREADS, smem, st>>>(tw, tx, W.N, W.K, rows, cps, partial, e, dbg);
+  skinny_gemm_kernel<BPAD><<<grid, SK_THREADS, smem, st>>>(tw, tx, W.N, W.K, rows, cps, partial, e, swiglu, dbg);
 }
 
 }  // namespace
@@ -248,9 +287,12 @@ const bf16* skinny_tiled_weights(cvk_ctx* ctx, const ConvW& W) {
 // scratch: device buffer of at least skinny_scratch_floats() floats, owned by the caller (LM session: stable across graph replays)
 size_t skinny_scratch_floats(int rows, int maxN) { return (size_t)32 * rows * maxN; }
 
-void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats) {
+// mode 0: fused epilogue (split-K reduced by splitk_finish_kernel); mode 1: leave the split-K partial sums [splits][rows][N]
+// in `scratch` for a fused consumer (returns the split count); mode 2: no split, SwiGLU epilogue on interleaved gate/up rows
+int conv_gemm_skinny_ex(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats,
+                        int mode) {
   CVK_REQUIRE(A.dtype == DT_BF16 && W.w16 != nullptr && W.taps == 1, "conv_gemm_skinny: bf16 1-tap operands required");
-  const int rows = ep.out.rows;
+  const int rows = mode == 1 ? A.rows : ep.out.rows;
   CVK_REQUIRE(rows <= 64 && A.rows >= rows, "conv_gemm_skinny: at most 64 rows");
   CVK_REQUIRE(W.K % 8 == 0 && A.ld % 8 == 0 && ((uintptr_t)A.p & 15) == 0, "conv_gemm_skinny: 16-byte aligned operands required");
   if (!ctx->encode_tiled) {
@@ -281,22 +323,23 @@ void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& 
   if (splits < 1) splits = 1;
   int cps = ceil_div(kchunks, splits);
   splits = ceil_div(kchunks, cps);                   // no empty split
-  if (splits > 1 && (scratch == nullptr || (size_t)splits * rows * W.N > scratch_floats)) {
+  if (mode == 2 || (splits > 1 && (scratch == nullptr || (size_t)splits * rows * W.N > scratch_floats))) {
     splits = 1;
     cps = kchunks;
   }
+  CVK_REQUIRE(mode != 1 || (scratch != nullptr && (size_t)splits * rows * W.N <= scratch_floats), "conv_gemm_skinny: scratch too small");
   EpiDev e = to_dev(ep);
   if (!e.bias) e.bias = W.bias;
   const double flops = 2.0 * rows * (double)W.N * W.K;
-  const double bytes = (double)W.N * W.K * 2 + (double)rows * W.K * 2 + (double)rows * W.N * ep.out.esize();
+  const double bytes = (double)W.N * W.K * 2 + (double)rows * W.K * 2 + (double)rows * W.N * 2;
   ProfScope ps(ctx, st, FAM_GEMM_TC, flops, bytes);
   dim3 grid(tiles, splits);
-  float* partial = splits > 1 ? scratch : nullptr;
-  if (BPAD == 32) launch<32>(st, grid, tw, tx, W, rows, cps, partial, e, (long long*)ctx->dbg);
-  else launch<64>(st, grid, tw, tx, W, rows, cps, partial, e, (long long*)ctx->dbg);
+  float* partial = (splits > 1 || mode == 1) ? scratch : nullptr;
+  if (BPAD == 32) launch<32>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg);
+  else launch<64>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
-  if (splits > 1) {
+  if (splits > 1 && mode == 0) {
     size_t total = (size_t)rows * W.N;
     int g = (int)((total + 255) / 256);
     if (g > 148 * 4) g = 148 * 4;
@@ -304,4 +347,15 @@ void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& 
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }
+  return splits;
+}
+
+void conv_gemm_skinny(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep, float* scratch, size_t scratch_floats) {
+  conv_gemm_skinny_ex(ctx, st, A, W, ep, scratch, scratch_floats, 0);
+}
+
+void skinny_set_carveout() {
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(splitk_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }

@@ -17,7 +17,6 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B atom row
-constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quarter, half the columns each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,15 +176,107 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
   }
 }
 
-template <int BN>
+// values of 16 consecutive columns of one row (fused epilogue math, no stores); columns >= N yield 0
+__device__ __forceinline__ void epi_math16(const EpiDev& e, int r, bool rin, int n0, int N, const float* acc, float* v, float* w2) {
+  int seq = 0;
+  bool valid = rin;
+  if (rin && e.row2seq) {
+    seq = e.row2seq[r];
+    valid = seq >= 0;
+  }
+  const bool full = n0 + 16 <= N;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = acc[i];
+  if (full) {
+    if (e.bias) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+    if (e.rowvec && valid) {
+      const float* rv = e.rowvec + (size_t)seq * e.rowvec_ld + n0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += rv[i];
+    }
+    if (e.act1 != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act1, v[i], e.act1_param, e.alpha1 ? e.alpha1[n0 + i] : 1.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= e.scale;
+    if (e.resid && rin) {
+      const float* rp = e.resid + (size_t)r * e.resid_ld + n0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 b = *reinterpret_cast<const float4*>(rp + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  } else {
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      float t = 0.f;
+      if (n < N) {
+        t = v[i] + (e.bias ? e.bias[n] : 0.f);
+        if (e.rowvec && valid) t += e.rowvec[(size_t)seq * e.rowvec_ld + n];
+        t = apply_act_fast(e.act1, t, e.act1_param, e.alpha1 ? e.alpha1[n] : 1.f) * e.scale;
+        if (e.resid && rin) t += e.resid[(size_t)r * e.resid_ld + n];
+      }
+      v[i] = t;
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  }
+  if (e.out2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      w2[i] = (valid && n0 + i < N) ? apply_act_fast(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
+  }
+}
+
+// 16 consecutive columns of one tile row into a SWIZZLE_128B staging tile (128-byte wide sub-tiles of 128 rows, 16 KB each)
+__device__ __forceinline__ void stage_store16(uint32_t stg, int dtype, int row, int c, const float* v) {
+  if (dtype == DT_BF16) {
+    const uint32_t sub = stg + (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
+    const uint32_t ch = (uint32_t)((c & 63) >> 3);
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i], v[i + 1]);
+      pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sub + ((ch ^ (uint32_t)(row & 7)) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sub + (((ch + 1) ^ (uint32_t)(row & 7)) << 4)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+  } else {
+    const uint32_t sub = stg + (uint32_t)(c >> 5) * 16384u + (uint32_t)row * 128u;
+    const uint32_t ch = (uint32_t)((c & 31) >> 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sub + (((ch + j) ^ (uint32_t)(row & 7)) << 4)), "r"(__float_as_uint(v[4 * j])),
+                   "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3]))
+                   : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int N, int K, int taps,
-                    int dil, int shift0, int rowsOut, EpiDev ep) {
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, int N, int K, int taps,
+                    int dil, int shift0, int rowsOut, EpiDev ep, int epi_mode) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_bias[BN], s_a1[BN], s_a2[BN];
 
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
@@ -254,19 +345,156 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       umma_commit(smem_u32(&bar_acc));          // accumulator complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only.  Everything that does not depend on the accumulator
+    // (row validity, bias / Snake alphas -> shared memory, first residual chunk) is fetched while the main loop runs, and
+    // the global loads of chunk c+1 are issued before the stores of chunk c (stores would otherwise fence the loads:
+    // the compiler cannot prove the epilogue pointers do not alias, and each chunk would pay a full L2 round trip).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int r = r0 + q * 32 + lane;
+    const bool rin = r < rowsOut;
+    if (epi_mode == 2) {
+      // coalesced output: the tile is staged in shared memory (the operand stages are free once the accumulator is
+      // complete) in SWIZZLE_128B sub-tiles and written by TMA stores - full 128-byte lines instead of one 32/64-byte
+      // piece per thread per row; rows / columns outside the matrix are clipped by the tensor map.
+      mbar_wait(smem_u32(&bar_acc), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int row = q * 32 + lane;
+      const uint32_t stg1 = smem_base;
+      const uint32_t stg2 = smem_base + (uint32_t)TC_BM * BN * (ep.out_dtype == DT_F32 ? 4u : 2u);
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+        if (n0 + c >= N) break;
+        float acc[16], v[16], w2[16];
+        tmem_ld16(trow0 + (uint32_t)c, acc);
+        epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
+        stage_store16(stg1, ep.out_dtype, row, c, v);
+        if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int w1 = ep.out_dtype == DT_F32 ? 32 : 64;
+        for (int sb = 0; sb * w1 < BN && n0 + sb * w1 < N; ++sb) tma_store_2d(&tmap_o, stg1 + sb * 16384u, n0 + sb * w1, r0);
+        if (ep.out2) {
+          const int w2c = ep.out2_dtype == DT_F32 ? 32 : 64;
+          for (int sb = 0; sb * w2c < BN && n0 + sb * w2c < N; ++sb) tma_store_2d(&tmap_o2, stg2 + sb * 16384u, n0 + sb * w2c, r0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    } else if (epi_mode == 0) {   // simple epilogue: loads inside the per-chunk routine
+      mbar_wait(smem_u32(&bar_acc), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+        if (n0 + c >= N) break;
+        float acc[16];
+        tmem_ld16(trow0 + (uint32_t)c, acc);
+        if (rin) epi_store16(ep, r, n0 + c, N, acc);
+      }
+    } else {
+    int seq = 0;
+    bool valid = rin;
+    if (rin && ep.row2seq) {
+      seq = ep.row2seq[r];
+      valid = seq >= 0;
+    }
+    for (int i = threadIdx.x - 64; i < BN; i += 256) {
+      const int n = n0 + i;
+      s_bias[i] = (ep.bias && n < N) ? ep.bias[n] : 0.f;
+      s_a1[i] = (ep.alpha1 && n < N) ? ep.alpha1[n] : 1.f;
+      s_a2[i] = (ep.alpha2 && n < N) ? ep.alpha2[n] : 1.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int c_begin = half * (BN / 2), c_end = (half + 1) * (BN / 2);
+    const float* pa_src = nullptr;      // residual row or per-sequence vector row (never both: checked on the host)
+    if (ep.resid && rin) pa_src = ep.resid + (size_t)r * ep.resid_ld + n0;
+    else if (ep.rowvec && valid) pa_src = ep.rowvec + (size_t)seq * ep.rowvec_ld + n0;
+    const bool pa_is_resid = ep.resid != nullptr;
+    const float* pb_src = (ep.accumulate && rin && ep.out_dtype == DT_F32) ? (const float*)ep.out + (size_t)r * ep.out_ld + n0 : nullptr;
+    float4 pa[4], pb[4];
+    auto prefetch = [&](int c) {
+      const bool full = n0 + c + 16 <= N;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pa[i] = (pa_src && full) ? *reinterpret_cast<const float4*>(pa_src + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[i] = (pb_src && full) ? *reinterpret_cast<const float4*>(pb_src + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (n0 + c_begin < N) prefetch(c_begin);
     mbar_wait(smem_u32(&bar_acc), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int r = r0 + q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+    for (int c = c_begin; c < c_end; c += 16) {
       if (n0 + c >= N) break;   // warp-uniform
       float acc[16];
       tmem_ld16(trow + (uint32_t)c, acc);
-      if (r < rowsOut) epi_store16(ep, r, n0 + c, N, acc);
+      if (n0 + c + 16 > N) {    // ragged last chunk: scalar path
+        if (rin)
+          for (int i = 0; i < 16 && n0 + c + i < N; ++i) epi_store<true>(ep, r, n0 + c + i, acc[i]);
+        continue;
+      }
+      float v[16];
+      const float av[16] = {pa[0].x, pa[0].y, pa[0].z, pa[0].w, pa[1].x, pa[1].y, pa[1].z, pa[1].w,
+                            pa[2].x, pa[2].y, pa[2].z, pa[2].w, pa[3].x, pa[3].y, pa[3].z, pa[3].w};
+      const float bv[16] = {pb[0].x, pb[0].y, pb[0].z, pb[0].w, pb[1].x, pb[1].y, pb[1].z, pb[1].w,
+                            pb[2].x, pb[2].y, pb[2].z, pb[2].w, pb[3].x, pb[3].y, pb[3].z, pb[3].w};
+      if (c + 16 < c_end && n0 + c + 16 < N) prefetch(c + 16);   // next chunk's loads go out before this chunk's stores
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float t = acc[i] + s_bias[c + i];
+        if (!pa_is_resid) t += av[i];
+        if (ep.act1 != ACT_NONE) t = apply_act_fast(ep.act1, t, ep.act1_param, s_a1[c + i]);
+        t *= ep.scale;
+        if (pa_is_resid) t += av[i];
+        if (!valid) t = 0.f;
+        v[i] = t;
+      }
+      if (!rin) continue;
+      const size_t o = (size_t)r * ep.out_ld + n0 + c;
+      if (ep.out_dtype == DT_F32) {
+        float* op = (float*)ep.out + o;
+        if (ep.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += bv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+        bf16* op = (bf16*)ep.out + o;
+        if (ep.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(op[i]);
+        }
+        __align__(16) bf16 tt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tt[i] = __float2bfloat16_rn(v[i]);
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(tt);
+        *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(tt + 8);
+      }
+      if (ep.out2) {
+        float w2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w2[i] = valid ? apply_act_fast(ep.act2, v[i], ep.act2_param, s_a2[c + i]) : 0.f;
+        const size_t o2 = (size_t)r * ep.out2_ld + n0 + c;
+        if (ep.out2_dtype == DT_F32) {
+          float* op = (float*)ep.out2 + o2;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(w2[i], w2[i + 1], w2[i + 2], w2[i + 3]);
+        } else {
+          bf16* op = (bf16*)ep.out2 + o2;
+          __align__(16) bf16 tt[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tt[i] = __float2bfloat16_rn(w2[i]);
+          *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(tt);
+          *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(tt + 8);
+        }
+      }
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -291,17 +519,17 @@ EncodeTiledFn get_encode(cvk_ctx* ctx) {
   return (EncodeTiledFn)ctx->encode_tiled;
 }
 
-template <int BN>
-void launch_tc(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const ConvW& W, int rowsOut,
-               const EpiDev& e) {
+template <int BN, int TC_STAGES>
+void launch_tc(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& to2,
+               const ConvW& W, int rowsOut, const EpiDev& e, int epi_mode) {
   constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    CVK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid(ceil_div(W.N, BN), ceil_div(rowsOut, TC_BM));
-  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ta, tw, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e);
+  conv_gemm_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, epi_mode);
 }
 
 }  // namespace
@@ -337,13 +565,38 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
   int rowsOut = ep.out.rows;
   CVK_REQUIRE((ep.out.ld * ep.out.esize()) % 16 == 0 && ((uintptr_t)ep.out.p & 15) == 0, "conv_gemm_tc: output rows must be 16-byte aligned");
   CVK_REQUIRE(!ep.resid.p || (ep.resid.ld % 4 == 0 && ((uintptr_t)ep.resid.p & 15) == 0), "conv_gemm_tc: residual alignment");
+  CVK_REQUIRE(!(ep.resid.p && ep.rowvec), "conv_gemm_tc: residual and per-sequence vector cannot be combined");
+  CVK_REQUIRE(!ep.rowvec || (ep.rowvec_ld % 4 == 0 && ((uintptr_t)ep.rowvec & 15) == 0), "conv_gemm_tc: rowvec alignment");
   CVK_REQUIRE(!ep.out2.p || ((ep.out2.ld * ep.out2.esize()) % 16 == 0 && ((uintptr_t)ep.out2.p & 15) == 0), "conv_gemm_tc: out2 alignment");
   const double flops = 2.0 * rowsOut * (double)W.N * W.K * W.taps;
   const double bytes = (double)rowsOut * W.K * 2 + (double)W.N * W.K * W.taps * 2 + (double)rowsOut * W.N * ep.out.esize();
   ProfScope ps(ctx, st, FAM_GEMM_TC, flops, bytes);
-  if (BN == 256) launch_tc<256>(ctx, st, ta, tw, W, rowsOut, e);
-  else if (BN == 128) launch_tc<128>(ctx, st, ta, tw, W, rowsOut, e);
-  else launch_tc<64>(ctx, st, ta, tw, W, rowsOut, e);
+  // epilogue mode: 2 = staged TMA stores (default when the tile fits the free operand stages and no read-modify-write of
+  // the output is needed), 0 = direct per-thread stores, 1 = direct stores with software-pipelined loads (experiment)
+  int epi_mode = ctx->tc_epi;
+  CUtensorMap to = ta, to2 = ta;
+  if (epi_mode == 2) {
+    const int stages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    const size_t stage_bytes = (size_t)stages * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+    const size_t need = (size_t)TC_BM * BN * ep.out.esize() + (ep.out2.p ? (size_t)TC_BM * BN * ep.out2.esize() : 0);
+    if (ep.accumulate || need > stage_bytes) epi_mode = 0;
+  }
+  if (epi_mode == 2) {
+    auto mk = [&](CUtensorMap* m, const Mat& o) {
+      cuuint64_t dims[2] = {(cuuint64_t)W.N, (cuuint64_t)rowsOut};
+      cuuint64_t strides[1] = {(cuuint64_t)o.ld * o.esize()};
+      cuuint32_t box[2] = {(cuuint32_t)(o.dtype == DT_F32 ? 32 : 64), TC_BM};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(m, o.dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, o.p, dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CVK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed: " + std::to_string((int)r));
+    };
+    mk(&to, ep.out);
+    if (ep.out2.p) mk(&to2, ep.out2);
+  }
+  if (BN == 256) launch_tc<256, 2>(ctx, st, ta, tw, to, to2, W, rowsOut, e, epi_mode);      // 2 x 48 KB stages: two CTAs (2 x 256 TMEM columns) per SM
+  else if (BN == 128) launch_tc<128, 3>(ctx, st, ta, tw, to, to2, W, rowsOut, e, epi_mode);
+  else launch_tc<64, 4>(ctx, st, ta, tw, to, to2, W, rowsOut, e, epi_mode);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

@@ -22,6 +22,7 @@ constexpr int SAMPLER_THREADS = 256, TOPK = 25, WIN = 10;
 struct LayerW {
   float *ln1, *ln2;
   ConvW qkv, o, gate_up, down;
+  ConvW gate_up_il;   // rows interleaved (2i = gate_i, 2i+1 = up_i) for the SwiGLU epilogue of the decode GEMM
 };
 }  // namespace
 
@@ -239,6 +240,166 @@ decode_attn_kernel(const T* __restrict__ qkv, int ld, const T* __restrict__ kc, 
   op[lane + 32] = from_f32<T>(o1 * inv);
 }
 
+// ---- fused decode kernels (bf16 path) -----------------------------------------------------------------------------
+// x[b] += sum_s partial[s][b] (+bias); xn[b] = rmsnorm(x[b]) * gamma  - split-K reduction, residual add and the next
+// RMSNorm (modeling_qwen2.py:258-263) in one pass; one CTA per row.
+__global__ void __launch_bounds__(D) finish_rms_kernel(const float* __restrict__ partial, int splits, int rows, float* __restrict__ x,
+                                                       const float* __restrict__ gamma, bf16* __restrict__ xn) {
+  __shared__ float red[D / 32];
+  const int b = blockIdx.x, n = threadIdx.x;
+  const float* p = partial + (size_t)b * D + n;
+  const size_t stride = (size_t)rows * D;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {      // independent loads in flight (a plain loop is one L2 round trip per split)
+    a0 += p[(size_t)s * stride];
+    a1 += p[(size_t)(s + 1) * stride];
+    a2 += p[(size_t)(s + 2) * stride];
+    a3 += p[(size_t)(s + 3) * stride];
+  }
+  for (; s < splits; ++s) a0 += p[(size_t)s * stride];
+  const float v = x[(size_t)b * D + n] + ((a0 + a1) + (a2 + a3));
+  x[(size_t)b * D + n] = v;
+  float ss = warp_sum(v * v);
+  if ((n & 31) == 0) red[n >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < D / 32; ++i) tot += red[i];
+  xn[(size_t)b * D + n] = __float2bfloat16_rn(gamma[n] * (v * rsqrtf(tot / D + RMS_EPS)));
+}
+
+// qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head), FOUR warps per
+// query head of the group (keys interleaved across them, flash-decoding style combine through shared memory).
+constexpr int AF_PARTS = 4;
+__global__ void __launch_bounds__((NH / NKV) * 32 * AF_PARTS)
+attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int splits, int rows, const float* __restrict__ bias,
+                  bf16* __restrict__ kc, bf16* __restrict__ vc, const int* __restrict__ ctx_len, int max_ctx,
+                  const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo) {
+  extern __shared__ float sm_all[];            // [G][max_ctx] scores | [G+2][64] staging | [G][PARTS][2] max/sum | [G][PARTS][64] partial O
+  constexpr int G = NH / NKV;
+  const int b = blockIdx.x, kvh = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = warp / AF_PARTS, part = warp % AF_PARTS;     // query head of the group, key partition
+  float* stage = sm_all + (size_t)G * max_ctx;
+  float* ml = stage + (G + 2) * HD;
+  float* po = ml + G * AF_PARTS * 2;
+  const int pos = ctx_len[b];
+  for (int e = threadIdx.x; e < (G + 2) * HD; e += blockDim.x) {
+    const int vec = e / HD, d = e % HD;
+    const int col = vec < G ? (kvh * G + vec) * HD + d : (vec == G ? NH * HD + kvh * HD + d : NH * HD + NKV * HD + kvh * HD + d);
+    float acc = bias[col];
+    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * rows + b) * QKV_N + col];
+    stage[e] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (G + 1) * (HD / 2); e += blockDim.x) {     // rotate the G query heads and k
+    const int vec = e / (HD / 2), i = e % (HD / 2);
+    const float fr = (float)pos * inv_freq[i];
+    const float c = cosf(fr), sn = sinf(fr);
+    float* p = stage + vec * HD;
+    const float x1 = p[i], x2 = p[i + HD / 2];
+    p[i] = x1 * c - x2 * sn;
+    p[i + HD / 2] = x2 * c + x1 * sn;
+  }
+  __syncthreads();
+  bf16* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
+  bf16* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
+  if (pos < max_ctx && threadIdx.x < 2 * HD) {
+    const int d = threadIdx.x % HD;
+    if (threadIdx.x < HD) kb[(size_t)pos * HD + d] = __float2bfloat16_rn(stage[G * HD + d]);
+    else vb[(size_t)pos * HD + d] = __float2bfloat16_rn(stage[(G + 1) * HD + d]);
+  }
+  __syncthreads();
+  const int L = min(pos + 1, max_ctx);
+  float* sc = sm_all + (size_t)w * max_ctx;
+  float qr[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) qr[d] = __bfloat162float(__float2bfloat16_rn(stage[w * HD + d])) * 0.125f;
+  float m = -INFINITY;
+  for (int j = part * 32 + lane; j < L; j += 32 * AF_PARTS) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(kb + (size_t)j * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u = k4[c];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h2[e]);
+        s = fmaf(qr[c * 8 + 2 * e], f.x, s);
+        s = fmaf(qr[c * 8 + 2 * e + 1], f.y, s);
+      }
+    }
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  if (lane == 0) ml[(w * AF_PARTS + part) * 2] = m;
+  __syncthreads();
+  float mh = ml[(w * AF_PARTS) * 2];
+#pragma unroll
+  for (int p2 = 1; p2 < AF_PARTS; ++p2) mh = fmaxf(mh, ml[(w * AF_PARTS + p2) * 2]);
+  float l = 0.f;
+  for (int j = part * 32 + lane; j < L; j += 32 * AF_PARTS) {
+    float p = expf(sc[j] - mh);
+    sc[j] = p;
+    l += p;
+  }
+  l = warp_sum(l);
+  if (lane == 0) ml[(w * AF_PARTS + part) * 2 + 1] = l;
+  __syncwarp();
+  // P.V over this warp's keys (the 32 keys of each of its groups are rows j0..j0+31): one pair of output dims per lane
+  float o0 = 0.f, o1 = 0.f;
+  for (int j0 = part * 32; j0 < L; j0 += 32 * AF_PARTS) {
+    const int jn = min(32, L - j0);
+    int jj = 0;
+    for (; jj + 4 <= jn; jj += 4) {
+      const float p0 = sc[j0 + jj], p1 = sc[j0 + jj + 1], p2 = sc[j0 + jj + 2], p3 = sc[j0 + jj + 3];
+      const bf16* v0 = vb + (size_t)(j0 + jj) * HD;
+      const float a0 = __bfloat162float(v0[lane]), a1 = __bfloat162float(v0[lane + 32]);
+      const float b0 = __bfloat162float(v0[HD + lane]), b1 = __bfloat162float(v0[HD + lane + 32]);
+      const float c0 = __bfloat162float(v0[2 * HD + lane]), c1 = __bfloat162float(v0[2 * HD + lane + 32]);
+      const float d0 = __bfloat162float(v0[3 * HD + lane]), d1 = __bfloat162float(v0[3 * HD + lane + 32]);
+      o0 = fmaf(p0, a0, o0); o1 = fmaf(p0, a1, o1);
+      o0 = fmaf(p1, b0, o0); o1 = fmaf(p1, b1, o1);
+      o0 = fmaf(p2, c0, o0); o1 = fmaf(p2, c1, o1);
+      o0 = fmaf(p3, d0, o0); o1 = fmaf(p3, d1, o1);
+    }
+    for (; jj < jn; ++jj) {
+      const float p = sc[j0 + jj];
+      o0 = fmaf(p, __bfloat162float(vb[(size_t)(j0 + jj) * HD + lane]), o0);
+      o1 = fmaf(p, __bfloat162float(vb[(size_t)(j0 + jj) * HD + lane + 32]), o1);
+    }
+  }
+  po[(w * AF_PARTS + part) * HD + lane] = o0;
+  po[(w * AF_PARTS + part) * HD + lane + 32] = o1;
+  __syncthreads();
+  if (part == 0) {
+    float lt = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int p2 = 0; p2 < AF_PARTS; ++p2) {
+      lt += ml[(w * AF_PARTS + p2) * 2 + 1];
+      t0 += po[(w * AF_PARTS + p2) * HD + lane];
+      t1 += po[(w * AF_PARTS + p2) * HD + lane + 32];
+    }
+    bf16* op = out + (size_t)b * ldo + (kvh * G + w) * HD;
+    const float inv = 1.f / lt;
+    op[lane] = __float2bfloat16_rn(t0 * inv);
+    op[lane + 32] = __float2bfloat16_rn(t1 * inv);
+  }
+}
+
+__global__ void interleave_rows_kernel(const float* __restrict__ gu /*[2*F][K]: gate rows then up rows*/, float* __restrict__ out, int F, int K) {
+  size_t total = (size_t)2 * F * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = i % K;
+    int r = i / K;
+    int src = (r & 1) ? F + (r >> 1) : (r >> 1);
+    out[i] = gu[(size_t)src * K + k];
+  }
+}
+
 // SwiGLU: silu(gate) * up; gu = [gate(4864) | up(4864)]
 template <typename T>
 __global__ void swiglu_kernel(const T* __restrict__ gu, int ld, int rows, T* __restrict__ out, int ldo) {
@@ -294,7 +455,8 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
                    int* __restrict__ live,
                    const float* __restrict__ speech_emb, float* __restrict__ next_x,
                    const int32_t* __restrict__ history, int hist_ld, const int32_t* __restrict__ hist_count,
-                   const int32_t* __restrict__ ignore_eos_in, int32_t* __restrict__ ids_out) {
+                   const int32_t* __restrict__ ignore_eos_in, int32_t* __restrict__ ids_out, const float* __restrict__ ln_gamma,
+                   bf16* __restrict__ xn_out) {
   extern __shared__ float sp[];            // V probabilities
   __shared__ float red[SAMPLER_THREADS / 32];
   __shared__ float part[SAMPLER_THREADS];
@@ -475,7 +637,23 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
   // (7) stop / length logic (llm.py:544-549)
   const bool stop = top >= EOS && top <= EOS + 2;
   if (!stop) {
-    for (int c = tid; c < D; c += SAMPLER_THREADS) next_x[(size_t)b * D + c] = speech_emb[(size_t)top * D + c];
+    float ss = 0.f;
+    for (int c = tid; c < D; c += SAMPLER_THREADS) {
+      const float v = speech_emb[(size_t)top * D + c];
+      next_x[(size_t)b * D + c] = v;
+      ss += v * v;
+    }
+    if (xn_out) {   // fused decode path: RMSNorm of the next layer-0 input (input_layernorm of layer 0)
+      ss = warp_sum(ss);
+      __syncthreads();
+      if ((tid & 31) == 0) red[tid >> 5] = ss;
+      __syncthreads();
+      float t2 = 0.f;
+      for (int i = 0; i < SAMPLER_THREADS / 32; ++i) t2 += red[i];
+      const float r = rsqrtf(t2 / D + RMS_EPS);
+      for (int c = tid; c < D; c += SAMPLER_THREADS)
+        xn_out[(size_t)b * D + c] = __float2bfloat16_rn(ln_gamma[c] * (speech_emb[(size_t)top * D + c] * r));
+    }
   }
   if (tid == 0) {
     bool fin = stop;
@@ -644,7 +822,18 @@ void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
     w.gate_up = concat_linear(ctx, {L + ".mlp.gate_proj.weight", L + ".mlp.up_proj.weight"}, {});
     w.down = make_linear(ctx, L + ".mlp.down_proj.weight", "");
     if (ctx->precision == CVK_PREC_BF16) {
+      w.gate_up_il.N = 2 * DFF; w.gate_up_il.K = D;
+      w.gate_up_il.w32 = (float*)ctx->dmalloc((size_t)2 * DFF * D * sizeof(float));
+      interleave_rows_kernel<<<148 * 8, 256>>>(w.gate_up.w32, w.gate_up_il.w32, DFF, D);
+      CVK_LAUNCH_CHECK();
+      finish_convw(ctx, w.gate_up_il);
+    }
+    if (ctx->precision == CVK_PREC_BF16) {
       skinny_tiled_weights(ctx, w.qkv); skinny_tiled_weights(ctx, w.o); skinny_tiled_weights(ctx, w.gate_up); skinny_tiled_weights(ctx, w.down);
+      skinny_tiled_weights(ctx, w.gate_up_il);
+      CVK_CHECK_CUDA(cudaFree(w.gate_up_il.w32));   // only the bf16 streaming copy is used
+      for (auto it = ctx->owned.begin(); it != ctx->owned.end(); ++it) if (*it == (void*)w.gate_up_il.w32) { ctx->owned.erase(it); break; }
+      w.gate_up_il.w32 = nullptr;
     }
     m->layers.push_back(w);
   }
@@ -678,6 +867,14 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   CVK_REQUIRE((NH / NKV) * max_context * sizeof(float) <= 200 * 1024, "session context too long for the decode attention kernel");
   CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
   CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
+  // keep every kernel of the decode step on the same (maximum) shared-memory carveout: alternating carveouts between
+  // consecutive kernels forces an SM reconfiguration (idle + several microseconds) at every boundary
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(finish_rms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  skinny_set_carveout();
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(((size_t)(NH / NKV) * max_context + (NH / NKV + 2) * HD + (NH / NKV) * AF_PARTS * (2 + HD)) * sizeof(float))));
   s->count = (int*)alloc(sizeof(int) * max_batch);
   s->done = (int*)alloc(sizeof(int) * max_batch);
   s->live = (int*)alloc(sizeof(int));
@@ -755,16 +952,72 @@ void llm_prefill(cvk_ctx* ctx, cvk_lm_session* sess, const int32_t* text, const 
 // One device step = head + sampler on the current hidden state (emits token k, gathers its embedding into x), then the
 // 24 layers on x (position base_len + k) leaving the next hidden state.  The reference's loop (llm.py:538-549) is the
 // same sequence rotated by half a step: its first iteration is the prefill.
+static bool lm_fused_path(cvk_ctx* ctx, cvk_lm_session* s) {
+  return s->kv_dtype == DT_BF16 && ctx->use_tc && ctx->use_skinny && ctx->lm_fused && s->g_B <= 64;
+}
+
+// bf16 decode step with fused kernels: 2 + 7 launches per layer instead of 2 + 12
+static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
+  const LlmModel* m = ctx->llm;
+  const int B = s->g_B;
+  const bool fused = true;
+  Mat x(s->x, DT_F32, B, D, D), xn(s->xn, DT_BF16, B, D, D), att(s->att, DT_BF16, B, D, D), ffa(s->ffa, DT_BF16, B, DFF, DFF),
+      logits(s->logits, DT_F32, B, VOUT, VOUT);
+  {
+    Epilogue e;
+    e.out = logits;
+    conv_gemm_skinny_ex(ctx, st, xn, m->head, e, s->scratch, s->scratch_floats, 0);
+  }
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
+                                                                       s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
+                                                                       m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
+                                                                       fused ? (bf16*)s->xn : nullptr);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  const size_t attn_smem = ((size_t)(NH / NKV) * s->max_ctx + (NH / NKV + 2) * HD + (NH / NKV) * AF_PARTS * (2 + HD)) * sizeof(float);
+  for (int li = 0; li < m->num_layers; ++li) {
+    const LayerW& w = m->layers[li];
+    bf16* kc = (bf16*)s->kcache + (size_t)li * s->max_batch * NKV * s->max_ctx * HD;
+    bf16* vc = (bf16*)s->vcache + (size_t)li * s->max_batch * NKV * s->max_ctx * HD;
+    Epilogue none;
+    int sp = conv_gemm_skinny_ex(ctx, st, xn, w.qkv, none, s->scratch, s->scratch_floats, 1);
+    attn_fused_kernel<<<dim3(B, NKV), (NH / NKV) * 32 * AF_PARTS, attn_smem, st>>>(s->scratch, sp, B, w.qkv.bias, kc, vc, s->ctx_len, s->max_ctx, m->d_inv_freq,
+                                                                        att.b16(), att.ld);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    sp = conv_gemm_skinny_ex(ctx, st, att, w.o, none, s->scratch, s->scratch_floats, 1);
+    finish_rms_kernel<<<B, D, 0, st>>>(s->scratch, sp, B, s->x, w.ln2, xn.b16());
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    {
+      Epilogue e;
+      e.out = ffa;
+      conv_gemm_skinny_ex(ctx, st, xn, w.gate_up_il, e, s->scratch, s->scratch_floats, 2);
+    }
+    sp = conv_gemm_skinny_ex(ctx, st, ffa, w.down, none, s->scratch, s->scratch_floats, 1);
+    const float* next_gamma = li + 1 < m->num_layers ? m->layers[li + 1].ln1 : m->final_norm;
+    finish_rms_kernel<<<B, D, 0, st>>>(s->scratch, sp, B, s->x, next_gamma, xn.b16());
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+}
+
 static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
+  if (lm_fused_path(ctx, s)) {
+    decode_step_fused(ctx, st, s);
+    return;
+  }
   const LlmModel* m = ctx->llm;
   const int adt = s->kv_dtype;
   const int B = s->g_B;
+  const bool fused = false;
   Mat hid(s->hidden, DT_F32, B, D, D), x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N),
       att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, VOUT, VOUT);
   head_logits(ctx, st, m, hid, xn, logits, s);
   ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
                                                                        s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
-                                                                       m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr);
+                                                                       m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
+                                                                       fused ? (bf16*)s->xn : nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
@@ -776,6 +1029,7 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
   const LlmModel* m = ctx->llm;
   CVK_REQUIRE(m && s->B > 0, "cvk_lm_prefill must run before cvk_lm_decode");
   const int B = s->B;
+  const bool was_fresh = s->fresh;
   if (s->fresh) {
     CVK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * B, st));
     CVK_CHECK_CUDA(cudaMemsetAsync(done, 0, sizeof(int32_t) * B, st));
@@ -790,6 +1044,12 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     }
     s->g_out_count = out_count; s->g_done = done; s->g_out_ids = out_ids; s->g_uniforms = uniforms; s->g_min = min_len; s->g_max = max_len;
     s->g_out_ld = out_ld; s->g_B = B;
+  }
+  s->g_B = B;
+  if (was_fresh && lm_fused_path(ctx, s)) {
+    // the fused step expects the final-normed hidden state of the previous position in xn
+    Mat hid(s->hidden, DT_F32, B, D, D), xn(s->xn, DT_BF16, B, D, D);
+    rmsnorm(ctx, st, hid, m->final_norm, RMS_EPS, xn);
   }
   const bool can_graph = ctx->use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;   // capture is illegal on the default streams
   if (can_graph && !s->graph) {
@@ -850,7 +1110,7 @@ void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* hist
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (int)sizeof(float)));
   ras_sampler_kernel<<<B, SAMPLER_THREADS, V * sizeof(float), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                                                                     nullptr, nullptr, nullptr, nullptr, history, hist_ld, hist_count, ignore_eos,
-                                                                    out_ids);
+                                                                    out_ids, nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

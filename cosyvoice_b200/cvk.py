@@ -28,6 +28,7 @@ SIGNATURES = {
     "cvk_last_error": (ctypes.c_char_p, [_vp]),
     "cvk_version": (ctypes.c_char_p, []),
     "cvk_launch_count": (ctypes.c_int64, [_vp]),
+    "cvk_last_op_ms": (ctypes.c_double, [_vp]),
     "cvk_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
     "cvk_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cvk_profile_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -164,6 +165,9 @@ class Context:
         self._check(self.lib.cvk_profile_read(self.h, family, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by), ctypes.byref(n)))
         return dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
 
+    def last_op_ms(self):
+        return float(self.lib.cvk_last_op_ms(self.h))
+
     def launch_count(self):
         return int(self.lib.cvk_launch_count(self.h))
 
@@ -184,7 +188,7 @@ class Context:
         b = _f32(bias, self.device) if bias is not None else None
         out = torch.empty(x.shape[0], w.shape[0], device=self.device)
         ms = ctypes.c_float(0)
-        tl = (ctypes.c_longlong * 128)() if timeline else None
+        tl = (ctypes.c_longlong * 1024)() if timeline else None
         self._check(self.lib.cvk_op_linear_small(self.h, _ptr(x), x.shape[0], x.shape[1], _ptr(w), _ptr(b), w.shape[0], _ptr(out), iters,
                                                  ctypes.byref(ms), tl, _stream()))
         return out, ms.value, (list(tl) if timeline else None)

@@ -161,3 +161,18 @@ def test_decode_weight_streaming_gemm_vs_tiled_bf16():
         c.set_option("use_skinny", 1)
     n = min(len(a), len(b), 8)
     assert n >= 6 and a[:n] == b[:n], (a[:16], b[:16])
+
+
+def test_decode_fused_kernels_vs_unfused_bf16():
+    """bf16 decode: fused (split-K finish + RMSNorm, qkv finish + RoPE + cache append + attention, SwiGLU epilogue) vs the
+    one-kernel-per-op path on the same weights: the first sampled ids agree (24-layer model)."""
+    c, sd = model("bf16", 24)
+    text, ptext, ptok, U = cases.lm_case()
+    a = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    c.set_option("lm_fused", 0)
+    try:
+        b = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
+    finally:
+        c.set_option("lm_fused", 1)
+    n = min(len(a), len(b), 6)
+    assert n >= 4 and a[:n] == b[:n], (a[:12], b[:12])

@@ -21,3 +21,10 @@ for (N, K) in ((1152, 896), (9728, 896), (896, 4864), (6564, 896)):
     print("   tma issue  :", issue[:16])
     print("   full ready :", full[:16])
     print("   acc ready  :", tl[1] - t0, " end:", tl[2] - t0)
+    import numpy as np
+    gg = np.array(tl[128:128 + 800]).reshape(-1, 4)
+    gg = gg[gg[:, 0] > 0]
+    t00 = gg[:, 0].min()
+    print(f"   CTAs {len(gg)}: entry spread {gg[:,0].max()-t00} ns; setup {np.median(gg[:,1]-gg[:,0]):.0f} ns; acc-ready after entry med {np.median(gg[:,2]-gg[:,0]):.0f} max {(gg[:,2]-gg[:,0]).max()} ns; "
+          f"end after entry med {np.median(gg[:,3]-gg[:,0]):.0f} max {(gg[:,3]-gg[:,0]).max()} ns; kernel span {gg[:,3].max()-t00} ns")
+    print("   epilogue (thread 64, cycles after acc ready): ld0", tl[3] - tl[1], "ld1", tl[4] - tl[1], "stores done", tl[5] - tl[1], "after final sync", tl[6] - tl[1])
