@@ -168,6 +168,7 @@ def run_ours(args):
     del sds
     torch.cuda.empty_cache()
     model.min_token_text_ratio = model.max_token_text_ratio = TOKEN_RATIO
+    model.lm_chains = args.lm_chains
     batch = args.batch
     inputs = synth.batch32_zero_shot(batch, base=rank * batch)              # weak scaling: every rank its own 32 requests
     h2d = sum(sum(v.numel() * v.element_size() for v in i.values()) for i in inputs)
@@ -291,6 +292,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug: 2-layer LM / reduced flow (NOT the benchmark config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=40.0)
+    ap.add_argument("--lm-chains", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

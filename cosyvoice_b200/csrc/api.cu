@@ -89,6 +89,13 @@ void cvk_destroy(cvk_ctx* ctx) {
 const char* cvk_last_error(cvk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double cvk_last_op_ms(cvk_ctx* ctx) { return ctx ? ctx->op_ms : 0.0; }
+int cvk_debug_read(cvk_ctx* ctx, long long* out, int n) {
+  if (!ctx || !ctx->dbg || !out || n > 1024) return CVK_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(out, ctx->dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return CVK_ERR_CUDA;
+  cudaMemset(ctx->dbg, 0, 1024 * sizeof(long long));
+  return CVK_OK;
+}
 
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   CVK_API_BEGIN
@@ -366,7 +373,7 @@ int cvk_lm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const i
 int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
                   int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, void* stream) {
   CVK_API_BEGIN
-  CVK_REQUIRE(s && uniforms && min_len && max_len && out_ids && out_count && done && n_steps > 0, "cvk_lm_decode: bad arguments");
+  CVK_REQUIRE(s && uniforms && min_len && max_len && out_ids && out_count && done && n_steps >= 0, "cvk_lm_decode: bad arguments");
   llm_decode(ctx, s, n_steps, uniforms, min_len, max_len, out_ids, out_ld, out_count, done, live_host, (cudaStream_t)stream);
   CVK_API_END
 }

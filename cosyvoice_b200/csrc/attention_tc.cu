@@ -70,6 +70,15 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// issue-only variant: several loads can be in flight before one tmem_wait() (each tcgen05.wait::ld is a full TMEM round trip)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -189,16 +198,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       const int j0 = it * AT_BK + cbase;
       const bool full = j0 + 64 <= klim;
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 16) {
-        float v[16];
-        tmem_ld16(tS + trow + (uint32_t)(cbase + c), v);
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c), ra);
+        tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c + 16), rb);
+        tmem_wait();
         if (full) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) m = fmaxf(m, v[e]);
+          for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaxf(__uint_as_float(ra[e]), __uint_as_float(rb[e])));
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (j0 + c + e < klim) m = fmaxf(m, v[e]);
+          for (int e = 0; e < 16; ++e) {
+            if (j0 + c + e < klim) m = fmaxf(m, __uint_as_float(ra[e]));
+            if (j0 + c + 16 + e < klim) m = fmaxf(m, __uint_as_float(rb[e]));
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -217,10 +230,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int j0 = t * AT_BK + cbase;
       const bool full = j0 + 64 <= klim;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 16) {
+      uint32_t rr[4][16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c4 * 16), rr[c4]);   // all 64 scores in flight
+      tmem_wait();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = c4 * 16;
         float v[16];
-        tmem_ld16(tS + trow + (uint32_t)(cbase + c), v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[c4][e]);
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {

@@ -102,12 +102,11 @@ __device__ __forceinline__ float fast_tanh(float x) {
 __device__ __forceinline__ float apply_act_fast(int act, float x, float param, float alpha) {
   switch (act) {
     case ACT_GELU: {
-      // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z)
-      float z = fabsf(x) * 0.70710678118654752440f;
-      float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-      float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-      float erfz = 1.f - poly * fast_exp(-z * z);
-      return 0.5f * x * (1.f + copysignf(erfz, x));
+      // 0.5 x (1 + erf(x/sqrt2)) with erf(z) = tanh(1.1283792 z + 0.1009114 z^3 + ...) folded into the classic
+      // x -> 0.5 x (1 + tanh(0.7978846 (x + 0.044715 x^3))) form on the hardware tanh: max |deviation| from the exact-erf GELU
+      // 5e-4, an eighth of a bf16 ulp at |x| ~ 1 (the result is stored as bf16); 6 instructions instead of ~25.
+      const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+      return 0.5f * x * (1.f + fast_tanh(u));
     }
     case ACT_SILU: return __fdividef(x, 1.f + fast_exp(-x));
     case ACT_MISH: {

@@ -72,6 +72,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// issue-only variant: several loads can be in flight before one tmem_wait() (each tcgen05.wait::ld is a full TMEM round trip)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -270,8 +279,18 @@ template <int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, int N, int K, int taps,
-                    int dil, int shift0, int rowsOut, EpiDev ep, int epi_mode) {
+                    int dil, int shift0, int rowsOut, EpiDev ep, int epi_mode, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
+  long long t_entry = 0;
+  if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_entry));
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  auto stamp = [&](int slot) {
+    if (dbg && cta_lin < 120) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      dbg[cta_lin * 8 + slot] = t;
+    }
+  };
   __shared__ __align__(8) uint64_t bar_full[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
@@ -310,6 +329,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0 && dbg && cta_lin < 120) { dbg[cta_lin * 8 + 0] = t_entry; stamp(1); }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -332,6 +352,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int s = it % TC_STAGES;
         const uint32_t round = (uint32_t)(it / TC_STAGES);
         mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+        if (it == 0) stamp(6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
@@ -358,22 +379,37 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // complete) in SWIZZLE_128B sub-tiles and written by TMA stores - full 128-byte lines instead of one 32/64-byte
       // piece per thread per row; rows / columns outside the matrix are clipped by the tensor map.
       mbar_wait(smem_u32(&bar_acc), 0);
+      if (threadIdx.x == 64) stamp(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16);
       const int row = q * 32 + lane;
       const uint32_t stg1 = smem_base;
       const uint32_t stg2 = smem_base + (uint32_t)TC_BM * BN * (ep.out_dtype == DT_F32 ? 4u : 2u);
 #pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         if (n0 + c >= N) break;
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(trow0 + (uint32_t)c, ra);             // two loads in flight, one wait
+        tmem_ld16_nowait(trow0 + (uint32_t)(c + 16), rb);
+        tmem_wait();
         float acc[16], v[16], w2[16];
-        tmem_ld16(trow0 + (uint32_t)c, acc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
         epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
         stage_store16(stg1, ep.out_dtype, row, c, v);
         if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
+        if (n0 + c + 16 < N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rb[i]);
+          epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
+          stage_store16(stg1, ep.out_dtype, row, c + 16, v);
+          if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c + 16, w2);
+        }
       }
+      if (threadIdx.x == 64) stamp(3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) stamp(4);
       if (threadIdx.x == 64) {
         const int w1 = ep.out_dtype == DT_F32 ? 32 : 64;
         for (int sb = 0; sb * w1 < BN && n0 + sb * w1 < N; ++sb) tma_store_2d(&tmap_o, stg1 + sb * 16384u, n0 + sb * w1, r0);
@@ -382,7 +418,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int sb = 0; sb * w2c < BN && n0 + sb * w2c < N; ++sb) tma_store_2d(&tmap_o2, stg2 + sb * 16384u, n0 + sb * w2c, r0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tile may be released once it has been read
+        stamp(5);
       }
     } else if (epi_mode == 0) {   // simple epilogue: loads inside the per-chunk routine
       mbar_wait(smem_u32(&bar_acc), 0);
@@ -529,7 +566,7 @@ void launch_tc(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUten
     attr_set = true;
   }
   dim3 grid(ceil_div(W.N, BN), ceil_div(rowsOut, TC_BM));
-  conv_gemm_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, epi_mode);
+  conv_gemm_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, epi_mode, (long long*)ctx->dbg);
 }
 
 }  // namespace

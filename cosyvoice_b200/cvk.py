@@ -29,6 +29,7 @@ SIGNATURES = {
     "cvk_version": (ctypes.c_char_p, []),
     "cvk_launch_count": (ctypes.c_int64, [_vp]),
     "cvk_last_op_ms": (ctypes.c_double, [_vp]),
+    "cvk_debug_read": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "cvk_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
     "cvk_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cvk_profile_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -164,6 +165,11 @@ class Context:
         ms, fl, by, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
         self._check(self.lib.cvk_profile_read(self.h, family, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by), ctypes.byref(n)))
         return dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
+
+    def debug_read(self, n=1024):
+        buf = (ctypes.c_longlong * n)()
+        self._check(self.lib.cvk_debug_read(self.h, buf, n))
+        return list(buf)
 
     def last_op_ms(self):
         return float(self.lib.cvk_last_op_ms(self.h))

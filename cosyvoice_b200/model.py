@@ -73,6 +73,8 @@ class B200CosyVoice2Model:
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(1986)
         self._sessions = {}
+        self._lm_streams = []
+        self.lm_chains = 1                   # independent decode chains run concurrently (see lm_generate)
         self._window = torch.from_numpy(self.speech_window).float().to(self.device)
         self.n_timesteps = 10
         self.min_token_text_ratio, self.max_token_text_ratio = 2.0, 20.0
@@ -109,51 +111,87 @@ class B200CosyVoice2Model:
         raise RuntimeError("B200CosyVoice2Model has no vLLM path (the LM runs in libcvk)")
 
     # ---------------------------------------------------------------- LM (llm/llm.py:458-549), batched
-    def _session(self, B, ctx_len):
-        key = (B, (ctx_len + 255) // 256 * 256)
+    def _session(self, B, ctx_len, chain=0):
+        key = (B, (ctx_len + 255) // 256 * 256, chain)
         if key not in self._sessions:
             self._sessions[key] = self.ctx.lm_session(key[0], key[1])
         return self._sessions[key]
 
     def lm_generate(self, texts, prompt_texts, prompt_speech_tokens, uniforms=None, steps_per_sync=32, on_progress=None):
-        """texts/prompt_texts/prompt_speech_tokens: lists of int32 tensors [1,n].  Returns a list of python id lists."""
+        """texts/prompt_texts/prompt_speech_tokens: lists of int32 tensors [1,n].  Returns a list of python id lists.
+
+        The decode step is latency-bound (small kernels on a fraction of the SMs), so the rows are split into
+        `self.lm_chains` independent groups, each with its own KV session, CUDA graph and stream: the chains' kernels
+        interleave on the GPU and hide each other's latencies.  Results are independent of the grouping (rows never
+        interact; every row consumes its own uniforms)."""
         B = len(texts)
-        tl = [int(t.shape[1] + p.shape[1]) for t, p in zip(texts, prompt_texts)]
-        sl = [int(s.shape[1]) for s in prompt_speech_tokens]
+        d = self.device
+        chains = 1 if on_progress is not None else max(1, min(self.lm_chains, B))
+        groups = [list(range(g, B, chains)) for g in range(chains)]
         mins = [int(t.shape[1] * self.min_token_text_ratio) for t in texts]      # llm.py:497-498
         maxs = [int(t.shape[1] * self.max_token_text_ratio) for t in texts]
         mx = max(maxs)
-        d = self.device
+        st = []
         with torch.cuda.stream(self.stream):
-            tt = torch.cat([torch.cat([p.reshape(-1).to(d, non_blocking=True), t.reshape(-1).to(d, non_blocking=True)])
-                            for t, p in zip(texts, prompt_texts)]).to(torch.int32)
-            ss = torch.cat([s.reshape(-1).to(d, non_blocking=True) for s in prompt_speech_tokens]).to(torch.int32) if sum(sl) \
-                else torch.zeros(1, dtype=torch.int32, device=d)
-            min_len = torch.tensor(mins, dtype=torch.int32, device=self.device)
-            max_len = torch.tensor(maxs, dtype=torch.int32, device=self.device)
-            sess = self._session(B, max(a + b for a, b in zip(tl, sl)) + 2 + mx + 8)
-            out_ids = torch.zeros(B, mx + 1, dtype=torch.int32, device=self.device)
-            out_count = torch.zeros(B, dtype=torch.int32, device=self.device)
-            done = torch.zeros(B, dtype=torch.int32, device=self.device)
             if uniforms is None and self.uniforms_override is not None:
                 uniforms = self.uniforms_override
             if uniforms is None:
-                uniforms = torch.rand(mx + 1, B, 2, device=self.device, generator=self.generator)
-            uniforms = uniforms.to(self.device).float().contiguous()
-            with self.ctx.lock:
-                self.ctx.lm_prefill(sess, tt.to(self.device), tl, ss.to(self.device), sl)
-            n = 0
-            while True:
+                uniforms = torch.rand(mx + 1, B, 2, device=d, generator=self.generator)
+            uniforms = uniforms.to(d).float()
+            for g, rows in enumerate(groups):
+                tl = [int(texts[r].shape[1] + prompt_texts[r].shape[1]) for r in rows]
+                sl = [int(prompt_speech_tokens[r].shape[1]) for r in rows]
+                tt = torch.cat([torch.cat([prompt_texts[r].reshape(-1).to(d, non_blocking=True), texts[r].reshape(-1).to(d, non_blocking=True)])
+                                for r in rows]).to(torch.int32)
+                ss = torch.cat([prompt_speech_tokens[r].reshape(-1).to(d, non_blocking=True) for r in rows]).to(torch.int32) if sum(sl) \
+                    else torch.zeros(1, dtype=torch.int32, device=d)
+                c = dict(rows=rows, n=len(rows),
+                         min_len=torch.tensor([mins[r] for r in rows], dtype=torch.int32, device=d),
+                         max_len=torch.tensor([maxs[r] for r in rows], dtype=torch.int32, device=d),
+                         sess=self._session(len(rows), max(a + b2 for a, b2 in zip(tl, sl)) + 2 + mx + 8, g),
+                         out_ids=torch.zeros(len(rows), mx + 1, dtype=torch.int32, device=d),
+                         out_count=torch.zeros(len(rows), dtype=torch.int32, device=d),
+                         done=torch.zeros(len(rows), dtype=torch.int32, device=d),
+                         U=uniforms[:, rows, :].contiguous(), live=len(rows))
                 with self.ctx.lock:
-                    live = self.ctx.lm_decode(sess, steps_per_sync, uniforms, min_len, max_len, out_ids, out_count, done)
-                n += steps_per_sync
-                if on_progress is not None:
-                    on_progress(out_ids, out_count, live)
-                if live == 0 or n > mx + steps_per_sync:
-                    break
-            cnt = out_count.cpu().tolist()
-            ids = out_ids.cpu()
-        return [ids[b, :cnt[b]].tolist() for b in range(B)]
+                    self.ctx.lm_prefill(c["sess"], tt, tl, ss, sl)        # prefills share the workspace arena: one stream, in order
+                st.append(c)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        while len(self._lm_streams) < chains:
+            self._lm_streams.append(torch.cuda.Stream(d))
+        n = 0
+        while True:
+            for g, c in enumerate(st):
+                if c["live"] == 0:
+                    continue
+                stream = self.stream if chains == 1 else self._lm_streams[g]
+                with torch.cuda.stream(stream), self.ctx.lock:
+                    if n == 0:
+                        stream.wait_event(ready)
+                    self.ctx.lm_decode(c["sess"], steps_per_sync, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"],
+                                       want_live=False)
+            for g, c in enumerate(st):
+                if c["live"] == 0:
+                    continue
+                stream = self.stream if chains == 1 else self._lm_streams[g]
+                with torch.cuda.stream(stream), self.ctx.lock:
+                    c["live"] = self.ctx.lm_decode(c["sess"], 0, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"])
+            n += steps_per_sync
+            if on_progress is not None:
+                on_progress(st[0]["out_ids"], st[0]["out_count"], st[0]["live"])
+            if all(c["live"] == 0 for c in st) or n > mx + steps_per_sync:
+                break
+        out = [None] * B
+        for c in st:
+            cnt = c["out_count"].cpu().tolist()
+            ids = c["out_ids"].cpu()
+            for i, r in enumerate(c["rows"]):
+                out[r] = ids[i, :cnt[i]].tolist()
+        if chains > 1:
+            for g in range(chains):
+                self.stream.wait_stream(self._lm_streams[g])
+        return out
 
     # ---------------------------------------------------------------- flow + vocoder
     def flow_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True):

@@ -48,6 +48,8 @@ const char* cvk_version(void);
 int64_t cvk_launch_count(cvk_ctx* ctx);
 /* mean device time (ms) of the kernel timed by the last cvk_op_* call when the "op_iters" option is > 0 (tools/gemm_probe.py) */
 double cvk_last_op_ms(cvk_ctx* ctx);
+/* debug: copy (and clear) the device timeline buffer filled by instrumented kernels when "debug_timeline" is on */
+int cvk_debug_read(cvk_ctx* ctx, long long* out, int n);
 /* debug switch: 1 (default) = bf16 GEMMs on the tcgen05 kernel, 0 = same operands through the SIMT kernel */
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value);
 

@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cosyvoice_b200 import cvk
 c = cvk.Context(0, "bf16", 12.0)
 c.set_option("op_iters", 10)
+c.set_option("debug_timeline", 1)
+import numpy as np
 g = torch.Generator().manual_seed(0)
 SHAPES = [  # name, rows, K, N, taps, dil, act
     ("est ff1 gelu", 40064, 256, 1024, 1, 1, "gelu"), ("est ff2", 40064, 1024, 256, 1, 1, "none"), ("est qkv", 40064, 256, 1536, 1, 1, "none"),
@@ -23,4 +25,10 @@ for name, rows, K, N, taps, dil, act in SHAPES:
             c.conv1d(x, [rows], w, b, dil=dil, shift0=-(taps - 1) * dil // 2, act=a)
         ms = c.last_op_ms()
         res.append(f"bn256={bn256} epi={epi}: {ms*1000:7.1f} us {2*rows*N*K*taps/ms/1e9:6.0f} TF")
+        if epi == 2:
+            t = np.array(c.debug_read(960)).reshape(-1, 8)
+            t = t[t[:, 0] > 0]
+            e0 = t[:, 0]
+            f = lambda k: f"{np.median(t[:, k] - e0):.0f}"
+            res.append(f"[ns after CTA entry, median of {len(t)} CTAs: setup {f(1)} first-operands {f(6)} acc-ready {f(2)} math+stage done {f(3)} barrier {f(4)} tma-store done {f(5)}; entry spread {e0.max()-e0.min()}]")
     print(f"{name:14s} M={rows} K={K} N={N} taps={taps}: " + " | ".join(res))
