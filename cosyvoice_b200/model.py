@@ -183,9 +183,10 @@ class B200CosyVoice2Model:
             if all(c["live"] == 0 for c in st) or n > mx + steps_per_sync:
                 break
         out = [None] * B
-        for c in st:
-            cnt = c["out_count"].cpu().tolist()
-            ids = c["out_ids"].cpu()
+        for g, c in enumerate(st):
+            with torch.cuda.stream(self.stream if chains == 1 else self._lm_streams[g]):
+                cnt = c["out_count"].cpu().tolist()
+                ids = c["out_ids"].cpu()
             for i, r in enumerate(c["rows"]):
                 out[r] = ids[i, :cnt[i]].tolist()
         if chains > 1:
@@ -252,6 +253,13 @@ class B200CosyVoice2Model:
         fade_in = fade_in.clone()
         fade_in[..., :n] = fade_in[..., :n] * self._window[:n] + fade_out[..., -n:] * self._window[n:]
         return fade_in
+
+    def _to_host(self, t):
+        """D2H on the model's stream (the kernels that produced `t` were enqueued there, not on torch's current stream)."""
+        with torch.cuda.stream(self.stream):
+            h = t.cpu()
+        self.stream.synchronize()
+        return h
 
     def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0):
         """cli/model.py:292-326"""
@@ -322,20 +330,20 @@ class B200CosyVoice2Model:
                                             this_uuid, stream=True, finalize=False)
                     token_offset += this_hop
                     self.token_hop_len = min(self.token_max_hop_len, self.token_hop_len * self.stream_scale_factor)
-                    yield {"tts_speech": speech.cpu()}
+                    yield {"tts_speech": self._to_host(speech)}
                 if self.llm_end_dict[this_uuid] is True and len(self.tts_speech_token_dict[this_uuid]) - token_offset < this_hop + PRE_LOOKAHEAD:
                     break
             p.join()
             this_tok = torch.tensor(self.tts_speech_token_dict[this_uuid]).unsqueeze(0)
             speech = self.token2wav(this_tok, flow_prompt_speech_token, prompt_speech_feat, flow_embedding, token_offset, this_uuid,
                                     finalize=True)
-            yield {"tts_speech": speech.cpu()}
+            yield {"tts_speech": self._to_host(speech)}
         else:
             p.join()
             this_tok = torch.tensor(self.tts_speech_token_dict[this_uuid]).unsqueeze(0)
             speech = self.token2wav(this_tok, flow_prompt_speech_token, prompt_speech_feat, flow_embedding, 0, this_uuid, finalize=True,
                                     speed=speed)
-            yield {"tts_speech": speech.cpu()}
+            yield {"tts_speech": self._to_host(speech)}
         with self.lock:
             self.tts_speech_token_dict.pop(this_uuid)
             self.llm_end_dict.pop(this_uuid)

@@ -209,7 +209,70 @@ def gen_masks():
     save("chunk_mask_130_50", mask=m.numpy())
 
 
+def stream_noise(k, n_samples):
+    """noise of the k-th vocoder call of a request (shared with tests/test_model_gpu.py)"""
+    g = torch.Generator().manual_seed(7000 + k)
+    return torch.randn(n_samples, 9, generator=g)
+
+
+def gen_stream():
+    """cosyvoice/cli/model.py:328-394 (CosyVoice2Model.tts) itself, stream=False and stream=True, on small modules."""
+    print("stream (reference CosyVoice2Model.tts)")
+    refimport.install()
+    from cosyvoice.cli.model import CosyVoice2Model
+    NL, kw = 2, dict(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2)
+    llm = refimport.build_llm(num_layers=NL)
+    llm.load_state_dict(lm.synth_state_dict(NL), strict=True)
+    fl = refimport.build_flow(**kw)
+    fl.load_state_dict(weights.synth_state_dict(flow.param_shapes(flow.FlowCfg(**kw)), 1986, flow.SYNTH_GAINS), strict=True)
+    hf = refimport.build_hift()
+    hf.load_state_dict(weights.synth_state_dict(hift.param_shapes(), 1986, hift.SYNTH_GAINS), strict=True)
+    text, ptext, ptok, U = cases.lm_case()
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    pfeat = pfeat[:, :18]
+    out = {}
+    for mode, stream in (("offline", False), ("stream", True)):
+        model = CosyVoice2Model(llm, fl, hf, fp16=False)
+        st = {"i": 0, "c": 0, "k": 0}
+
+        def get_u():
+            u = float(U[st["i"], min(st["c"], 1)])
+            st["c"] += 1
+            return u
+        orig_mn, orig_rl = torch.Tensor.multinomial, torch.randn_like
+
+        def fake_mn(t, n, replacement=False, generator=None):
+            r = torch.tensor([sampling.draw_index(t.detach().numpy(), get_u())])
+            return r
+
+        def fake_rl(x, *a, **k):
+            if x.dim() == 3 and x.shape[2] == 9:
+                z = stream_noise(st["k"], x.shape[1]).unsqueeze(0)
+                st["k"] += 1
+                return z
+            return orig_rl(x, *a, **k)
+        # the LM thread consumes one (u1,u2) pair per generated token: advance the step counter from the token list length
+        orig_infer = llm.sampling_ids
+
+        def sampling_ids(weighted_scores, decoded_tokens, sampling_, ignore_eos=True):
+            st["i"], st["c"] = len(decoded_tokens), 0
+            return orig_infer(weighted_scores, decoded_tokens, sampling_, ignore_eos)
+        llm.sampling_ids = sampling_ids
+        torch.Tensor.multinomial, torch.randn_like = fake_mn, fake_rl
+        try:
+            chunks = [o["tts_speech"] for o in model.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                         llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                         stream=stream)]
+        finally:
+            torch.Tensor.multinomial, torch.randn_like = orig_mn, orig_rl
+            llm.sampling_ids = orig_infer
+        print(f"  {mode}: {len(chunks)} chunks, lengths {[c.shape[1] for c in chunks]}, hop_len after = {model.token_hop_len}")
+        out[mode + "_lens"] = np.array([c.shape[1] for c in chunks], dtype=np.int64)
+        out[mode + "_wav"] = torch.cat(chunks, 1).numpy()
+    save("stream_tts", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "flow", "lm", "sampling", "mel", "masks"]
+    which = sys.argv[1:] or ["hift", "flow", "lm", "sampling", "mel", "masks", "stream"]
     for w in which:
         globals()["gen_" + w]()

@@ -1,0 +1,91 @@
+"""GPU: the host-side mirror of cosyvoice/cli/model.py:245-394 (B200CosyVoice2Model.tts / token2wav / tts_batch) against
+outputs of the reference CosyVoice2Model.tts itself (tests/golden/stream_tts.npz: offline and streaming runs on small
+modules with the RNG streams injected) - chunk schedule, cache/fade bookkeeping and waveform."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import maxdiff
+from oracle import cases, flow, hift, lm, weights
+from oracle.make_golden import stream_noise
+
+pytestmark = pytest.mark.gpu
+_m = {}
+
+
+def model():
+    if "m" not in _m:
+        from cosyvoice_b200.model import B200CosyVoice2Model
+        NL, kw = 2, dict(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2)
+        m = B200CosyVoice2Model(precision="fp32", device=0, workspace_gb=4.0)
+        m.load_state_dicts(lm.synth_state_dict(NL), weights.synth_state_dict(flow.param_shapes(flow.FlowCfg(**kw)), 1986, flow.SYNTH_GAINS),
+                           weights.synth_state_dict(hift.param_shapes(), 1986, hift.SYNTH_GAINS))
+        _m["m"] = m
+    return _m["m"]
+
+
+def request():
+    text, ptext, ptok, U = cases.lm_case()
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    return dict(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext, llm_prompt_speech_token=ptok,
+                flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat[:, :18]), U
+
+
+def hooks(m, U):
+    st = {"k": 0}
+
+    def noise_fn(n):
+        z = stream_noise(st["k"], n).to(m.device)
+        st["k"] += 1
+        return z
+    m.uniforms_override = U[:, None, :]
+    m.noise_fn = noise_fn
+    m.token_hop_len = 25
+
+
+@pytest.mark.parametrize("stream", [False, True])
+def test_tts_matches_reference_model(stream, golden):
+    g = golden("stream_tts")
+    m = model()
+    req, U = request()
+    hooks(m, U)
+    try:
+        chunks = [o["tts_speech"] for o in m.tts(**req, stream=stream)]
+    finally:
+        m.uniforms_override, m.noise_fn = None, None
+    key = "stream" if stream else "offline"
+    assert [c.shape[1] for c in chunks] == g[key + "_lens"].tolist()          # chunk schedule: bit-exact bookkeeping
+    assert all(c.device.type == "cpu" and c.dtype == torch.float32 and c.shape[0] == 1 for c in chunks)
+    wav = torch.cat(chunks, 1)
+    ref = torch.from_numpy(g[key + "_wav"])
+    # The excitation phase is 2*pi*480*cumsum(f0/sr), so fp32 summation-order differences in the f0 predictor grow along the
+    # utterance: tight bound on the first second, looser on the rest (measured: 2e-4 / 5e-4 over 5.6 s).
+    d_head = maxdiff(wav[:, :24000], ref[:, :24000])
+    rel = ((wav - ref).norm() / ref.norm()).item()
+    print(f"[{key}] max|d| first second {d_head:.3g}, relative L2 over {wav.shape[1]} samples {rel:.3g}, max|d| {maxdiff(wav, ref):.3g}")
+    assert d_head < 5e-3, d_head
+    assert rel < 0.05, rel
+    if stream:
+        assert m.token_hop_len == 100        # the reference leaves the doubled hop on the instance (cli/model.py:359-360)
+
+
+def test_tts_batch_equals_single_requests(golden):
+    g = golden("stream_tts")
+    m = model()
+    req, U = request()
+    req2 = dict(req)
+    g2 = torch.Generator().manual_seed(123)
+    req2["text"] = torch.randint(0, 151643, (1, 5), generator=g2, dtype=torch.int32)
+    st = {"k": 0}
+    n1 = 140 * 960
+    noise1 = stream_noise(0, n1)
+    Ub = torch.rand(141, 2, 2, generator=g2)
+    Ub[:, 0] = U[:141]
+    ids = m.lm_generate([req["text"], req2["text"]], [req["prompt_text"]] * 2, [req["llm_prompt_speech_token"]] * 2, uniforms=Ub)
+    n2 = len(ids[1]) * 960
+    noise = torch.cat([noise1, torch.randn(n2, 9, generator=g2)], 0)
+    wavs = m.tts_batch([req, req2], uniforms=Ub, noise=noise)
+    assert wavs[0].shape[1] == n1 and wavs[1].shape[1] == n2
+    ref = torch.from_numpy(g["offline_wav"])
+    assert maxdiff(wavs[0][:, :24000], ref[:, :24000]) < 5e-3
+    assert ((wavs[0] - ref).norm() / ref.norm()).item() < 0.05
