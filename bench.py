@@ -82,20 +82,38 @@ def dist_env():
 
 
 # ================================================================================================ reference arm (CPU)
+_REF_WEIGHTS = {}
+
+
+def host_threads():
+    """Threads the CPU arm may use: the affinity mask, clipped by the cgroup CPU quota, at most 32 (batch-1 decode does not scale
+    past that and oversubscribing a quota-limited container is slower than running fewer threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
 def cpu_reference_sample(full=True, threads=None):
     """The reference's algorithm (oracle port, CPU fp32 torch) on ONE Z10 utterance of the batch-32 workload: LM decode of
     5*n_text tokens with KV cache + RAS sampling, flow (NFE 10, CFG), HiFT.  Returns (audio_seconds, wall_seconds, info)."""
     import torch
     from oracle import flow as oflow, hift as ohift, lm as olm, weights as oweights
     from cosyvoice_b200 import synth
-    threads = threads or os.cpu_count()
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     NL = 24 if full else 2
     fcfg = oflow.FlowCfg() if full else oflow.FlowCfg(2, 1, 2, 2)
-    lsd = olm.synth_state_dict(NL)
-    lsd["llm_decoder.bias"][6561:6564] = -1e4
-    fsd = oweights.synth_state_dict(oflow.param_shapes(fcfg), 1986, oflow.SYNTH_GAINS)
-    hsd = oweights.synth_state_dict(ohift.param_shapes(), 1986, ohift.SYNTH_GAINS)
+    if full not in _REF_WEIGHTS:                       # generated once per process, outside every timed region
+        lsd = olm.synth_state_dict(NL)
+        lsd["llm_decoder.bias"][6561:6564] = -1e4
+        _REF_WEIGHTS[full] = (lsd, oweights.synth_state_dict(oflow.param_shapes(fcfg), 1986, oflow.SYNTH_GAINS),
+                              oweights.synth_state_dict(ohift.param_shapes(), 1986, ohift.SYNTH_GAINS))
+    lsd, fsd, hsd = _REF_WEIGHTS[full]
     utt = synth.z10_utterance(0, 50)
     g = torch.Generator().manual_seed(0)
     n_tok = int(50 * TOKEN_RATIO)
@@ -119,10 +137,10 @@ def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = host_threads()
     vals = []
-    for _ in range(args.warmup):
-        cpu_reference_sample(full=not args.small, threads=cores)
+    for _ in range(args.warmup):                       # CPU warm-up (page-in, thread pool): the same code on small modules
+        cpu_reference_sample(full=False, threads=cores)
     info = {}
     for _ in range(max(args.steps, 1)):
         a, w, info = cpu_reference_sample(full=not args.small, threads=cores)
@@ -136,6 +154,7 @@ def run_reference(args):
             "ms_per_step": 1000 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "CosyVoice2-0.5B zero-shot batch-32 NFE=10 (bounded sample: one utterance per step)",
+                       "warmup_note": "CPU warm-up steps run the same code on 2-layer modules (thread pool / page-in only)",
                        "reference_impl": "oracle port of cosyvoice/{llm,flow,hifigan} (torch CPU fp32; /root/reference is absent on the GPU box)"},
             "cpu_baseline": {"value": v, "unit": "audio-sec/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -169,6 +188,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
     model.min_token_text_ratio = model.max_token_text_ratio = TOKEN_RATIO
     model.lm_chains = args.lm_chains
+    for kv in args.opt:                                # debug/experiment switches of the library (cvk_set_option)
+        k, v = kv.split("=")
+        model.ctx.set_option(k, int(v))
     batch = args.batch
     inputs = synth.batch32_zero_shot(batch, base=rank * batch)              # weak scaling: every rank its own 32 requests
     h2d = sum(sum(v.numel() * v.element_size() for v in i.values()) for i in inputs)
@@ -262,7 +284,7 @@ def run_ours(args):
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         a, w, info = cpu_reference_sample(full=full)
-        cpu = {"value": a / w, "unit": "audio-sec/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": a / w, "unit": "audio-sec/s", "cores": host_threads(), "kind": "port",
                "sample": f"1 of the {batch} utterances (250 speech tokens, 10 s audio): LM {info['lm_s']:.1f}s flow {info['flow_s']:.1f}s HiFT {info['hift_s']:.1f}s"}
     line = {"metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,6 +315,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=40.0)
     ap.add_argument("--lm-chains", type=int, default=1)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (cvk_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

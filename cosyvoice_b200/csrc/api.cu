@@ -90,6 +90,10 @@ const char* cvk_last_error(cvk_ctx* ctx) { return ctx ? ctx->last_error.c_str() 
 int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double cvk_last_op_ms(cvk_ctx* ctx) { return ctx ? ctx->op_ms : 0.0; }
 int cvk_debug_read(cvk_ctx* ctx, long long* out, int n) {
+  if (ctx && ctx->tl && out && n == 4096) {   // LM-chain timeline
+    if (cudaMemcpy(out, ctx->tl, 4096 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return CVK_ERR_CUDA;
+    return CVK_OK;
+  }
   if (!ctx || !ctx->dbg || !out || n > 1024) return CVK_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if (cudaMemcpy(out, ctx->dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return CVK_ERR_CUDA;
@@ -103,11 +107,21 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   if (k == "use_tc") ctx->use_tc = value;
   else if (k == "tc_bn256") ctx->tc_bn256 = value;
   else if (k == "tc_epi") ctx->tc_epi = value;
+  else if (k == "tc_persist") ctx->tc_persist = value;
+  else if (k == "op_out_bf16") ctx->op_out_bf16 = value;
   else if (k == "op_iters") ctx->op_iters = value;
   else if (k == "use_graph") ctx->use_graph = value;
   else if (k == "use_tc_attn") ctx->use_tc_attn = value;
   else if (k == "use_skinny") ctx->use_skinny = value;
   else if (k == "lm_fused") ctx->lm_fused = value;
+  else if (k == "pdl") ctx->pdl = value;
+  else if (k == "chain_timeline") {
+    if (value && !ctx->tl) {
+      ctx->tl = ctx->dmalloc(4096 * sizeof(long long));
+      CVK_CHECK_CUDA(cudaMemset(ctx->tl, 0, 4096 * sizeof(long long)));
+    }
+    if (!value) ctx->tl = nullptr;
+  }
   else if (k == "debug_timeline") {
     if (value && !ctx->dbg) {
       ctx->dbg = ctx->dmalloc(1024 * sizeof(long long));
@@ -200,7 +214,7 @@ int cvk_op_conv1d(cvk_ctx* ctx, const float* x, const int* lens, int B, int K, c
   Mat a = arena_mat(ctx, ctx->act_dtype, s.R, K);
   zero_mat(ctx, st, a);
   pack_rows(ctx, st, x, K, s, a);
-  Mat o = arena_mat(ctx, DT_F32, s.R, N);
+  Mat o = arena_mat(ctx, ctx->op_out_bf16 ? DT_BF16 : DT_F32, s.R, N);
   Epilogue e;
   e.act1 = act;
   e.act1_param = 0.1f;

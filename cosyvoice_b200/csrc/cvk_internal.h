@@ -159,16 +159,27 @@ struct cvk_ctx {
   void* mel_model = nullptr;
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
+  int op_out_bf16 = 0;                      // cvk_op_conv1d: bf16 output matrix (the estimator's usual epilogue) instead of fp32
   int op_iters = 0;                         // cvk_op_conv1d: repeat the GEMM launch this many times and time it
   double op_ms = 0.0;
   int tc_epi = 2;                           // tcgen05 GEMM epilogue: 2 = smem-staged TMA stores, 0 = direct stores, 1 = direct + prefetch
+  int tc_persist = 2;                       // tcgen05 GEMM, tiles > SMs: persistent CTAs + double-buffered TMEM accumulators (2 = 16 epilogue warps, 1 = 8, 0 = off)
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
   void* dbg = nullptr;                      // device int64[1024] timeline buffer (debug option)
+  void* tl = nullptr;                       // device int64[4096] LM-chain timeline (debug option chain_timeline): 4 slots per launch
+  int tl_seq = 0;
+  long long* tl_next() {                    // slot block of the next launch of the decode chain (null when the option is off)
+    if (!tl) return nullptr;
+    long long* p = (long long*)tl + 4 * (tl_seq % 1024);
+    ++tl_seq;
+    return p;
+  }
   int prof_on = 0;
   int in_capture = 0;
   std::vector<ProfRec> prof;
   std::unordered_map<const void*, void*> tiled;   // bf16 weight -> streaming (pre-tiled, pre-swizzled) copy for the skinny GEMM
   std::vector<cudaEvent_t> event_pool;
+  int pdl = 1;                              // LM decode chain: programmatic dependent launch (next kernel's prologue + weight prefetch overlap this kernel)
   int lm_fused = 1;                         // LM decode: fused finish+rmsnorm / rope+attention / SwiGLU-epilogue kernels
   int use_skinny = 1;                       // LM decode GEMMs on the weight-streaming split-K kernel
   int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)
@@ -188,6 +199,24 @@ struct cvk_ctx {
   }
   bool has_raw(const std::string& name) const { return raw.find(name) != raw.end(); }
 };
+
+// kernel launch with the optional PDL attribute (see common.cuh pdl_wait/pdl_trigger)
+template <typename... KArgs, typename... Args>
+inline void launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  CVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
 
 // ------------------------------------------------------------------------------------------------ shared ops
 // geometry

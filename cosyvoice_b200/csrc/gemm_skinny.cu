@@ -104,8 +104,10 @@ template <int BPAD>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUtensorMap tmap_x, int N, int K, int rows,
                    int chunks_per_split, float* __restrict__ partial /*[splits][rows][N] or null*/, EpiDev ep, int swiglu,
-                   long long* __restrict__ dbg) {
+                   long long* __restrict__ dbg, long long* __restrict__ tl) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
+  tl_stamp(tl, 0);
   long long t_entry = 0;
   if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_entry));
   __shared__ __align__(8) uint64_t bar_full[SK_STAGES];
@@ -154,7 +156,21 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
+      // The weights are written by no kernel of the chain: the first ring of weight slabs is requested BEFORE waiting for the
+      // producer of the activations, so the HBM stream of this kernel overlaps the tail of the previous one.
+      const int pre = min(iters, SK_STAGES);
+      for (int it = 0; it < pre; ++it) {
+        const uint32_t fb = smem_u32(&bar_full[it]);
+        mbar_expect_tx(fb, STAGE);
+        bulk_load(base + it * STAGE, w_tiled + ((size_t)blockIdx.x * kchunks + (kc0 + it)) * (SK_BM * SK_BK), A_BYTES, fb);
+      }
+      pdl_wait();
+      tl_stamp(tl, 1);
+      for (int it = 0; it < pre; ++it) {
+        tma_load_2d(base + it * STAGE + A_BYTES, &tmap_x, smem_u32(&bar_full[it]), (kc0 + it) * SK_BK, 0);
+        if (trace && it < 32) dbg[8 + it] = clock64();
+      }
+      for (int it = pre; it < iters; ++it) {
         const int s = it % SK_STAGES;
         const uint32_t round = (uint32_t)(it / SK_STAGES);
         mbar_wait(smem_u32(&bar_empty[s]), (round & 1u) ^ 1u);
@@ -165,8 +181,11 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
         tma_load_2d(sb, &tmap_x, fb, (kc0 + it) * SK_BK, 0);
         if (trace && it < 32) dbg[8 + it] = clock64();
       }
+    } else {
+      pdl_wait();
     }
   } else if (warp == 1) {
+    pdl_wait();
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
         const int s = it % SK_STAGES;
@@ -185,6 +204,7 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     const int q = warp & 3;
     const int n_pre = n0 + q * 32 + lane;
     const float bias_n = (!partial && !swiglu && ep.bias && n_pre < N) ? ep.bias[n_pre] : 0.f;   // fetched while the weights stream
+    pdl_wait();
     mbar_wait(smem_u32(&bar_acc), 0);
     if (trace && threadIdx.x == 64) dbg[1] = clock64();
     if (dbg && threadIdx.x == 64 && cta_lin < 200) {
@@ -236,19 +256,25 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     dbg[128 + cta_lin * 4 + 3] = t;
   }
+  tl_stamp(tl, 2);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(BPAD < 32 ? 32 : BPAD)) : "memory");
   }
 }
 
 // out = epilogue(sum_s partial[s]) in fixed split order
-__global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int rows, int N, EpiDev ep) {
+__global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int rows, int N, EpiDev ep, long long* __restrict__ tl) {
+  pdl_trigger();
+  tl_stamp(tl, 0);
+  pdl_wait();
+  tl_stamp(tl, 1);
   size_t total = (size_t)rows * N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += partial[(size_t)s * total + i];
     epi_store(ep, (int)(i / N), (int)(i % N), acc);
   }
+  tl_stamp(tl, 2);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -257,14 +283,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 template <int BPAD>
 void launch(cudaStream_t st, dim3 grid, const bf16* tw, const CUtensorMap& tx, const ConvW& W, int rows, int cps, float* partial,
-            const EpiDev& e, int swiglu, long long* dbg) {
+            const EpiDev& e, int swiglu, long long* dbg, bool pdl, long long* tl) {
   constexpr size_t smem = (size_t)SK_STAGES * (SK_BM * SK_BK * 2 + BPAD * SK_BK * 2) + 1024;
   static bool attr = false;
   if (!attr) {
     CVK_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  skinny_gemm_kernel<BPAD><<<grid, SK_THREADS, smem, st>>>(tw, tx, W.N, W.K, rows, cps, partial, e, swiglu, dbg);
+  launch_ex(skinny_gemm_kernel<BPAD>, grid, dim3(SK_THREADS), smem, st, pdl, tw, tx, W.N, W.K, rows, cps, partial, e, swiglu, dbg, tl);
 }
 
 }  // namespace
@@ -335,15 +361,16 @@ int conv_gemm_skinny_ex(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW
   ProfScope ps(ctx, st, FAM_GEMM_TC, flops, bytes);
   dim3 grid(tiles, splits);
   float* partial = (splits > 1 || mode == 1) ? scratch : nullptr;
-  if (BPAD == 32) launch<32>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg);
-  else launch<64>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg);
+  long long* tl = ctx->tl_next();
+  if (BPAD == 32) launch<32>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg, ctx->pdl != 0, tl);
+  else launch<64>(st, grid, tw, tx, W, rows, cps, partial, e, mode == 2, (long long*)ctx->dbg, ctx->pdl != 0, tl);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   if (splits > 1 && mode == 0) {
     size_t total = (size_t)rows * W.N;
     int g = (int)((total + 255) / 256);
     if (g > 148 * 4) g = 148 * 4;
-    splitk_finish_kernel<<<g, 256, 0, st>>>(partial, splits, rows, W.N, e);
+    launch_ex(splitk_finish_kernel, dim3(g), dim3(256), 0, st, ctx->pdl != 0, (const float*)partial, splits, rows, W.N, e, ctx->tl_next());
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }

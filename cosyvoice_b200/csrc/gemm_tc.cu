@@ -120,10 +120,7 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += rv[i];
   }
-  if (e.act1 != ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act1, v[i], e.act1_param, e.alpha1 ? e.alpha1[n0 + i] : 1.f);
-  }
+  act16_fast(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1 + n0 : nullptr);
   if (e.scale != 1.f) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= e.scale;
@@ -167,8 +164,12 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
   if (e.out2) {
     float w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      w[i] = valid ? apply_act_fast(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
+    for (int i = 0; i < 16; ++i) w[i] = v[i];
+    act16_fast(e.act2, w, e.act2_param, e.alpha2 ? e.alpha2 + n0 : nullptr);
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = 0.f;
+    }
     size_t o2 = (size_t)r * e.out2_ld + n0;
     if (e.out2_dtype == DT_F32) {
       float* op = (float*)e.out2 + o2;
@@ -209,10 +210,7 @@ __device__ __forceinline__ void epi_math16(const EpiDev& e, int r, bool rin, int
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += rv[i];
     }
-    if (e.act1 != ACT_NONE) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act1, v[i], e.act1_param, e.alpha1 ? e.alpha1[n0 + i] : 1.f);
-    }
+    act16_fast(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1 + n0 : nullptr);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= e.scale;
     if (e.resid && rin) {
@@ -241,9 +239,18 @@ __device__ __forceinline__ void epi_math16(const EpiDev& e, int r, bool rin, int
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
   }
   if (e.out2) {
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      w2[i] = (valid && n0 + i < N) ? apply_act_fast(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
+      for (int i = 0; i < 16; ++i) w2[i] = v[i];
+      act16_fast(e.act2, w2, e.act2_param, e.alpha2 ? e.alpha2 + n0 : nullptr);
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w2[i] = 0.f;
+      }
+    } else {
+      for (int i = 0; i < 16; ++i)
+        w2[i] = (valid && n0 + i < N) ? apply_act_fast(e.act2, v[i], e.act2_param, e.alpha2 ? e.alpha2[n0 + i] : 1.f) : 0.f;
+    }
   }
 }
 
@@ -541,6 +548,165 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// One CTA per SM walks a static list of 128x128 output tiles (column tile fastest, so the CTAs running at the same time
+// share A rows in L2).  Two TMEM accumulators (2 x 128 columns): the MMA warp fills buffer t&1 for tile t while the eight
+// epilogue warps drain buffer (t-1)&1, so the epilogue (TMEM -> registers -> fused math -> swizzled staging tile -> TMA
+// store) overlaps the next tile's main loop, and barrier setup / TMEM allocation / tensor-map fetch are paid once per SM
+// instead of once per tile.  The operand ring runs across tile boundaries (the producer never drains).
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int NSTG, int EW>   // EW epilogue warps (8 or 16): EW/4 warps share a TMEM lane quarter and split the columns
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                            const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, int N, int K, int taps,
+                            int dil, int shift0, int rowsOut, EpiDev ep, int ntn, int ntiles, int stg_bufs) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int BN = 128;
+  __shared__ __align__(8) uint64_t bar_full[NSTG];
+  __shared__ __align__(8) uint64_t bar_empty[NSTG];
+  __shared__ __align__(8) uint64_t bar_accf[2];
+  __shared__ __align__(8) uint64_t bar_acce[2];
+  __shared__ uint32_t tmem_base_slot;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = smem_base + NSTG * STAGE_BYTES;          // 64 KB staging region (one 64 KB or two 32 KB tiles)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = (K + TC_BK - 1) / TC_BK;
+  const int iters = taps * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_accf[b]), 1);
+      mbar_init(smem_u32(&bar_acce[b]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(2u * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const uint32_t s = it % NSTG, round = it / NSTG;
+          mbar_wait(smem_u32(&bar_empty[s]), (round & 1u) ^ 1u);
+          const int j = i / kchunks, kc = i - j * kchunks;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t fb = smem_u32(&bar_full[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, fb, kc * TC_BK, r0 + shift0 + j * dil);
+          tma_load_3d(sa + A_BYTES, &tmap_w, fb, kc * TC_BK, j, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1u, use = tcount >> 1;
+        mbar_wait(smem_u32(&bar_acce[buf]), (use & 1u) ^ 1u);     // the epilogue has drained this accumulator (first use: free)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const uint32_t s = it % NSTG, round = it / NSTG;
+          mbar_wait(smem_u32(&bar_full[s]), round & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&bar_empty[s]));
+        }
+        umma_commit(smem_u32(&bar_accf[buf]));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int CPP = BN / (EW / 4);                 // columns per warp
+    constexpr int ETHREADS = 32 * EW;
+    const int row = q * 32 + lane;
+    const uint32_t out_tile_bytes = (uint32_t)TC_BM * BN * (ep.out_dtype == DT_F32 ? 4u : 2u);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int r0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+      const int r = r0 + row;
+      const bool rin = r < rowsOut;
+      const uint32_t buf = tcount & 1u, use = tcount >> 1;
+      // staging tile of this iteration: with two buffers the one used two tiles ago has been read by its TMA store
+      // (thread 64 waited for that before reaching this barrier)
+      if (tcount > 0) asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+      const uint32_t stg1 = stg_base + (stg_bufs == 2 ? (tcount & 1u) * 32768u : 0u);
+      const uint32_t stg2 = stg1 + out_tile_bytes;
+      mbar_wait(smem_u32(&bar_accf[buf]), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow0 = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = part * CPP; c < (part + 1) * CPP; c += 32) {
+        if (n0 + c >= N) break;
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(trow0 + (uint32_t)c, ra);
+        tmem_ld16_nowait(trow0 + (uint32_t)(c + 16), rb);
+        tmem_wait();
+        float acc[16], v[16], w2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
+        epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
+        stage_store16(stg1, ep.out_dtype, row, c, v);
+        if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
+        if (n0 + c + 16 < N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rb[i]);
+          epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
+          stage_store16(stg1, ep.out_dtype, row, c + 16, v);
+          if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c + 16, w2);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+      if (threadIdx.x == 64) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mbar_arrive(smem_u32(&bar_acce[buf]));      // every epilogue thread has finished reading this accumulator
+        const int w1 = ep.out_dtype == DT_F32 ? 32 : 64;
+        for (int sb = 0; sb * w1 < BN && n0 + sb * w1 < N; ++sb) tma_store_2d(&tmap_o, stg1 + sb * 16384u, n0 + sb * w1, r0);
+        if (ep.out2) {
+          const int w2c = ep.out2_dtype == DT_F32 ? 32 : 64;
+          for (int sb = 0; sb * w2c < BN && n0 + sb * w2c < N; ++sb) tma_store_2d(&tmap_o2, stg2 + sb * 16384u, n0 + sb * w2c, r0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (stg_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * BN) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -567,6 +733,20 @@ void launch_tc(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUten
   }
   dim3 grid(ceil_div(W.N, BN), ceil_div(rowsOut, TC_BM));
   conv_gemm_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, epi_mode, (long long*)ctx->dbg);
+}
+
+template <int NSTG, int EW>
+void launch_tc_persist(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& to2,
+                       const ConvW& W, int rowsOut, const EpiDev& e, int stg_bufs) {
+  constexpr size_t smem = (size_t)NSTG * (TC_BM * TC_BK * 2 + 128 * TC_BK * 2) + 65536 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<NSTG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int ntn = ceil_div(W.N, 128), ntiles = ntn * ceil_div(rowsOut, TC_BM);
+  const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
+  conv_gemm_tc_persist_kernel<NSTG, EW><<<grid, 64 + 32 * EW, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, ntn, ntiles, stg_bufs);
 }
 
 }  // namespace
@@ -630,6 +810,16 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
     };
     mk(&to, ep.out);
     if (ep.out2.p) mk(&to2, ep.out2);
+  }
+  const size_t need_stage = (size_t)TC_BM * 128 * ep.out.esize() + (ep.out2.p ? (size_t)TC_BM * 128 * ep.out2.esize() : 0);
+  const int ntiles_p = ceil_div(W.N, 128) * ceil_div(rowsOut, TC_BM);
+  if (ctx->tc_persist && BN == 128 && epi_mode == 2 && need_stage <= 65536 && ntiles_p > ctx->num_sms) {
+    // more tiles than SMs: persistent CTAs with double-buffered accumulators (epilogue overlaps the next main loop)
+    if (ctx->tc_persist == 2) launch_tc_persist<4, 16>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
+    else launch_tc_persist<4, 8>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    return;
   }
   if (BN == 256) launch_tc<256, 2>(ctx, st, ta, tw, to, to2, W, rowsOut, e, epi_mode);      // 2 x 48 KB stages: two CTAs (2 x 256 TMEM columns) per SM
   else if (BN == 128) launch_tc<128, 3>(ctx, st, ta, tw, to, to2, W, rowsOut, e, epi_mode);

@@ -63,7 +63,7 @@ struct cvk_lm_session {
   const float* g_uniforms = nullptr;
   const int32_t *g_min = nullptr, *g_max = nullptr;
   int32_t *g_out_ids = nullptr, *g_out_count = nullptr, *g_done = nullptr;
-  int g_out_ld = 0, g_B = 0;
+  int g_out_ld = 0, g_B = 0, g_pdl = -1;
   float* scratch = nullptr;      // split-K partial sums of the weight-streaming GEMM
   size_t scratch_floats = 0;
   std::vector<void*> owned;
@@ -244,9 +244,14 @@ decode_attn_kernel(const T* __restrict__ qkv, int ld, const T* __restrict__ kc, 
 // x[b] += sum_s partial[s][b] (+bias); xn[b] = rmsnorm(x[b]) * gamma  - split-K reduction, residual add and the next
 // RMSNorm (modeling_qwen2.py:258-263) in one pass; one CTA per row.
 __global__ void __launch_bounds__(D) finish_rms_kernel(const float* __restrict__ partial, int splits, int rows, float* __restrict__ x,
-                                                       const float* __restrict__ gamma, bf16* __restrict__ xn) {
+                                                       const float* __restrict__ gamma, bf16* __restrict__ xn, long long* __restrict__ tl) {
   __shared__ float red[D / 32];
+  pdl_trigger();
+  tl_stamp(tl, 0);
   const int b = blockIdx.x, n = threadIdx.x;
+  const float gam = gamma[n];            // constant: fetched before waiting for the producer of `partial`
+  pdl_wait();
+  tl_stamp(tl, 1);
   const float* p = partial + (size_t)b * D + n;
   const size_t stride = (size_t)rows * D;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -266,7 +271,8 @@ __global__ void __launch_bounds__(D) finish_rms_kernel(const float* __restrict__
   float tot = 0.f;
 #pragma unroll
   for (int i = 0; i < D / 32; ++i) tot += red[i];
-  xn[(size_t)b * D + n] = __float2bfloat16_rn(gamma[n] * (v * rsqrtf(tot / D + RMS_EPS)));
+  xn[(size_t)b * D + n] = __float2bfloat16_rn(gam * (v * rsqrtf(tot / D + RMS_EPS)));
+  tl_stamp(tl, 2);
 }
 
 // qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head), FOUR warps per
@@ -275,7 +281,7 @@ constexpr int AF_PARTS = 4;
 __global__ void __launch_bounds__((NH / NKV) * 32 * AF_PARTS)
 attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int splits, int rows, const float* __restrict__ bias,
                   bf16* __restrict__ kc, bf16* __restrict__ vc, const int* __restrict__ ctx_len, int max_ctx,
-                  const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo) {
+                  const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo, long long* __restrict__ tl, long long* __restrict__ ph) {
   extern __shared__ float sm_all[];            // [G][max_ctx] scores | [G+2][64] staging | [G][PARTS][2] max/sum | [G][PARTS][64] partial O
   constexpr int G = NH / NKV;
   const int b = blockIdx.x, kvh = blockIdx.y;
@@ -284,6 +290,12 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
   float* stage = sm_all + (size_t)G * max_ctx;
   float* ml = stage + (G + 2) * HD;
   float* po = ml + G * AF_PARTS * 2;
+  pdl_trigger();
+  tl_stamp(tl, 0);
+  pdl_wait();
+  tl_stamp(tl, 1);
+#define AF_PHASE(i) do { if (ph && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); ph[1000 + (i)] = t_; } } while (0)
+  AF_PHASE(0);
   const int pos = ctx_len[b];
   for (int e = threadIdx.x; e < (G + 2) * HD; e += blockDim.x) {
     const int vec = e / HD, d = e % HD;
@@ -293,6 +305,7 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
     stage[e] = acc;
   }
   __syncthreads();
+  AF_PHASE(1);
   for (int e = threadIdx.x; e < (G + 1) * (HD / 2); e += blockDim.x) {     // rotate the G query heads and k
     const int vec = e / (HD / 2), i = e % (HD / 2);
     const float fr = (float)pos * inv_freq[i];
@@ -303,6 +316,7 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
     p[i + HD / 2] = x2 * c + x1 * sn;
   }
   __syncthreads();
+  AF_PHASE(2);
   bf16* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
   bf16* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
   if (pos < max_ctx && threadIdx.x < 2 * HD) {
@@ -311,32 +325,48 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
     else vb[(size_t)pos * HD + d] = __float2bfloat16_rn(stage[(G + 1) * HD + d]);
   }
   __syncthreads();
+  AF_PHASE(3);
   const int L = min(pos + 1, max_ctx);
   float* sc = sm_all + (size_t)w * max_ctx;
-  float qr[HD];
+  // Lane (r, c): key j0 + 4u + r, 16-byte chunk c of its row.  One load instruction of the warp covers 4 contiguous cache rows
+  // (512 B) and 8 of them are in flight per lane, so a block of 32 keys costs ONE memory round trip (the per-key scalar loop this
+  // replaces paid one round trip per 4 keys and dominated the decode step).
+  const int r = lane >> 3, c = lane & 7;
+  float q[8];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) qr[d] = __bfloat162float(__float2bfloat16_rn(stage[w * HD + d])) * 0.125f;
+  for (int e = 0; e < 8; ++e) q[e] = __bfloat162float(__float2bfloat16_rn(stage[w * HD + c * 8 + e])) * 0.125f;
   float m = -INFINITY;
-  for (int j = part * 32 + lane; j < L; j += 32 * AF_PARTS) {
-    const uint4* k4 = reinterpret_cast<const uint4*>(kb + (size_t)j * HD);
-    float s = 0.f;
+  for (int j0 = part * 32; j0 < L; j0 += 32 * AF_PARTS) {
+    uint4 kk[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 u = k4[c];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * 4 + r;
+      kk[u] = j < L ? *reinterpret_cast<const uint4*>(kb + (size_t)j * HD + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kk[u]);
+      float sdot = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h2[e]);
-        s = fmaf(qr[c * 8 + 2 * e], f.x, s);
-        s = fmaf(qr[c * 8 + 2 * e + 1], f.y, s);
+        const float2 f = __bfloat1622float2(h2[e]);
+        sdot = fmaf(q[2 * e], f.x, sdot);
+        sdot = fmaf(q[2 * e + 1], f.y, sdot);
+      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      const int j = j0 + u * 4 + r;
+      if (j < L) {
+        if (c == 0) sc[j] = sdot;
+        m = fmaxf(m, sdot);
       }
     }
-    sc[j] = s;
-    m = fmaxf(m, s);
   }
   m = warp_max(m);
   if (lane == 0) ml[(w * AF_PARTS + part) * 2] = m;
   __syncthreads();
+  AF_PHASE(4);
   float mh = ml[(w * AF_PARTS) * 2];
 #pragma unroll
   for (int p2 = 1; p2 < AF_PARTS; ++p2) mh = fmaxf(mh, ml[(w * AF_PARTS + p2) * 2]);
@@ -349,32 +379,41 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
   l = warp_sum(l);
   if (lane == 0) ml[(w * AF_PARTS + part) * 2 + 1] = l;
   __syncwarp();
-  // P.V over this warp's keys (the 32 keys of each of its groups are rows j0..j0+31): one pair of output dims per lane
-  float o0 = 0.f, o1 = 0.f;
+  // P.V over this warp's keys with the same (r, c) tiling: 8 output dims per lane, reduced over the 4 key sub-rows at the end
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (int j0 = part * 32; j0 < L; j0 += 32 * AF_PARTS) {
-    const int jn = min(32, L - j0);
-    int jj = 0;
-    for (; jj + 4 <= jn; jj += 4) {
-      const float p0 = sc[j0 + jj], p1 = sc[j0 + jj + 1], p2 = sc[j0 + jj + 2], p3 = sc[j0 + jj + 3];
-      const bf16* v0 = vb + (size_t)(j0 + jj) * HD;
-      const float a0 = __bfloat162float(v0[lane]), a1 = __bfloat162float(v0[lane + 32]);
-      const float b0 = __bfloat162float(v0[HD + lane]), b1 = __bfloat162float(v0[HD + lane + 32]);
-      const float c0 = __bfloat162float(v0[2 * HD + lane]), c1 = __bfloat162float(v0[2 * HD + lane + 32]);
-      const float d0 = __bfloat162float(v0[3 * HD + lane]), d1 = __bfloat162float(v0[3 * HD + lane + 32]);
-      o0 = fmaf(p0, a0, o0); o1 = fmaf(p0, a1, o1);
-      o0 = fmaf(p1, b0, o0); o1 = fmaf(p1, b1, o1);
-      o0 = fmaf(p2, c0, o0); o1 = fmaf(p2, c1, o1);
-      o0 = fmaf(p3, d0, o0); o1 = fmaf(p3, d1, o1);
+    uint4 vv[8];
+    float pp[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * 4 + r;
+      vv[u] = j < L ? *reinterpret_cast<const uint4*>(vb + (size_t)j * HD + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+      pp[u] = j < L ? sc[j] : 0.f;
     }
-    for (; jj < jn; ++jj) {
-      const float p = sc[j0 + jj];
-      o0 = fmaf(p, __bfloat162float(vb[(size_t)(j0 + jj) * HD + lane]), o0);
-      o1 = fmaf(p, __bfloat162float(vb[(size_t)(j0 + jj) * HD + lane + 32]), o1);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        acc[2 * e] = fmaf(pp[u], f.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(pp[u], f.y, acc[2 * e + 1]);
+      }
     }
   }
-  po[(w * AF_PARTS + part) * HD + lane] = o0;
-  po[(w * AF_PARTS + part) * HD + lane + 32] = o1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (r == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) po[(w * AF_PARTS + part) * HD + c * 8 + e] = acc[e];
+  }
   __syncthreads();
+  AF_PHASE(5);
   if (part == 0) {
     float lt = 0.f, t0 = 0.f, t1 = 0.f;
 #pragma unroll
@@ -388,6 +427,9 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
     op[lane] = __float2bfloat16_rn(t0 * inv);
     op[lane + 32] = __float2bfloat16_rn(t1 * inv);
   }
+  AF_PHASE(6);
+  tl_stamp(tl, 2);
+#undef AF_PHASE
 }
 
 __global__ void interleave_rows_kernel(const float* __restrict__ gu /*[2*F][K]: gate rows then up rows*/, float* __restrict__ out, int F, int K) {
@@ -456,7 +498,7 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
                    const float* __restrict__ speech_emb, float* __restrict__ next_x,
                    const int32_t* __restrict__ history, int hist_ld, const int32_t* __restrict__ hist_count,
                    const int32_t* __restrict__ ignore_eos_in, int32_t* __restrict__ ids_out, const float* __restrict__ ln_gamma,
-                   bf16* __restrict__ xn_out) {
+                   bf16* __restrict__ xn_out, long long* __restrict__ tl) {
   extern __shared__ float sp[];            // V probabilities
   __shared__ float red[SAMPLER_THREADS / 32];
   __shared__ float part[SAMPLER_THREADS];
@@ -470,6 +512,10 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool standalone = ids_out != nullptr;
+  pdl_trigger();
+  tl_stamp(tl, 0);
+  pdl_wait();
+  tl_stamp(tl, 1);
   if (!standalone && done[b]) return;
   float* x = scores + (size_t)b * V;
   const int per = (V + SAMPLER_THREADS - 1) / SAMPLER_THREADS;
@@ -961,6 +1007,7 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
   const LlmModel* m = ctx->llm;
   const int B = s->g_B;
   const bool fused = true;
+  ctx->tl_seq = 0;
   Mat x(s->x, DT_F32, B, D, D), xn(s->xn, DT_BF16, B, D, D), att(s->att, DT_BF16, B, D, D), ffa(s->ffa, DT_BF16, B, DFF, DFF),
       logits(s->logits, DT_F32, B, VOUT, VOUT);
   {
@@ -968,10 +1015,11 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
     e.out = logits;
     conv_gemm_skinny_ex(ctx, st, xn, m->head, e, s->scratch, s->scratch_floats, 0);
   }
-  ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
-                                                                       s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
-                                                                       m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
-                                                                       fused ? (bf16*)s->xn : nullptr);
+  const bool pdl = ctx->pdl != 0;
+  launch_ex(ras_sampler_kernel, dim3(B), dim3(SAMPLER_THREADS), VOUT * sizeof(float), st, pdl, s->logits, VOUT, 1, s->g_uniforms, B, s->g_min,
+            s->g_max, s->g_out_ids, s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, (const int*)s->base_len, s->live,
+            (const float*)m->speech_emb, s->x, (const int32_t*)nullptr, 0, (const int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr,
+            (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next());
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   const size_t attn_smem = ((size_t)(NH / NKV) * s->max_ctx + (NH / NKV + 2) * HD + (NH / NKV) * AF_PARTS * (2 + HD)) * sizeof(float);
@@ -981,12 +1029,12 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
     bf16* vc = (bf16*)s->vcache + (size_t)li * s->max_batch * NKV * s->max_ctx * HD;
     Epilogue none;
     int sp = conv_gemm_skinny_ex(ctx, st, xn, w.qkv, none, s->scratch, s->scratch_floats, 1);
-    attn_fused_kernel<<<dim3(B, NKV), (NH / NKV) * 32 * AF_PARTS, attn_smem, st>>>(s->scratch, sp, B, w.qkv.bias, kc, vc, s->ctx_len, s->max_ctx, m->d_inv_freq,
-                                                                        att.b16(), att.ld);
+    launch_ex(attn_fused_kernel, dim3(B, NKV), dim3((NH / NKV) * 32 * AF_PARTS), attn_smem, st, pdl, (const float*)s->scratch, sp, B,
+              (const float*)w.qkv.bias, kc, vc, (const int*)s->ctx_len, s->max_ctx, (const float*)m->d_inv_freq, att.b16(), att.ld, ctx->tl_next(), (long long*)ctx->dbg);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
     sp = conv_gemm_skinny_ex(ctx, st, att, w.o, none, s->scratch, s->scratch_floats, 1);
-    finish_rms_kernel<<<B, D, 0, st>>>(s->scratch, sp, B, s->x, w.ln2, xn.b16());
+    launch_ex(finish_rms_kernel, dim3(B), dim3(D), 0, st, pdl, (const float*)s->scratch, sp, B, s->x, (const float*)w.ln2, xn.b16(), ctx->tl_next());
     ctx->launches++;
     CVK_LAUNCH_CHECK();
     {
@@ -996,7 +1044,7 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
     }
     sp = conv_gemm_skinny_ex(ctx, st, ffa, w.down, none, s->scratch, s->scratch_floats, 1);
     const float* next_gamma = li + 1 < m->num_layers ? m->layers[li + 1].ln1 : m->final_norm;
-    finish_rms_kernel<<<B, D, 0, st>>>(s->scratch, sp, B, s->x, next_gamma, xn.b16());
+    launch_ex(finish_rms_kernel, dim3(B), dim3(D), 0, st, pdl, (const float*)s->scratch, sp, B, s->x, next_gamma, xn.b16(), ctx->tl_next());
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }
@@ -1017,7 +1065,7 @@ static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
   ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
                                                                        s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
                                                                        m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
-                                                                       fused ? (bf16*)s->xn : nullptr);
+                                                                       fused ? (bf16*)s->xn : nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
@@ -1036,14 +1084,14 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     s->fresh = false;
   }
   bool same = s->g_out_count == out_count && s->g_done == done && s->g_out_ids == out_ids && s->g_uniforms == uniforms &&
-              s->g_min == min_len && s->g_max == max_len && s->g_out_ld == out_ld && s->g_B == B;
+              s->g_min == min_len && s->g_max == max_len && s->g_out_ld == out_ld && s->g_B == B && s->g_pdl == ctx->pdl;
   if (!same) {
     if (s->graph) {
       cudaGraphExecDestroy(s->graph);
       s->graph = nullptr;
     }
     s->g_out_count = out_count; s->g_done = done; s->g_out_ids = out_ids; s->g_uniforms = uniforms; s->g_min = min_len; s->g_max = max_len;
-    s->g_out_ld = out_ld; s->g_B = B;
+    s->g_out_ld = out_ld; s->g_B = B; s->g_pdl = ctx->pdl;
   }
   s->g_B = B;
   if (was_fresh && lm_fused_path(ctx, s)) {
@@ -1110,7 +1158,7 @@ void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* hist
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (int)sizeof(float)));
   ras_sampler_kernel<<<B, SAMPLER_THREADS, V * sizeof(float), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                                                                     nullptr, nullptr, nullptr, nullptr, history, hist_ld, hist_count, ignore_eos,
-                                                                    out_ids, nullptr, nullptr);
+                                                                    out_ids, nullptr, nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

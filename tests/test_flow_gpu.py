@@ -103,3 +103,27 @@ def test_ragged_batch_vs_oracle(precision):
         d = maxdiff(mel[o:o + L], ref)
         assert d < (5e-3 if precision == "fp32" else 0.5), d
         o += L
+
+
+def test_persistent_gemm_flow_bit_identical():
+    """A batch large enough for the persistent tcgen05 GEMM path (tiles > SMs; bf16 and fp32 outputs, second outputs, residual /
+    per-sequence-vector epilogues): the whole flow is bit-identical with the path switched off."""
+    c, sd, cfg = model("bf16", "small")
+    g = torch.Generator().manual_seed(31)
+    B = 12
+    n_tok = [int(x) for x in torch.randint(200, 330, (B,), generator=g)]
+    toks = torch.cat([torch.randint(0, 6561, (n + 40,), generator=g, dtype=torch.int32) for n in n_tok])
+    tl = [n + 40 for n in n_tok]
+    pf = torch.randn(B * 80, 80, generator=g)
+    emb = torch.randn(B, 192, generator=g)
+    outs = []
+    for on in (2, 0):
+        c.set_option("tc_persist", on)
+        try:
+            mel, lens = c.flow_inference(toks, tl, pf, [80] * B, emb, n_timesteps=3)
+            outs.append(mel.clone())
+        finally:
+            c.set_option("tc_persist", 2)
+    assert lens == [2 * n for n in n_tok]
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), maxdiff(outs[0], outs[1])

@@ -120,3 +120,28 @@ def test_attention_tcgen05_long_ragged(chunk):
     torch.cuda.synchronize()
     assert maxdiff(simt, ref) < 2e-2
     assert maxdiff(out, ref) < 2e-2, maxdiff(out, ref)      # P rounded to bf16 before P.V
+
+
+@pytest.mark.parametrize("case", [(256, 384, 3, -2, "mish"), (256, 1024, 1, 0, "gelu"), (1024, 256, 1, 0, "none")],
+                         ids=["K256N384t3", "K256N1024", "K1024N256"])
+def test_conv_gemm_persistent_tiles(case):
+    """More output tiles than SMs: the persistent tcgen05 kernel (double-buffered TMEM accumulators, operand ring running
+    across tile boundaries) == the one-tile-per-CTA kernel bit for bit, and == torch fp32 to bf16 operand rounding."""
+    K, N, taps, shift0, act = case
+    g = torch.Generator().manual_seed(K + N)
+    lens = [5000, 3333, 4100, 129]                      # ~99 row tiles x 2-8 column tiles, ragged tails
+    xs = [torch.randn(T, K, generator=g) for T in lens]
+    w = torch.randn(N, K, taps, generator=g) / (K * taps) ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    c = ctx("bf16")
+    x = torch.cat(xs, 0)
+    a = c.conv1d(x, lens, w, b, shift0=shift0, act=act)
+    outs = []
+    for mode in (0, 1):                                  # one tile per CTA; persistent with 8 epilogue warps (default: 16)
+        c.set_option("tc_persist", mode)
+        try:
+            outs.append(c.conv1d(x, lens, w, b, shift0=shift0, act=act))
+        finally:
+            c.set_option("tc_persist", 2)
+    assert torch.equal(a, outs[0]) and torch.equal(a, outs[1]), (maxdiff(a, outs[0]), maxdiff(a, outs[1]))
+    assert maxdiff(a, _ref_conv(xs, w, b, 1, shift0, act)) < 3e-2
