@@ -2,25 +2,28 @@
 // Attention; flow/decoder.py:439-449): head_dim 64, ragged sequences, full or block-causal (chunk) masking.
 //
 // One CTA = 128 queries of one (sequence, head).  S = Q K^T and O += P V are tcgen05.mma with accumulators in TMEM
-// (S: 128 columns, O: 64 columns); Q/K/V tiles arrive by TMA (SWIZZLE_128B) straight out of the fused QKV activation
+// (S: three 64-column half-tile buffers, O: 64 columns); Q/K/V tiles arrive by TMA (SWIZZLE_128B) straight out of the fused QKV activation
 // matrix; V is consumed MN-major so no transpose is ever materialised; the mask is a predicate on (query, key) indices.
 // Softmax is two-pass (pass 1: row maxima from S tiles, pass 2: P = exp2(S - max) and O accumulation) so O is never
 // read-modify-written: exp throughput, not the tensor pipe, bounds this kernel, and the extra Q K^T costs ~1/4 of it.
-// Warps 0-7: softmax (two threads per query row, one per 64-key half; TMEM lane == row), warp 8: TMA producer,
-// warp 9: MMA issuer.
-// Two CTAs are co-resident per SM (TMEM 2 x 256 columns, smem 2 x ~112 KB) so one CTA's exps overlap the other's MMAs.
+// Both passes are software-pipelined through multiple S buffers in TMEM (see the kernel comment).
+// Warps 0-7: softmax (two threads per query row, 32 keys of every 64-key half tile each; TMEM lane == row), warp 8: TMA
+// producer, warp 9: MMA issuer.
+// Two CTAs are co-resident per SM (TMEM 2 x 256 columns, smem 2 x 98 KB): 16 softmax warps per SM hide the TMEM-load and
+// exp latencies (ncu on the first version, which only fitted one CTA per SM: 33 % issue utilisation, long-scoreboard bound).
 #include "common.cuh"
 
 namespace {
 
-constexpr int AT_BQ = 128, AT_BK = 128, AT_HD = 64;
+constexpr int AT_BQ = 128, AT_BK = 64, AT_HD = 64;    // 128 queries x 64-key half tiles
+constexpr int AT_KVST = 3;                             // K/V stages (one half tile each)
 constexpr int AT_THREADS = 320;   // warps 0-7 softmax (2 threads per query row: key halves), warp 8 TMA, warp 9 MMA
 constexpr uint32_t Q_BYTES = AT_BQ * AT_HD * 2;        // 16 KB
-constexpr uint32_t K_BYTES = AT_BK * AT_HD * 2;        // 16 KB
-constexpr uint32_t V_BYTES = AT_BK * AT_HD * 2;        // 16 KB
-constexpr uint32_t P_BYTES = AT_BQ * AT_BK * 2;        // 32 KB (two 128x64 SW128 tiles)
-constexpr uint32_t KV_STAGE = K_BYTES + V_BYTES;
-constexpr uint32_t AT_SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 1024;
+constexpr uint32_t K_BYTES = AT_BK * AT_HD * 2;        // 8 KB
+constexpr uint32_t V_BYTES = AT_BK * AT_HD * 2;        // 8 KB
+constexpr uint32_t P_BYTES = 2 * AT_BQ * AT_BK * 2;    // 32 KB: two 128x64 SW128 P buffers
+constexpr uint32_t KV_STAGE = K_BYTES + V_BYTES;       // 16 KB
+constexpr uint32_t AT_SMEM = Q_BYTES + AT_KVST * KV_STAGE + P_BYTES + 1024;   // 97 KB: two CTAs per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -91,13 +94,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Pipeline (all hand-offs are mbarriers; one elected MMA thread, one TMA thread, 256 softmax threads).  The unit of work is a
+// HALF tile of 64 keys: K/V arrive in three 16 KB stages, S half tiles rotate through three 64-column TMEM buffers ([0,64)
+// [64,128) [192,256); O lives in [128,192)) and P through two 16 KB shared-memory buffers.
+//   pass 1  the MMA thread runs up to three S half tiles ahead of the softmax threads, which only reduce row maxima;
+//   pass 2  the MMA thread issues S(g+1) before it waits for P(g): the tensor pipe computes the next scores while the softmax
+//           threads (two per query row, 32 keys each) turn S(g) into P(g), and P(g+1) is written while P(g) V is being read.
+// 97 KB of shared memory and 256 TMEM columns per CTA: two CTAs (16 softmax warps) per SM.
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const __grid_constant__ CUtensorMap tmv,
                const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale_log2e, int kv_div,
                bf16* __restrict__ out, int ldo) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_s, bar_p, bar_o;
-  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2];
+  __shared__ __align__(8) uint64_t bar_q, bar_o, bar_p1done;
+  __shared__ __align__(8) uint64_t bar_full[AT_KVST], bar_empty[AT_KVST];   // K/V stages
+  __shared__ __align__(8) uint64_t s1_full[3], s1_free[3];          // pass 1: S half-tile buffers
+  __shared__ __align__(8) uint64_t s_full[3], s_free[3];            // pass 2: S half-tile buffers
+  __shared__ __align__(8) uint64_t p_full[2], p_free[2];            // pass 2: P half-tile buffers
   __shared__ uint32_t tmem_slot;
   __shared__ float xch[2][AT_BQ];   // row max / row sum exchange between the two threads of a row
 
@@ -107,25 +120,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (i0 >= L) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sKV = base + Q_BYTES, sP = sKV + 2 * KV_STAGE;
+  const uint32_t sQ = base, sKV = base + Q_BYTES, sP = sKV + AT_KVST * KV_STAGE;
   // keys visible to this query tile: all of the sequence, or up to the end of the last query's chunk
   const int i_last = min(i0 + AT_BQ, L) - 1;
   const int kmax = chunk > 0 ? min(L, (i_last / chunk + 1) * chunk) : L;
-  const int ntiles = (kmax + AT_BK - 1) / AT_BK;
-  const int iters = 2 * ntiles;
+  const int G = (kmax + AT_BK - 1) / AT_BK;      // half tiles per pass
 
-  // instruction descriptors: D=f32, A=B=bf16, M=128;  S: N=128, both K-major;  O: N=64, B (=V) MN-major
+  // instruction descriptors: D=f32, A=B=bf16, M=128;  S: N=64, both K-major;  O: N=64, B (=V) MN-major
   constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
   constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar_q), 1);
-    mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 256);
     mbar_init(smem_u32(&bar_o), 1);
-    for (int s = 0; s < 2; ++s) {
+    mbar_init(smem_u32(&bar_p1done), 256);
+    for (int s = 0; s < AT_KVST; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(smem_u32(&s1_full[s]), 1);
+      mbar_init(smem_u32(&s1_free[s]), 256);
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_free[s]), 256);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&p_full[s]), 256);
+      mbar_init(smem_u32(&p_free[s]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -136,115 +157,134 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tS = tmem_slot, tO = tmem_slot + 128;
+  const uint32_t tbase = tmem_slot, tO = tmem_slot + 128;
+  // S half-tile buffer g%3 -> first TMEM column
+  auto scol = [](int g) -> uint32_t { const int sb = g % 3; return sb == 0 ? 0u : (sb == 1 ? 64u : 192u); };
 
   if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
       tma_load_2d(sQ, &tmq, smem_u32(&bar_q), h * AT_HD, s0 + i0);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it & 1;
-        const uint32_t round = (uint32_t)(it >> 1);
-        const int tile = it < ntiles ? it : it - ntiles;
-        const bool pass2 = it >= ntiles;
+      for (int it = 0; it < 2 * G; ++it) {
+        const int st = it % AT_KVST;
+        const uint32_t round = (uint32_t)(it / AT_KVST);
+        const bool pass2 = it >= G;
+        const int g = pass2 ? it - G : it;
         mbar_wait(smem_u32(&bar_empty[st]), (round & 1u) ^ 1u);
         const uint32_t fb = smem_u32(&bar_full[st]);
         mbar_expect_tx(fb, pass2 ? KV_STAGE : K_BYTES);
-        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, s0 + tile * AT_BK);
-        if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, s0 + tile * AT_BK);
+        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, s0 + g * AT_BK);
+        if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, s0 + g * AT_BK);
       }
     }
   } else if (warp == 9) {
     if (lane == 0) {
       mbar_wait(smem_u32(&bar_q), 0);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it & 1;
-        const uint32_t round = (uint32_t)(it >> 1);
-        const bool pass2 = it >= ntiles;
-        const int tile = pass2 ? it - ntiles : it;
-        mbar_wait(smem_u32(&bar_full[st]), round & 1u);
+      // ---- pass 1: S(g) into buffer g%3; the K stage is released as soon as the MMA has consumed it
+      for (int g = 0; g < G; ++g) {
+        const int st = g % AT_KVST, sb = g % 3;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((g / AT_KVST) & 1));
+        mbar_wait(smem_u32(&s1_free[sb]), (uint32_t)(((g / 3) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sK = sKV + st * KV_STAGE, sV = sK + K_BYTES;
+        const uint32_t sK = sKV + st * KV_STAGE;
 #pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k) umma(tS, desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
-        umma_commit(smem_u32(&bar_s));
-        mbar_wait(smem_u32(&bar_p), (uint32_t)(it & 1));     // softmax threads are done with S (and wrote P in pass 2)
+        for (int k = 0; k < AT_HD / 16; ++k) umma(tbase + scol(g), desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s1_full[sb]));
+        umma_commit(smem_u32(&bar_empty[st]));
+      }
+      // every pass-1 score has been read before pass 2 reuses the columns
+      mbar_wait(smem_u32(&bar_p1done), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- pass 2
+      auto issue_s = [&](int g) {
+        const int it = G + g, st = it % AT_KVST;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((it / AT_KVST) & 1));
+        mbar_wait(smem_u32(&s_free[g % 3]), (uint32_t)(((g / 3) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (pass2) {
+        const uint32_t sK = sKV + st * KV_STAGE;
 #pragma unroll
-          for (int k = 0; k < AT_BK / 16; ++k) {
-            // A = P: two K-major 128x64 tiles (16 KB each), 32 B per 16-key step inside a tile
-            // B = V: MN-major, 16 keys = 16 rows of 128 B = 2048 B per step
-            const uint32_t pa = sP + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32;
-            umma(tO, desc_sw128(pa), desc_sw128(sV + k * 2048), IDESC_O, (tile > 0 || k > 0) ? 1u : 0u);
-          }
-        }
+        for (int k = 0; k < AT_HD / 16; ++k) umma(tbase + scol(g), desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[g % 3]));
+      };
+      issue_s(0);
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) issue_s(g + 1);
+        const int it = G + g, st = it % AT_KVST, pb = g & 1;
+        mbar_wait(smem_u32(&p_full[pb]), (uint32_t)((g >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sV = sKV + st * KV_STAGE + K_BYTES;
+        const uint32_t pa = sP + pb * 16384;
+#pragma unroll
+        for (int k = 0; k < AT_BK / 16; ++k)      // 64 keys = 4 steps of 16: A = P (K-major, 32 B per step), B = V (MN-major, 2048 B per step)
+          umma(tO, desc_sw128(pa + k * 32), desc_sw128(sV + k * 2048), IDESC_O, (g > 0 || k > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&p_free[pb]));
         umma_commit(smem_u32(&bar_empty[st]));
       }
       umma_commit(smem_u32(&bar_o));
     }
   } else {
-    // softmax warps: two threads per query row (key halves [0,64) and [64,128) of every tile)
+    // softmax warps: two threads per query row, keys [0,32) / [32,64) of every half tile
     const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;
     const int i = i0 + row;
     const int klim = i < L ? (chunk > 0 ? min(L, (i / chunk + 1) * chunk) : L) : 0;
     const uint32_t trow = ((uint32_t)(q4 * 32) << 16);
-    const int cbase = half * 64;
+    const int cb2 = half * 32;
     float m = -INFINITY;
-    for (int it = 0; it < ntiles; ++it) {
-      mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
+    for (int g = 0; g < G; ++g) {
+      const int sb = g % 3;
+      mbar_wait(smem_u32(&s1_full[sb]), (uint32_t)((g / 3) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int j0 = it * AT_BK + cbase;
-      const bool full = j0 + 64 <= klim;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t ra[16], rb[16];
-        tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c), ra);
-        tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c + 16), rb);
-        tmem_wait();
-        if (full) {
+      const int j0 = g * AT_BK + cb2;
+      const bool full = j0 + 32 <= klim;
+      const uint32_t tS = tbase + scol(g) + trow + (uint32_t)cb2;
+      uint32_t rr[2][16];
+      tmem_ld16_nowait(tS, rr[0]);
+      tmem_ld16_nowait(tS + 16u, rr[1]);
+      tmem_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&s1_free[sb]));       // the scores are in registers: the buffer may be overwritten
+      if (full) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaxf(__uint_as_float(ra[e]), __uint_as_float(rb[e])));
-        } else {
+        for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaxf(__uint_as_float(rr[0][e]), __uint_as_float(rr[1][e])));
+      } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (j0 + c + e < klim) m = fmaxf(m, __uint_as_float(ra[e]));
-            if (j0 + c + 16 + e < klim) m = fmaxf(m, __uint_as_float(rb[e]));
-          }
+        for (int e = 0; e < 16; ++e) {
+          if (j0 + e < klim) m = fmaxf(m, __uint_as_float(rr[0][e]));
+          if (j0 + 16 + e < klim) m = fmaxf(m, __uint_as_float(rr[1][e]));
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(smem_u32(&bar_p));
     }
+    mbar_arrive(smem_u32(&bar_p1done));
     xch[half][row] = m;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     m = fmaxf(xch[0][row], xch[1][row]);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float mneg = (m == -INFINITY) ? 0.f : -m * scale_log2e;
     float lsum = 0.f;
-    const uint32_t prow = sP + (uint32_t)half * (AT_BQ * 128) + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-    for (int t = 0; t < ntiles; ++t) {
-      const int it = ntiles + t;
-      mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
+    for (int g = 0; g < G; ++g) {
+      const int pb = g & 1;
+      mbar_wait(smem_u32(&s_full[g % 3]), (uint32_t)((g / 3) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int j0 = t * AT_BK + cbase;
-      const bool full = j0 + 64 <= klim;
-      uint32_t rr[4][16];
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) tmem_ld16_nowait(tS + trow + (uint32_t)(cbase + c4 * 16), rr[c4]);   // all 64 scores in flight
+      const int j0 = g * AT_BK + cb2;
+      const bool full = j0 + 32 <= klim;
+      uint32_t rr[2][16];
+      const uint32_t tS = tbase + scol(g) + trow + (uint32_t)cb2;
+      tmem_ld16_nowait(tS, rr[0]);
+      tmem_ld16_nowait(tS + 16u, rr[1]);
       tmem_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&s_free[g % 3]));
+      mbar_wait(smem_u32(&p_free[pb]), (uint32_t)(((g >> 1) & 1) ^ 1));    // P(g-2) has been consumed by its MMA
+      const uint32_t prow = sP + (uint32_t)pb * 16384u + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < 2; ++c4) {
         const int c = c4 * 16;
-        float v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[c4][e]);
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-          float p0 = fast_ex2(fmaf(v[e], scale_log2e, mneg));
-          float p1 = fast_ex2(fmaf(v[e + 1], scale_log2e, mneg));
+          float p0 = fast_ex2(fmaf(__uint_as_float(rr[c4][e]), scale_log2e, mneg));
+          float p1 = fast_ex2(fmaf(__uint_as_float(rr[c4][e + 1]), scale_log2e, mneg));
           if (!full) {
             if (j0 + c + e >= klim) p0 = 0.f;
             if (j0 + c + e + 1 >= klim) p1 = 0.f;
@@ -253,16 +293,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        // keys c..c+15 of this half -> 16-B chunks (c/8) and (c/8+1), XOR-swizzled by (row & 7)
-        const uint32_t ch = (uint32_t)(c >> 3);
+        // keys cb2+c .. +15 of the half tile -> 16-B chunks ch, ch+1 of the 128-B row, XOR-swizzled by (row & 7)
+        const uint32_t ch = (uint32_t)((cb2 + c) >> 3);
         const uint32_t a0 = prow + (((ch) ^ (uint32_t)(row & 7)) << 4);
         const uint32_t a1 = prow + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P stores -> visible to the tensor (async) proxy
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(smem_u32(&bar_p));
+      mbar_arrive(smem_u32(&p_full[pb]));
     }
     xch[half][row] = lsum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
