@@ -26,6 +26,7 @@ void llm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const int
 void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
                 int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, cudaStream_t st);
 void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, cudaStream_t st);
+void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st);
 void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st);
 void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, cudaStream_t st);
@@ -395,6 +396,12 @@ int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int 
   CVK_API_BEGIN
   CVK_REQUIRE(embeds && lens && logp && B > 0, "cvk_lm_forward_logp: bad arguments");
   llm_forward_logp(ctx, embeds, lens, B, logp, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s && logits, "cvk_lm_last_logits: bad arguments");
+  llm_last_logits(ctx, s, logits, (cudaStream_t)stream);
   CVK_API_END
 }
 int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,

@@ -275,21 +275,36 @@ __global__ void __launch_bounds__(D) finish_rms_kernel(const float* __restrict__
   tl_stamp(tl, 2);
 }
 
-// qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head), FOUR warps per
-// query head of the group (keys interleaved across them, flash-decoding style combine through shared memory).
-constexpr int AF_PARTS = 4;
-__global__ void __launch_bounds__((NH / NKV) * 32 * AF_PARTS)
+// qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head).
+// The attention itself is flash-decoding on warp-level tensor-core MMAs (m16n8k16, bf16 in / fp32 accumulate): the 7 query heads
+// of the group are the M rows of the tile (7 of 16 used - tcgen05's M >= 64 would waste 9/10 of the tile and need TMEM), each of
+// the 16 warps walks its own 16-key blocks with an online softmax held in registers, K and V fragments come straight from the
+// cache with 4-byte loads (V's key pairs are formed with byte permutes, the output dims of a 16-dim block are assigned to the
+// two n-tiles as evens / odds so that each lane ends up with 4 consecutive dims), P never leaves registers (the QK^T accumulator
+// layout is the A-operand layout of the P V MMA), and the warps' partial (max, sum, O) are merged through shared memory.
+// The CUDA-core version this replaces spent 6.8 + 4.7 us in QK^T / P V at 215 keys (bf16->fp32 conversion + FMA per element, per
+// head), a third of the whole decode step.
+constexpr int AF_WARPS = 16;
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h2);
+}
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {   // A rows 8..15 are zero
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(32 * AF_WARPS)
 attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int splits, int rows, const float* __restrict__ bias,
                   bf16* __restrict__ kc, bf16* __restrict__ vc, const int* __restrict__ ctx_len, int max_ctx,
                   const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo, long long* __restrict__ tl, long long* __restrict__ ph) {
-  extern __shared__ float sm_all[];            // [G][max_ctx] scores | [G+2][64] staging | [G][PARTS][2] max/sum | [G][PARTS][64] partial O
+  extern __shared__ float sm_all[];            // [G+2][64] staging | [WARPS][8][2] max/sum | [WARPS][G][64] partial O
   constexpr int G = NH / NKV;
   const int b = blockIdx.x, kvh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = warp / AF_PARTS, part = warp % AF_PARTS;     // query head of the group, key partition
-  float* stage = sm_all + (size_t)G * max_ctx;
+  float* stage = sm_all;
   float* ml = stage + (G + 2) * HD;
-  float* po = ml + G * AF_PARTS * 2;
+  float* po = ml + AF_WARPS * 8 * 2;
   pdl_trigger();
   tl_stamp(tl, 0);
   pdl_wait();
@@ -327,105 +342,105 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
   __syncthreads();
   AF_PHASE(3);
   const int L = min(pos + 1, max_ctx);
-  float* sc = sm_all + (size_t)w * max_ctx;
-  // Lane (r, c): key j0 + 4u + r, 16-byte chunk c of its row.  One load instruction of the warp covers 4 contiguous cache rows
-  // (512 B) and 8 of them are in flight per lane, so a block of 32 keys costs ONE memory round trip (the per-key scalar loop this
-  // replaces paid one round trip per 4 keys and dominated the decode step).
-  const int r = lane >> 3, c = lane & 7;
-  float q[8];
+  const int g = lane >> 2, tid = lane & 3;       // MMA fragment coordinates: row / column group
+  uint32_t qa[4][2];                             // Q as the A operand: [k step][dims tid*2.. | +8]; row g = query head g (row 7 unused)
 #pragma unroll
-  for (int e = 0; e < 8; ++e) q[e] = __bfloat162float(__float2bfloat16_rn(stage[w * HD + c * 8 + e])) * 0.125f;
-  float m = -INFINITY;
-  for (int j0 = part * 32; j0 < L; j0 += 32 * AF_PARTS) {
-    uint4 kk[8];
+  for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u * 4 + r;
-      kk[u] = j < L ? *reinterpret_cast<const uint4*>(kb + (size_t)j * HD + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+    for (int hv = 0; hv < 2; ++hv) {
+      const int d = kk * 16 + hv * 8 + tid * 2;
+      qa[kk][hv] = g < G ? pack_bf16x2(__bfloat162float(__float2bfloat16_rn(stage[g * HD + d])) * 0.125f,
+                                       __bfloat162float(__float2bfloat16_rn(stage[g * HD + d + 1])) * 0.125f)
+                         : 0u;
     }
+  float o[4][2][4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kk[u]);
-      float sdot = 0.f;
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h2[e]);
-        sdot = fmaf(q[2 * e], f.x, sdot);
-        sdot = fmaf(q[2 * e + 1], f.y, sdot);
-      }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-      const int j = j0 + u * 4 + r;
-      if (j < L) {
-        if (c == 0) sc[j] = sdot;
-        m = fmaxf(m, sdot);
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[q][t][e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  for (int j0 = warp * 16; j0 < L; j0 += AF_WARPS * 16) {
+    // every load of the block is issued before the first use: one memory round trip per 16 keys.  Rows past the end are
+    // clamped to the last valid row (finite data), their probabilities are forced to zero below.
+    uint32_t kf[2][4][2], vw[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (size_t)min(j0 + nt * 8 + g, L - 1) * HD);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        kf[nt][kk][0] = kr[kk * 8 + tid];
+        kf[nt][kk][1] = kr[kk * 8 + 4 + tid];
       }
     }
-  }
-  m = warp_max(m);
-  if (lane == 0) ml[(w * AF_PARTS + part) * 2] = m;
-  __syncthreads();
-  AF_PHASE(4);
-  float mh = ml[(w * AF_PARTS) * 2];
+    {
+      const uint32_t* v0 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + tid * 2, L - 1) * HD);
+      const uint32_t* v1 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + tid * 2 + 1, L - 1) * HD);
+      const uint32_t* v2 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 8 + tid * 2, L - 1) * HD);
+      const uint32_t* v3 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 9 + tid * 2, L - 1) * HD);
 #pragma unroll
-  for (int p2 = 1; p2 < AF_PARTS; ++p2) mh = fmaxf(mh, ml[(w * AF_PARTS + p2) * 2]);
-  float l = 0.f;
-  for (int j = part * 32 + lane; j < L; j += 32 * AF_PARTS) {
-    float p = expf(sc[j] - mh);
-    sc[j] = p;
-    l += p;
-  }
-  l = warp_sum(l);
-  if (lane == 0) ml[(w * AF_PARTS + part) * 2 + 1] = l;
-  __syncwarp();
-  // P.V over this warp's keys with the same (r, c) tiling: 8 output dims per lane, reduced over the 4 key sub-rows at the end
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int j0 = part * 32; j0 < L; j0 += 32 * AF_PARTS) {
-    uint4 vv[8];
-    float pp[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u * 4 + r;
-      vv[u] = j < L ? *reinterpret_cast<const uint4*>(vb + (size_t)j * HD + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-      pp[u] = j < L ? sc[j] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h2[e]);
-        acc[2 * e] = fmaf(pp[u], f.x, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(pp[u], f.y, acc[2 * e + 1]);
+      for (int q = 0; q < 4; ++q) {
+        vw[q][0] = v0[q * 8 + g];
+        vw[q][1] = v1[q * 8 + g];
+        vw[q][2] = v2[q * 8 + g];
+        vw[q][3] = v3[q * 8 + g];
       }
     }
-  }
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-  }
-  if (r == 0) {
+    for (int kk = 0; kk < 4; ++kk) {
+      mma_16816(s0, qa[kk][0], qa[kk][1], kf[0][kk][0], kf[0][kk][1]);
+      mma_16816(s1, qa[kk][0], qa[kk][1], kf[1][kk][0], kf[1][kk][1]);
+    }
+    // this lane: head g, keys j0 + 2 tid + {0,1} (s0) and j0 + 8 + 2 tid + {0,1} (s1)
+    const int ka = j0 + tid * 2;
+    const bool va0 = ka < L, va1 = ka + 1 < L, vb0 = ka + 8 < L, vb1 = ka + 9 < L;
+    float mx = fmaxf(fmaxf(va0 ? s0[0] : -INFINITY, va1 ? s0[1] : -INFINITY), fmaxf(vb0 ? s1[0] : -INFINITY, vb1 ? s1[1] : -INFINITY));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);          // finite: key j0 itself is valid
+    const float corr = __expf(m_run - m_new);      // exp(-inf) = 0 on the first block
+    const float p0 = va0 ? __expf(s0[0] - m_new) : 0.f, p1 = va1 ? __expf(s0[1] - m_new) : 0.f;
+    const float p2 = vb0 ? __expf(s1[0] - m_new) : 0.f, p3 = vb1 ? __expf(s1[1] - m_new) : 0.f;
+    l_run = l_run * corr + ((p0 + p1) + (p2 + p3));
+    m_run = m_new;
+    const uint32_t pa0 = pack_bf16x2(p0, p1), pa2 = pack_bf16x2(p2, p3);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) po[(w * AF_PARTS + part) * HD + c * 8 + e] = acc[e];
+    for (int q = 0; q < 4; ++q) {
+      o[q][0][0] *= corr; o[q][0][1] *= corr;
+      o[q][1][0] *= corr; o[q][1][1] *= corr;
+      // n-tile 0: even dims of the 16-dim block, n-tile 1: odd dims (low / high halves of the loaded words)
+      mma_16816(o[q][0], pa0, pa2, __byte_perm(vw[q][0], vw[q][1], 0x5410), __byte_perm(vw[q][2], vw[q][3], 0x5410));
+      mma_16816(o[q][1], pa0, pa2, __byte_perm(vw[q][0], vw[q][1], 0x7632), __byte_perm(vw[q][2], vw[q][3], 0x7632));
+    }
+  }
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (g < G) {
+    if (tid == 0) {
+      ml[(warp * 8 + g) * 2] = m_run;
+      ml[(warp * 8 + g) * 2 + 1] = l_run;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)     // dims 16 q + 4 tid .. + 3
+      *reinterpret_cast<float4*>(po + ((size_t)warp * G + g) * HD + q * 16 + tid * 4) = make_float4(o[q][0][0], o[q][1][0], o[q][0][1], o[q][1][1]);
   }
   __syncthreads();
   AF_PHASE(5);
-  if (part == 0) {
-    float lt = 0.f, t0 = 0.f, t1 = 0.f;
+  for (int e = threadIdx.x; e < G * HD; e += blockDim.x) {
+    const int hq = e / HD, d = e % HD;
+    float M = -INFINITY;
 #pragma unroll
-    for (int p2 = 0; p2 < AF_PARTS; ++p2) {
-      lt += ml[(w * AF_PARTS + p2) * 2 + 1];
-      t0 += po[(w * AF_PARTS + p2) * HD + lane];
-      t1 += po[(w * AF_PARTS + p2) * HD + lane + 32];
+    for (int w2 = 0; w2 < AF_WARPS; ++w2) M = fmaxf(M, ml[(w2 * 8 + hq) * 2]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < AF_WARPS; ++w2) {
+      const float wgt = __expf(ml[(w2 * 8 + hq) * 2] - M);    // warps without keys: exp(-inf) = 0
+      den = fmaf(wgt, ml[(w2 * 8 + hq) * 2 + 1], den);
+      num = fmaf(wgt, po[((size_t)w2 * G + hq) * HD + d], num);
     }
-    bf16* op = out + (size_t)b * ldo + (kvh * G + w) * HD;
-    const float inv = 1.f / lt;
-    op[lane] = __float2bfloat16_rn(t0 * inv);
-    op[lane + 32] = __float2bfloat16_rn(t1 * inv);
+    out[(size_t)b * ldo + (kvh * G + hq) * HD + d] = __float2bfloat16_rn(num / den);
   }
   AF_PHASE(6);
   tl_stamp(tl, 2);
@@ -920,7 +935,7 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   skinny_set_carveout();
   CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(((size_t)(NH / NKV) * max_context + (NH / NKV + 2) * HD + (NH / NKV) * AF_PARTS * (2 + HD)) * sizeof(float))));
+                                      (int)(((NH / NKV + 2) * HD + AF_WARPS * 8 * 2 + AF_WARPS * (NH / NKV) * HD) * sizeof(float))));
   s->count = (int*)alloc(sizeof(int) * max_batch);
   s->done = (int*)alloc(sizeof(int) * max_batch);
   s->live = (int*)alloc(sizeof(int));
@@ -1022,14 +1037,14 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
             (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next());
   ctx->launches++;
   CVK_LAUNCH_CHECK();
-  const size_t attn_smem = ((size_t)(NH / NKV) * s->max_ctx + (NH / NKV + 2) * HD + (NH / NKV) * AF_PARTS * (2 + HD)) * sizeof(float);
+  const size_t attn_smem = ((NH / NKV + 2) * HD + AF_WARPS * 8 * 2 + AF_WARPS * (NH / NKV) * HD) * sizeof(float);
   for (int li = 0; li < m->num_layers; ++li) {
     const LayerW& w = m->layers[li];
     bf16* kc = (bf16*)s->kcache + (size_t)li * s->max_batch * NKV * s->max_ctx * HD;
     bf16* vc = (bf16*)s->vcache + (size_t)li * s->max_batch * NKV * s->max_ctx * HD;
     Epilogue none;
     int sp = conv_gemm_skinny_ex(ctx, st, xn, w.qkv, none, s->scratch, s->scratch_floats, 1);
-    launch_ex(attn_fused_kernel, dim3(B, NKV), dim3((NH / NKV) * 32 * AF_PARTS), attn_smem, st, pdl, (const float*)s->scratch, sp, B,
+    launch_ex(attn_fused_kernel, dim3(B, NKV), dim3(32 * AF_WARPS), attn_smem, st, pdl, (const float*)s->scratch, sp, B,
               (const float*)w.qkv.bias, kc, vc, (const int*)s->ctx_len, s->max_ctx, (const float*)m->d_inv_freq, att.b16(), att.ld, ctx->tl_next(), (long long*)ctx->dbg);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
@@ -1132,6 +1147,11 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     CVK_CHECK_CUDA(cudaMemcpyAsync(live_host, s->live, sizeof(int), cudaMemcpyDeviceToHost, st));
     CVK_CHECK_CUDA(cudaStreamSynchronize(st));
   }
+}
+
+void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st) {
+  CVK_REQUIRE(s->B > 0 && s->logits, "cvk_lm_last_logits: no decode step has run");
+  CVK_CHECK_CUDA(cudaMemcpyAsync(logits, s->logits, sizeof(float) * (size_t)s->B * VOUT, cudaMemcpyDeviceToDevice, st));
 }
 
 // teacher-forced log-probs for every position (parity tests)

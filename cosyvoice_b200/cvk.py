@@ -55,6 +55,7 @@ SIGNATURES = {
     "cvk_lm_prefill": (ctypes.c_int, [_vp, _vp, _vp, _c_int_p, _vp, _c_int_p, ctypes.c_int, _vp]),
     "cvk_lm_decode": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _c_int_p, _vp]),
     "cvk_lm_forward_logp": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
+    "cvk_lm_last_logits": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "cvk_ras_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "cvk_mel_spectrogram": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
 }
@@ -301,6 +302,11 @@ class Context:
         embeds = _f32(embeds, self.device)
         out = torch.empty(embeds.shape[0], 6564, device=self.device)
         self._check(self.lib.cvk_lm_forward_logp(self.h, _ptr(embeds), _ints(lens), len(lens), _ptr(out), _stream()))
+        return out
+
+    def lm_last_logits(self, sess, B):
+        out = torch.empty(B, 6564, device=self.device)
+        self._check(self.lib.cvk_lm_last_logits(self.h, sess, _ptr(out), _stream()))
         return out
 
     def ras_sample(self, logp, history, hist_count, uniforms, ignore_eos):

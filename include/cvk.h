@@ -144,6 +144,9 @@ int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uni
                   void* stream);
 /* teacher-forced log-probs for parity tests: embeds [sum L, 896] -> logp [sum L, 6564] */
 int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens_host, int B, float* logp, void* stream);
+/* parity tests: the head logits [B][6564] (llm_decoder output, llm.py:542, before log_softmax) that the most recent decode step
+ * sampled from, copied to `logits` (device) */
+int cvk_lm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, void* stream);
 /* utils/common.py:138-167 + llm.py:150-160 as one kernel.  logp [B,V] (modified in place like the reference),
  * history [B, hist_ld] with hist_count [B] valid entries, uniforms [B,2], ignore_eos [B]; out ids [B]. */
 int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
