@@ -246,6 +246,71 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, int rows,
   }
 }
 
+// C == 256 (every LayerNorm of the flow estimator): the row lives in registers (two float4 per lane), read once with 16-byte
+// loads, written with 8/16-byte stores; the activation dispatch is outside the element loop.  FAST = bf16 mode (hardware
+// approximations, error two orders below the bf16 rounding of the stored result); the fp32 parity mode keeps libm.
+template <typename TO, bool FAST>
+__global__ void layernorm256_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, int act, float post_scale, const int* __restrict__ row2seq,
+                                    TO* __restrict__ out, int ldo, const float* __restrict__ rowvec, int rowvec_ld) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xp = x + (size_t)warp * ldx;
+  TO* op = out + (size_t)warp * ldo;
+  const int seq = row2seq ? row2seq[warp] : 0;
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  float v[8];
+  if (seq < 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(xp + c0), b = *reinterpret_cast<const float4*>(xp + c1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const float mean = warp_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) * (1.f / 256.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] -= mean;
+      q = fmaf(v[i], v[i], q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= rstd;
+    if (gamma) {
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), gb = *reinterpret_cast<const float4*>(gamma + c1);
+      v[0] *= ga.x; v[1] *= ga.y; v[2] *= ga.z; v[3] *= ga.w; v[4] *= gb.x; v[5] *= gb.y; v[6] *= gb.z; v[7] *= gb.w;
+      if (beta) {
+        const float4 ba = *reinterpret_cast<const float4*>(beta + c0), bb = *reinterpret_cast<const float4*>(beta + c1);
+        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w; v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+      }
+    }
+    if (act == ACT_MISH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = FAST ? apply_act_fast(ACT_MISH, v[i], 0.f, 1.f) : apply_act(ACT_MISH, v[i], 0.f, 1.f);
+    } else if (act != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = FAST ? apply_act_fast(act, v[i], 0.f, 1.f) : apply_act(act, v[i], 0.f, 1.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= post_scale;
+    if (rowvec) {
+      const float* rv = rowvec + (size_t)seq * rowvec_ld;
+      const float4 ra = *reinterpret_cast<const float4*>(rv + c0), rb = *reinterpret_cast<const float4*>(rv + c1);
+      v[0] += ra.x; v[1] += ra.y; v[2] += ra.z; v[3] += ra.w; v[4] += rb.x; v[5] += rb.y; v[6] += rb.z; v[7] += rb.w;
+    }
+  }
+  if constexpr (sizeof(TO) == 4) {
+    *reinterpret_cast<float4*>((float*)op + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>((float*)op + c1) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    *reinterpret_cast<uint2*>((bf16*)op + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>((bf16*)op + c1) = make_uint2(*reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+  }
+}
+
 // Qwen2 RMSNorm (modeling_qwen2.py:258-263): w * (x * rsqrt(mean(x^2) + eps))
 template <typename TO>
 __global__ void rmsnorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ gamma, float eps,
@@ -336,6 +401,22 @@ void layernorm(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const float* gamma, 
   CVK_REQUIRE(x.dtype == DT_F32, "layernorm input must be fp32");
   int rows = x.rows, C = x.cols;
   int blocks = ceil_div(rows, 8);
+  const bool vec = C == 256 && x.ld % 4 == 0 && ((uintptr_t)x.p & 15) == 0 && (out.ld * out.esize()) % 16 == 0 && ((uintptr_t)out.p & 15) == 0 &&
+                   (!rowvec || (rowvec_ld % 4 == 0 && ((uintptr_t)rowvec & 15) == 0)) && (!gamma || ((uintptr_t)gamma & 15) == 0) &&
+                   (!beta || ((uintptr_t)beta & 15) == 0);
+  if (vec) {
+    const bool fast = ctx->precision == CVK_PREC_BF16;
+    if (out.dtype == DT_F32) {
+      if (fast) layernorm256_kernel<float, true><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, gamma, beta, eps, act, post_scale, row2seq, out.f32(), out.ld, rowvec, rowvec_ld);
+      else layernorm256_kernel<float, false><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, gamma, beta, eps, act, post_scale, row2seq, out.f32(), out.ld, rowvec, rowvec_ld);
+    } else {
+      if (fast) layernorm256_kernel<bf16, true><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, gamma, beta, eps, act, post_scale, row2seq, out.b16(), out.ld, rowvec, rowvec_ld);
+      else layernorm256_kernel<bf16, false><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, gamma, beta, eps, act, post_scale, row2seq, out.b16(), out.ld, rowvec, rowvec_ld);
+    }
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    return;
+  }
   if (out.dtype == DT_F32)
     layernorm_kernel<float><<<blocks, 256, 0, st>>>(x.f32(), x.ld, rows, C, gamma, beta, eps, act, post_scale, row2seq, out.f32(), out.ld, rowvec, rowvec_ld);
   else
