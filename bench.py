@@ -268,7 +268,7 @@ def run_ours(args):
     value = audio_s / (dev_ms / 1000.0)
     e2e_v = audio_e2e / (e2e_ms / 1000.0)
     # dominant kernel family = the one with the largest share of device time
-    fam_names = ["conv_gemm_tc (tcgen05 bf16)", "conv_gemm_simt (fp32 CUDA cores)", "attention (fp32 math flash kernel)"]
+    fam_names = ["conv_gemm_tc (tcgen05 bf16)", "conv_gemm_simt (fp32 CUDA cores)", "attention (tcgen05 flash kernel; fp32-math CUDA-core kernel for rel-pos / fp32 mode)"]
     dom = max(range(3), key=lambda f: prof[f]["ms"])
     p = prof[dom]
     if dom == 0:
@@ -278,7 +278,12 @@ def run_ours(args):
         # CUDA-core kernels: report against the tensor roof they should be moved to (frac shows the gap)
         ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
-    roof.update({"traffic": None, "kernel": fam_names[dom], "launches": p["launches"], "avg_launch_ms": p["ms"] / max(p["launches"], 1),
+    traffic, traffic_note = None, "no ncu capture committed for this kernel"
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    if dom == 0 and os.path.exists(tpath):            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from `ncu --set full`
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+    roof.update({"traffic": traffic, "traffic_note": traffic_note, "kernel": fam_names[dom], "launches": p["launches"], "avg_launch_ms": p["ms"] / max(p["launches"], 1),
                  "share_of_step": p["ms"] / dev_ms, "peak_source": pk["source"],
                  "families_ms": {fam_names[f]: prof[f]["ms"] for f in range(3)}})
     cpu = None
