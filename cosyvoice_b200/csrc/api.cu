@@ -27,6 +27,9 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
                 int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, cudaStream_t st);
 void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, cudaStream_t st);
 void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st);
+void llm_session_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, cudaStream_t st);
+void llm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids, const int32_t* kinds, int n, cudaStream_t st);
+void llm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, cudaStream_t st);
 void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st);
 void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, cudaStream_t st);
@@ -396,6 +399,24 @@ int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int 
   CVK_API_BEGIN
   CVK_REQUIRE(embeds && lens && logp && B > 0, "cvk_lm_forward_logp: bad arguments");
   llm_forward_logp(ctx, embeds, lens, B, logp, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s != nullptr, "cvk_lm_begin: bad arguments");
+  llm_session_begin(ctx, s, B, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids_host, const int32_t* kinds_host, int n, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s && ids_host && kinds_host && n > 0, "cvk_lm_feed: bad arguments");
+  llm_feed(ctx, s, ids_host, kinds_host, n, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_lm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(s && logp, "cvk_lm_next_logp: bad arguments");
+  llm_next_logp(ctx, s, logp, (cudaStream_t)stream);
   CVK_API_END
 }
 int cvk_lm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, void* stream) {

@@ -46,6 +46,7 @@ struct cvk_lm_session {
   int* ctx_len = nullptr;   // [max_batch] cache position of the token currently being fed
   int* base_len = nullptr;  // [max_batch] prompt length L0
   bool fresh = false;
+  int fed = 0;              // positions pushed by cvk_lm_feed since cvk_lm_begin
   int64_t graph_kernels = 0;
   int* count = nullptr;     // [max_batch] tokens generated so far
   int* done = nullptr;      // [max_batch]
@@ -926,8 +927,17 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->base_len = (int*)alloc(sizeof(int) * max_batch);
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT * (int)sizeof(float)));
   CVK_REQUIRE((NH / NKV) * max_context * sizeof(float) <= 200 * 1024, "session context too long for the decode attention kernel");
-  CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
-  CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NH / NKV) * max_context * sizeof(float))));
+  {
+    // the limit is per function, not per session: never lower it for a smaller session created later
+    static int decode_attn_smem = 0;
+    const int need = (int)((NH / NKV) * max_context * sizeof(float));
+    CVK_REQUIRE(need <= 200 * 1024, "session context too long for the decode attention kernel (max ~7300 positions)");
+    if (need > decode_attn_smem) {
+      CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+      CVK_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+      decode_attn_smem = need;
+    }
+  }
   // keep every kernel of the decode step on the same (maximum) shared-memory carveout: alternating carveouts between
   // consecutive kernels forces an SM reconfiguration (idle + several microseconds) at every boundary
   CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1147,6 +1157,83 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     CVK_CHECK_CUDA(cudaMemcpyAsync(live_host, s->live, sizeof(int), cudaMemcpyDeviceToHost, st));
     CVK_CHECK_CUDA(cudaStreamSynchronize(st));
   }
+}
+
+// ---------------------------------------------------------------------------------------------- incremental feeding
+// Primitives for the text-streaming LM (Qwen2LM.inference_bistream, llm.py:551-661), whose control flow (5 text : 15 speech
+// interleaving, fill-token forcing) lives on the host: start an empty session, push arbitrary embeddings (text ids ->
+// embed_tokens, speech ids -> speech_embedding, 0/1 -> llm_embedding sos/task) through the cached decode path one position at a
+// time, read the log-probabilities of the next token.  Sampling is cvk_ras_sample.
+namespace {
+__global__ void feed_embed_kernel(int kind, int id, int B, const float* __restrict__ text_emb, const float* __restrict__ llm_emb,
+                                  const float* __restrict__ speech_emb, float* __restrict__ x) {
+  const float* src = kind == 0 ? text_emb + (size_t)id * D : (kind == 1 ? speech_emb + (size_t)id * D : llm_emb + (size_t)id * D);
+  for (int b = 0; b < B; ++b)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) x[(size_t)b * D + c] = src[c];
+}
+__global__ void bump_ctx_kernel(int* __restrict__ ctx_len, int B) {
+  if (threadIdx.x < B) ctx_len[threadIdx.x] += 1;
+}
+__global__ void zero_state_kernel(int* ctx_len, int* base_len, int* live, int n, int B) {
+  if (threadIdx.x < n) {
+    ctx_len[threadIdx.x] = 0;
+    base_len[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) *live = B;
+}
+}  // namespace
+
+void llm_session_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, cudaStream_t st) {
+  CVK_REQUIRE(ctx->llm, "llm stage not finalised");
+  CVK_REQUIRE(B >= 1 && B <= s->max_batch && s->max_batch <= 1024, "cvk_lm_begin: bad batch");
+  if (s->graph) {
+    cudaGraphExecDestroy(s->graph);
+    s->graph = nullptr;
+  }
+  zero_state_kernel<<<1, round_up(s->max_batch, 32), 0, st>>>(s->ctx_len, s->base_len, s->live, s->max_batch, B);
+  CVK_CHECK_CUDA(cudaMemsetAsync(s->hidden, 0, sizeof(float) * (size_t)s->max_batch * D, st));
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  s->B = B;
+  s->fresh = true;
+  s->fed = 0;
+}
+
+// ids / kinds: HOST arrays of n entries (kind 0 text id, 1 speech id, 2 llm_embedding row); every row of the session receives the
+// same positions (the text-streaming path is one utterance per session)
+void llm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids, const int32_t* kinds, int n, cudaStream_t st) {
+  const LlmModel* m = ctx->llm;
+  CVK_REQUIRE(m && s->B > 0, "cvk_lm_begin or cvk_lm_prefill must run before cvk_lm_feed");
+  CVK_REQUIRE(s->fed + n < s->max_ctx, "cvk_lm_feed: session context exhausted");
+  const int adt = s->kv_dtype, B = s->B;
+  Mat x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N), att(s->att, adt, B, D, D),
+      gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF);
+  for (int i = 0; i < n; ++i) {
+    const int kind = kinds[i], id = ids[i];
+    CVK_REQUIRE((kind == 0 && id >= 0 && id < 151936) || (kind == 1 && id >= 0 && id < VOUT) || (kind == 2 && id >= 0 && id < 2),
+                "cvk_lm_feed: id out of range");
+    feed_embed_kernel<<<1, 256, 0, st>>>(kind, id, B, m->text_emb, m->llm_emb, m->speech_emb, s->x);
+    for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
+    bump_ctx_kernel<<<1, round_up(B, 32), 0, st>>>(s->ctx_len, B);
+    ctx->launches += 2;
+    CVK_LAUNCH_CHECK();
+  }
+  CVK_CHECK_CUDA(cudaMemcpyAsync(s->hidden, s->x, sizeof(float) * (size_t)B * D, cudaMemcpyDeviceToDevice, st));
+  s->fed += n;
+  s->fresh = false;      // the step-graph decode (cvk_lm_decode) is not mixed with host-driven feeding
+}
+
+// log_softmax(llm_decoder(final_norm(hidden))) of the last fed position -> logp [B][6564] (device)
+void llm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, cudaStream_t st) {
+  const LlmModel* m = ctx->llm;
+  CVK_REQUIRE(m && s->B > 0 && s->fed > 0, "cvk_lm_feed must run before cvk_lm_next_logp");
+  const int B = s->B;
+  Mat hid(s->hidden, DT_F32, B, D, D), xn(s->xn, s->kv_dtype, B, D, D), logits(s->logits, DT_F32, B, VOUT, VOUT);
+  head_logits(ctx, st, m, hid, xn, logits, s);
+  logsoftmax_rows_kernel<<<B, SAMPLER_THREADS, 0, st>>>(s->logits, VOUT);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  CVK_CHECK_CUDA(cudaMemcpyAsync(logp, s->logits, sizeof(float) * (size_t)B * VOUT, cudaMemcpyDeviceToDevice, st));
 }
 
 void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st) {

@@ -56,6 +56,9 @@ SIGNATURES = {
     "cvk_lm_decode": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _c_int_p, _vp]),
     "cvk_lm_forward_logp": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
     "cvk_lm_last_logits": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "cvk_lm_begin": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "cvk_lm_feed": (ctypes.c_int, [_vp, _vp, _c_int_p, _c_int_p, ctypes.c_int, _vp]),
+    "cvk_lm_next_logp": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "cvk_ras_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "cvk_mel_spectrogram": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
 }
@@ -302,6 +305,18 @@ class Context:
         embeds = _f32(embeds, self.device)
         out = torch.empty(embeds.shape[0], 6564, device=self.device)
         self._check(self.lib.cvk_lm_forward_logp(self.h, _ptr(embeds), _ints(lens), len(lens), _ptr(out), _stream()))
+        return out
+
+    def lm_begin(self, sess, B=1):
+        self._check(self.lib.cvk_lm_begin(self.h, sess, B, _stream()))
+
+    def lm_feed(self, sess, ids, kinds):
+        """ids / kinds: python int lists (kind 0 text id, 1 speech id, 2 llm_embedding row)"""
+        self._check(self.lib.cvk_lm_feed(self.h, sess, _ints(ids), _ints(kinds), len(ids), _stream()))
+
+    def lm_next_logp(self, sess, B=1):
+        out = torch.empty(B, 6564, device=self.device)
+        self._check(self.lib.cvk_lm_next_logp(self.h, sess, _ptr(out), _stream()))
         return out
 
     def lm_last_logits(self, sess, B):

@@ -194,6 +194,96 @@ class B200CosyVoice2Model:
                 self.stream.wait_stream(self._lm_streams[g])
         return out
 
+    def lm_generate_bistream(self, text, prompt_text, prompt_speech_token, uniforms=None):
+        """llm/llm.py:551-661 (Qwen2LM.inference_bistream): `text` is a generator of int32 [1,k] chunks; speech ids are yielded
+        as soon as they are decoded.  The interleaving (5 text : 15 speech), the forced / sampled fill tokens and the final
+        'decode until eos' phase are the reference's control flow line for line; the arithmetic runs on the device through
+        cvk_lm_begin / cvk_lm_feed / cvk_lm_next_logp / cvk_ras_sample.  uniforms [n,2]: row len(out_tokens) is consumed by the
+        draw that produces that token (default: drawn from the model's generator)."""
+        mix_text, mix_speech = 5, 15
+        fill_token, speech_vocab = 6563, 6561
+        TEXT, SPEECH, LLM = 0, 1, 2
+        d = self.device
+        ptext = [int(x) for x in prompt_text.reshape(-1).tolist()]
+        pspeech = [int(x) for x in prompt_speech_token.reshape(-1).tolist()]
+        max_ctx = 4096
+        with torch.cuda.stream(self.stream), self.ctx.lock:
+            sess = self._session(1, max_ctx - 8, chain=-1)
+            self.ctx.lm_begin(sess, 1)
+        if uniforms is None and self.uniforms_override is not None:
+            uniforms = self.uniforms_override[:, 0, :]
+        # `lm_input` has the reference variable's exact life cycle (list of (kind, id) positions): every model call pushes ALL
+        # of it, it is replaced after a yielded token and - like the reference - left untouched when a fill token ends a decode
+        # burst, so a final phase entered right after a fill token pushes that last input a second time (llm.py:634-637, 643).
+        lm_input = [(LLM, 0)]
+        text_cache = list(ptext)
+        out_tokens = []
+        next_fill_index = (len(pspeech) // mix_speech + 1) * mix_speech - len(pspeech)
+        fed = [0]
+
+        def forward(want_logp):
+            """llm.py:617-622: push lm_input through the cached model; log-probs of the next id"""
+            with torch.cuda.stream(self.stream), self.ctx.lock:
+                fed[0] += len(lm_input)
+                if fed[0] >= max_ctx - 16:
+                    raise RuntimeError("text-streaming LM: session context exhausted")
+                self.ctx.lm_feed(sess, [i for _, i in lm_input], [k for k, _ in lm_input])
+                return self.ctx.lm_next_logp(sess, 1) if want_logp else None
+
+        def sample(logp, ignore_eos):
+            """llm.py:627 / 650 sampling_ids"""
+            with torch.cuda.stream(self.stream), self.ctx.lock:
+                i = len(out_tokens)
+                u = uniforms[i].reshape(1, 2) if uniforms is not None else torch.rand(1, 2, device=d, generator=self.generator)
+                hist = torch.tensor([out_tokens[-16:] or [0]], dtype=torch.int32)
+                top = self.ctx.ras_sample(logp, hist, torch.tensor([min(len(out_tokens), 16)], dtype=torch.int32), u,
+                                          torch.tensor([1 if ignore_eos else 0], dtype=torch.int32))
+                return int(top.item())
+
+        for this_text in text:
+            text_cache += [int(x) for x in this_text.reshape(-1).tolist()]
+            while pspeech:                                            # llm.py:595-604
+                if len(text_cache) >= mix_text:
+                    lm_input = lm_input + [(TEXT, t) for t in text_cache[:mix_text]] + [(SPEECH, t) for t in pspeech[:mix_speech]]
+                    text_cache, pspeech = text_cache[mix_text:], pspeech[mix_speech:]
+                else:
+                    break
+            if not pspeech:                                           # llm.py:606-640
+                if (out_tokens and out_tokens[-1] == fill_token) or (not out_tokens and len(lm_input) == 1):
+                    if len(text_cache) >= mix_text:
+                        lm_text = [(TEXT, t) for t in text_cache[:mix_text]]
+                        lm_input = lm_text if (out_tokens and out_tokens[-1] == fill_token) else lm_input + lm_text
+                        text_cache = text_cache[mix_text:]
+                    else:
+                        continue
+                while True:
+                    forced = next_fill_index != -1 and len(out_tokens) == next_fill_index
+                    logp = forward(want_logp=not forced)              # the reference runs the model before overriding the draw
+                    if forced:
+                        top = fill_token
+                        next_fill_index += mix_speech + 1
+                    else:
+                        top = sample(logp, ignore_eos=True)
+                    if top == fill_token:
+                        next_fill_index = len(out_tokens) + mix_speech + 1
+                    out_tokens.append(top)
+                    if top >= speech_vocab:
+                        if top == fill_token:
+                            break
+                        raise ValueError(f"should not get token {top}")
+                    yield top
+                    lm_input = [(SPEECH, top)]
+        lm_input = lm_input + [(TEXT, t) for t in text_cache] + [(LLM, 1)]       # llm.py:643
+        while True:
+            top = sample(forward(want_logp=True), ignore_eos=False)
+            out_tokens.append(top)
+            if top >= speech_vocab:
+                if top == speech_vocab:
+                    break
+                raise ValueError(f"should not get token {top}")
+            yield top
+            lm_input = [(SPEECH, top)]
+
     # ---------------------------------------------------------------- flow + vocoder
     def flow_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True):
         """lists per utterance: tokens [1,N] int, prompt_tokens [1,P], prompt_feats [1,Tp,80], embeddings [1,192]
@@ -290,6 +380,20 @@ class B200CosyVoice2Model:
 
     def llm_job(self, text, prompt_text, llm_prompt_speech_token, llm_embedding, uuid):
         """cli/model.py:101-129 (non-generator text).  Tokens are appended to the session list as they arrive."""
+        if hasattr(text, "__next__") or (hasattr(text, "__iter__") and not torch.is_tensor(text)):
+            # cli/model.py:113-123: text generator -> bi-stream decoding, tokens appended one by one
+            cur_silent, max_silent = 0, 5                  # cli/model.py:102,121-127 (silent_tokens is empty for CosyVoice2)
+            for tok in self.lm_generate_bistream(iter(text), prompt_text, llm_prompt_speech_token):
+                if tok in self.silent_tokens:
+                    cur_silent += 1
+                    if cur_silent > max_silent:
+                        continue
+                else:
+                    cur_silent = 0
+                self.tts_speech_token_dict[uuid].append(tok)
+            self.llm_end_dict[uuid] = True
+            return
+
         def progress(out_ids, out_count, live):
             n = int(out_count[0].item())
             have = len(self.tts_speech_token_dict[uuid])

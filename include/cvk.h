@@ -144,6 +144,15 @@ int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uni
                   void* stream);
 /* teacher-forced log-probs for parity tests: embeds [sum L, 896] -> logp [sum L, 6564] */
 int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens_host, int B, float* logp, void* stream);
+/* Text-streaming LM (Qwen2LM.inference_bistream, llm.py:551-661: the caller interleaves 5 text : 15 speech embeddings and forces
+ * fill tokens; cli/model.py:113-123 drives it when `text` is a generator).  cvk_lm_begin empties the session (B rows, normally 1);
+ * cvk_lm_feed pushes n positions through the KV-cached decode path (llm.py:617-621 forward_one_step): ids_host / kinds_host are
+ * HOST arrays, kind 0 = text id (embed_tokens), 1 = speech id (speech_embedding), 2 = llm_embedding row (0 sos, 1 task_id);
+ * cvk_lm_next_logp writes log_softmax(llm_decoder(y_pred[:, -1])) (llm.py:622) of the last position to logp [B][6564] (device).
+ * The draw itself is cvk_ras_sample (llm.py:627 sampling_ids). */
+int cvk_lm_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, void* stream);
+int cvk_lm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids_host, const int32_t* kinds_host, int n, void* stream);
+int cvk_lm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, void* stream);
 /* parity tests: the head logits [B][6564] (llm_decoder output, llm.py:542, before log_softmax) that the most recent decode step
  * sampled from, copied to `logits` (device) */
 int cvk_lm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, void* stream);

@@ -49,6 +49,17 @@ def lm_case(n_text=7, n_prompt_text=4, n_prompt_speech=9, seed=3, n_uniform=400)
     return text, ptext, ptok, U
 
 
+def bistream_case(seed=11, n_uniform=400):
+    """Text-streaming LM case: prompt text 6 ids, prompt speech 22 tokens (one full 5:15 block + 7 left over, first forced fill
+    after 8 generated tokens), text arriving in chunks of 3 / 4 / 2 / 5 / 3 ids."""
+    g = _g(4000 + seed)
+    ptext = torch.randint(0, 151643, (1, 6), dtype=torch.int32, generator=g)
+    ptok = torch.randint(0, 6561, (1, 22), dtype=torch.int32, generator=g)
+    chunks = [torch.randint(0, 151643, (1, n), dtype=torch.int32, generator=g) for n in (3, 4, 2, 5, 3)]
+    U = torch.rand(n_uniform, 2, generator=g)
+    return chunks, ptext, ptok, U
+
+
 def sampling_case(n=64, V=6564, seed=4):
     """Random log-prob vectors of varying peakiness + random decoded histories + uniforms."""
     g = _g(5000 + seed)

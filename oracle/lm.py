@@ -151,3 +151,88 @@ def inference(sd, text, prompt_text, prompt_speech_token, uniforms, num_layers=2
         out.append(top)
         lm_in = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
     return (out, logps) if return_logp else out
+
+
+FILL_TOKEN = 6563          # llm.py:277 speech_token_size + 2
+MIX_RATIO = (5, 15)        # llm.py:267
+
+
+def bistream_state_dict(num_layers):
+    """Synthetic weights for the text-streaming case: the plain synthetic model practically never emits the stop id, and
+    inference_bistream has no length cap (llm.py:642-661 decodes 'until met eos'), so the eos logit is raised until eos is a likely
+    draw once it is allowed (final phase only - it is masked during the interleaved phase, llm.py:627)."""
+    sd = {k: v.clone() for k, v in synth_state_dict(num_layers).items()}
+    sd["llm_decoder.bias"][6561] += 8.0
+    sd["llm_decoder.bias"][6562] -= 30.0       # the other ids >= 6561 raise ValueError in the reference (llm.py:635, 653)
+    sd["llm_decoder.bias"][6563] -= 30.0       # natural fill tokens are possible in principle; this case only has forced ones
+    return sd
+
+
+def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, uniforms, num_layers=24, return_trace=False):
+    """llm.py:551-661 (Qwen2LM branch).  text_chunks: list of int tensors [1,k] (the text generator); uniforms [n,2], row
+    len(out_tokens) is consumed by the draw that produces out_tokens[len(out_tokens)].  Returns the yielded ids (fill tokens are
+    kept in the internal history only) and optionally the list of out_tokens including fill tokens."""
+    emb_t = lambda ids: F.embedding(ids.long(), sd["llm.model.model.embed_tokens.weight"])
+    sos = sd["llm_embedding.weight"][0].reshape(1, 1, -1)
+    task = sd["llm_embedding.weight"][1].reshape(1, 1, -1)
+    sp = F.embedding(prompt_speech_token.long(), sd["speech_embedding.weight"]) if prompt_speech_token.shape[1] else torch.zeros(1, 0, D)
+    lm_input = sos
+    out_tokens, yielded, past = [], [], None
+    text_cache = emb_t(prompt_text)
+    P = prompt_speech_token.shape[1]
+    next_fill_index = (int(P / MIX_RATIO[1]) + 1) * MIX_RATIO[1] - P
+
+    def step(lm_input, past, ignore_eos):
+        y, past = qwen2_forward(sd, lm_input, past, num_layers)
+        logp = logprobs(sd, y[:, -1]).squeeze(0)
+        return logp, past
+
+    for this_text in text_chunks:
+        text_cache = torch.cat([text_cache, emb_t(this_text)], dim=1)
+        while sp.shape[1] != 0:
+            if text_cache.shape[1] >= MIX_RATIO[0]:
+                lm_input = torch.cat([lm_input, text_cache[:, :MIX_RATIO[0]], sp[:, :MIX_RATIO[1]]], dim=1)
+                text_cache, sp = text_cache[:, MIX_RATIO[0]:], sp[:, MIX_RATIO[1]:]
+            else:
+                break
+        if sp.shape[1] == 0:
+            if (len(out_tokens) != 0 and out_tokens[-1] == FILL_TOKEN) or (len(out_tokens) == 0 and lm_input.shape[1] == 1):
+                if text_cache.shape[1] >= MIX_RATIO[0]:
+                    lm_input_text = text_cache[:, :MIX_RATIO[0]]
+                    if len(out_tokens) != 0 and out_tokens[-1] == FILL_TOKEN:
+                        lm_input = lm_input_text
+                    else:
+                        lm_input = torch.cat([lm_input, lm_input_text], dim=1)
+                    text_cache = text_cache[:, MIX_RATIO[0]:]
+                else:
+                    continue
+            while True:
+                logp, past = step(lm_input, past, True)
+                if next_fill_index != -1 and len(out_tokens) == next_fill_index:
+                    top = FILL_TOKEN
+                    next_fill_index += MIX_RATIO[1] + 1
+                else:
+                    i = len(out_tokens)
+                    top = sampling.ras_sample(logp.numpy(), out_tokens, float(uniforms[i, 0]), float(uniforms[i, 1]), ignore_eos=True)
+                if top == FILL_TOKEN:
+                    next_fill_index = len(out_tokens) + MIX_RATIO[1] + 1
+                out_tokens.append(top)
+                if top >= 6561:
+                    if top == FILL_TOKEN:
+                        break
+                    raise ValueError(f"should not get token {top}")
+                yielded.append(top)
+                lm_input = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
+    lm_input = torch.cat([lm_input, text_cache, task], dim=1)
+    while True:
+        logp, past = step(lm_input, past, False)
+        i = len(out_tokens)
+        top = sampling.ras_sample(logp.numpy(), out_tokens, float(uniforms[i, 0]), float(uniforms[i, 1]), ignore_eos=False)
+        out_tokens.append(top)
+        if top >= 6561:
+            if top == 6561:
+                break
+            raise ValueError(f"should not get token {top}")
+        yielded.append(top)
+        lm_input = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
+    return (yielded, out_tokens) if return_trace else yielded

@@ -163,6 +163,38 @@ def gen_lm():
              logp_rows=rlogp[-4:, ::41].numpy(), logp_step0_top=np.sort(logps[0].numpy())[-32:])
 
 
+def gen_bistream():
+    """cosyvoice/llm/llm.py:551-661 (Qwen2LM.inference_bistream) with the text arriving in chunks."""
+    print("lm bistream")
+    NL = 2
+    ref = refimport.build_llm(num_layers=NL)
+    sd = lm.bistream_state_dict(NL)
+    ref.load_state_dict(sd, strict=True)
+    chunks, ptext, ptok, U = cases.bistream_case()
+    st = {"i": 0, "c": 0}
+
+    def get_u():
+        u = float(U[st["i"], min(st["c"], 1)])
+        st["c"] += 1
+        return u
+    orig = ref.sampling_ids
+
+    def sampling_ids(weighted_scores, decoded_tokens, sampling_, ignore_eos=True):
+        st["i"], st["c"] = len(decoded_tokens), 0          # uniforms are indexed by the position in out_tokens
+        return orig(weighted_scores, decoded_tokens, sampling_, ignore_eos)
+    ref.sampling_ids = sampling_ids
+    ids = []
+    with patched_multinomial(get_u):
+        for tok in ref.inference_bistream(text=iter(chunks), prompt_text=ptext, prompt_text_len=torch.tensor([ptext.shape[1]], dtype=torch.int32),
+                                          prompt_speech_token=ptok, prompt_speech_token_len=torch.tensor([ptok.shape[1]], dtype=torch.int32),
+                                          embedding=torch.zeros(0, 192)):
+            ids.append(int(tok))
+    ref.sampling_ids = orig
+    o, trace = lm.inference_bistream(sd, chunks, ptext, ptok, U, NL, return_trace=True)
+    print(f"  {len(ids)} ids yielded, {sum(1 for t in trace if t == lm.FILL_TOKEN)} fill tokens, oracle == reference: {o == ids}")
+    save("lm_bistream_l2", ids=np.array(ids, dtype=np.int32), trace=np.array(trace, dtype=np.int32))
+
+
 def gen_sampling():
     print("sampling")
     refimport.install()
@@ -273,6 +305,6 @@ def gen_stream():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "flow", "lm", "sampling", "mel", "masks", "stream"]
+    which = sys.argv[1:] or ["hift", "flow", "lm", "bistream", "sampling", "mel", "masks", "stream"]
     for w in which:
         globals()["gen_" + w]()

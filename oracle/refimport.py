@@ -242,8 +242,19 @@ def _pin_forward_one_step(enc):
     ``attention_mask=None`` (equivalent to an all-ones mask) to the unmodified HF model."""
     import types
 
+    class _CacheView:
+        """inference_bistream reads the cached length as ``cache[0][0].size(2)`` (llm.py:621): the tuple-style indexing that
+        the pinned transformers' DynamicCache still offers and 5.5's does not.  Index access only; HF gets the real object."""
+        def __init__(self, dc):
+            self.dc = dc
+
+        def __getitem__(self, i):
+            if hasattr(self.dc, "layers"):
+                return self.dc.layers[i].keys, self.dc.layers[i].values
+            return self.dc.key_cache[i], self.dc.value_cache[i]
+
     def forward_one_step(self, xs, masks, cache=None):
         outs = self.model(inputs_embeds=xs, attention_mask=None, output_hidden_states=True, return_dict=True,
-                          use_cache=True, past_key_values=cache)
-        return outs.hidden_states[-1], outs.past_key_values
+                          use_cache=True, past_key_values=cache.dc if isinstance(cache, _CacheView) else cache)
+        return outs.hidden_states[-1], _CacheView(outs.past_key_values)
     enc.forward_one_step = types.MethodType(forward_one_step, enc)

@@ -237,3 +237,15 @@ def test_decode_attention_logits_fused_vs_unfused_bf16(n_prompt):
     d_unfused = (lb - lt)[fin].abs().max().item()
     print(f"n_prompt={n_prompt}: max |logp - fp32| fused {d_fused:.4g}, unfused {d_unfused:.4g} (|logp| up to {lt[fin].abs().max().item():.3g})")
     assert d_fused < 1.5 * d_unfused + 0.05, (d_fused, d_unfused)
+
+
+def test_bistream_ids_match_reference_fp32(golden):
+    """§8 a7, text-streaming LM (llm.py:551-661) through cvk_lm_begin / cvk_lm_feed / cvk_lm_next_logp / cvk_ras_sample and the
+    host control flow of B200CosyVoice2Model.lm_generate_bistream: ids identical to the reference's, token for token."""
+    from cosyvoice_b200.model import B200CosyVoice2Model
+    g = golden("lm_bistream_l2")
+    chunks, ptext, ptok, U = cases.bistream_case()
+    m = B200CosyVoice2Model(precision="fp32", device=0, workspace_gb=2.0)
+    m.ctx.load_state_dict("llm", lm.bistream_state_dict(2), [2])            # LM stage only
+    ids = list(m.lm_generate_bistream(iter(chunks), ptext, ptok, uniforms=U))
+    assert ids == g["ids"].tolist()
