@@ -204,8 +204,7 @@ def run_ours(args):
         return model.tts_batch(inputs_dev, to_host=False, return_stats=True)
 
     def step_e2e():
-        # N > 1: the waveforms stay on the device until the NCCL gather; rank 0 then does the single device-to-host copy of the job
-        return model.tts_batch(pinned, to_host=(dist is None), return_stats=True)
+        return model.tts_batch(pinned, to_host=True, return_stats=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,7 +237,9 @@ def run_ours(args):
     prof = [model.ctx.profile_read(f) for f in range(3)]
     model.ctx.profile(0)
     # ---- timed region 2: end to end through the public API (pinned host inputs in, waveforms out to host)
-    step_e2e()
+    wavs, _ = step_e2e()
+    if dist is not None:
+        gather_waveforms(wavs, dist, dev)              # untimed: NCCL sets up its point-to-point channels on first use
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,10 +250,7 @@ def run_ours(args):
         audio_e2e += sum(w.shape[-1] for w in wavs) / 24000.0
         d2h = sum(w.numel() * 4 for w in wavs)
         if dist is not None:
-            with torch.cuda.stream(model.stream):
-                allw = gather_waveforms(wavs, dist, dev)                     # NCCL gather of the results + D2H on rank 0
-            if allw is not None:
-                d2h = sum(w.numel() * 4 for ws in allw for w in ws)
+            gather_waveforms(wavs, dist, dev)                                # NCCL gather of the results on rank 0
     f1.record(model.stream)
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1000 * (time.perf_counter() - t0))

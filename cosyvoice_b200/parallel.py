@@ -45,38 +45,34 @@ def broadcast_state_dicts(sds, device, llm_shapes, flow_shapes, hift_shapes, dis
 
 
 def gather_waveforms(wavs, dist, device):
-    """wavs: list of [1,N_i] tensors of this rank (device tensors are gathered without a host round trip).  Returns on rank 0 a
-    list (per rank) of lists of CPU waveforms, else None.  One collective for the lengths, one for the samples, and on rank 0 one
-    device-to-host copy per rank buffer (not per utterance)."""
+    """wavs: list of [1,N_i] tensors of this rank.  Returns on rank 0 a list (per rank) of lists of CPU waveforms, else None."""
     if dist is None or dist.get_world_size() == 1:
-        return [[w.cpu() for w in wavs]]
+        return [wavs]
     world, rank = dist.get_world_size(), dist.get_rank()
-    lens = torch.tensor([w.shape[-1] for w in wavs], dtype=torch.int64)
-    meta = torch.tensor([len(wavs), int(lens.sum()) if len(wavs) else 0], dtype=torch.int64, device=device)
-    metas = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    metas = torch.stack(metas).cpu()                       # one sync
-    maxn, total = int(metas[:, 0].max()), int(metas[:, 1].max())
+    lens = torch.tensor([w.shape[-1] for w in wavs], dtype=torch.int64, device=device)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = len(wavs)
+    dist.all_reduce(counts)
+    maxn = int(counts.max())
     lens_p = torch.zeros(maxn, dtype=torch.int64, device=device)
-    lens_p[:len(wavs)] = lens.to(device)
+    lens_p[:len(wavs)] = lens
     all_lens = [torch.zeros(maxn, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(all_lens, lens_p)
+    total = max(int(l.sum()) for l in all_lens)
     flat = torch.zeros(total, dtype=torch.float32, device=device)
     if wavs:
-        cat = torch.cat([w.reshape(-1).to(device, non_blocking=True) for w in wavs])
+        cat = torch.cat([w.reshape(-1).to(device) for w in wavs])
         flat[:cat.numel()] = cat
     bufs = [torch.zeros(total, dtype=torch.float32, device=device) for _ in range(world)] if rank == 0 else None
     dist.gather(flat, bufs, dst=0)
     if rank != 0:
         return None
-    all_lens = torch.stack(all_lens).cpu()
     out = []
     for r in range(world):
-        host = bufs[r][:int(metas[r, 1])].cpu()            # one D2H per rank
         o, lst = 0, []
-        for i in range(int(metas[r, 0])):
-            n = int(all_lens[r, i])
-            lst.append(host[o:o + n].unsqueeze(0))
+        for i in range(int(counts[r])):
+            n = int(all_lens[r][i])
+            lst.append(bufs[r][o:o + n].cpu().unsqueeze(0))
             o += n
         out.append(lst)
     return out
