@@ -89,3 +89,32 @@ def test_tts_batch_equals_single_requests(golden):
     ref = torch.from_numpy(g["offline_wav"])
     assert maxdiff(wavs[0][:, :24000], ref[:, :24000]) < 5e-3
     assert ((wavs[0] - ref).norm() / ref.norm()).item() < 0.05
+
+
+def test_tts_with_text_generator_bistream(golden):
+    """cli/model.py:113-123 + llm.py:551-661: `text` given as a generator -> the LM thread runs the text-streaming decode while
+    the main thread streams audio chunks.  The speech ids equal the reference's (golden from Qwen2LM.inference_bistream), so the
+    audio length is 960 samples per id and the chunk schedule is the deterministic hop 25 -> 50 -> 100 one."""
+    from cosyvoice_b200.model import B200CosyVoice2Model
+    g = golden("lm_bistream_l2")
+    chunks, ptext, ptok, U = cases.bistream_case()
+    kw = dict(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2)
+    m = B200CosyVoice2Model(precision="fp32", device=0, workspace_gb=4.0)
+    m.load_state_dicts(lm.bistream_state_dict(2), weights.synth_state_dict(flow.param_shapes(flow.FlowCfg(**kw)), 1986, flow.SYNTH_GAINS),
+                       weights.synth_state_dict(hift.param_shapes(), 1986, hift.SYNTH_GAINS))
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    ftok = ptok[:, :9]
+    m.uniforms_override = U[:, None, :]
+    m.token_hop_len = 25
+    try:
+        outs = [o["tts_speech"] for o in m.tts(text=iter(chunks), flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                               llm_prompt_speech_token=ptok, flow_prompt_speech_token=ftok,
+                                               prompt_speech_feat=pfeat[:, :18], stream=True)]
+    finally:
+        m.uniforms_override = None
+    n_ids = len(g["ids"])
+    assert sum(o.shape[1] for o in outs) == n_ids * 960
+    assert len(outs) >= 4 and all(torch.isfinite(o).all() for o in outs)
+    # first chunk: hop 25 + pad to a multiple of 25 of the 9 prompt tokens (cli/model.py:347-350) = 41 tokens minus the 8-frame
+    # mel cache kept back (3840 samples)
+    assert outs[0].shape[1] == 41 * 960 - 3840
