@@ -325,8 +325,9 @@ def cfm_noise(T):
     return torch.randn([1, 80, 50 * 300], generator=g)[:, :, :T]
 
 
-def cfm_solve(sd, mu, mask, spks, cond, n_timesteps=10, cfg=None, streaming=False, z=None):
-    """flow_matching.py:203-227 + 71-124 (cosine schedule, Euler, classifier-free guidance 0.7)."""
+def cfm_solve(sd, mu, mask, spks, cond, n_timesteps=10, cfg=None, streaming=False, z=None, est=None):
+    """flow_matching.py:203-227 + 71-124 (cosine schedule, Euler, classifier-free guidance 0.7).  ``est`` replaces the CosyVoice2
+    U-Net estimator (the CosyVoice3 DiT, oracle/dit.py) with the same (x, mask, mu, t, spks, cond, streaming) signature."""
     T = mu.shape[2]
     x = cfm_noise(T) if z is None else z
     t_span = torch.linspace(0, 1, n_timesteps + 1)
@@ -335,8 +336,9 @@ def cfm_solve(sd, mu, mask, spks, cond, n_timesteps=10, cfg=None, streaming=Fals
     zeros = torch.zeros_like(mu)
     for step in range(1, len(t_span)):
         x_in = torch.cat([x, x], 0)
-        out = estimator(sd, x_in, torch.cat([mask, mask], 0), torch.cat([mu, zeros], 0), torch.cat([t, t], 0),
-                        torch.cat([spks, torch.zeros_like(spks)], 0), torch.cat([cond, zeros], 0), cfg, streaming)
+        args = (x_in, torch.cat([mask, mask], 0), torch.cat([mu, zeros], 0), torch.cat([t, t], 0),
+                torch.cat([spks, torch.zeros_like(spks)], 0), torch.cat([cond, zeros], 0))
+        out = est(*args, streaming) if est is not None else estimator(sd, *args, cfg, streaming)
         d, dc = out[:1], out[1:]
         x = x + dt * ((1.0 + CFG_RATE) * d - CFG_RATE * dc)
         t = t + dt

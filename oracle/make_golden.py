@@ -127,6 +127,40 @@ def gen_flow():
 
 
 @torch.inference_mode()
+def gen_dit():
+    """CosyVoice3 flow: cosyvoice/flow/DiT/dit.py:145-176 (estimator) and cosyvoice/flow/flow.py:369-414 (inference)."""
+    print("dit (CosyVoice3 flow)")
+    from . import dit
+    for tag, depth in (("small", 2), ("full", 22)):
+        ref = refimport.build_flow3(depth)
+        shapes = dit.flow_param_shapes(depth)
+        rsd = ref.state_dict()
+        assert set(rsd.keys()) == set(shapes.keys()), set(rsd.keys()) ^ set(shapes.keys())
+        assert all(tuple(rsd[k].shape) == tuple(shapes[k]) for k in shapes)
+        sd = weights.synth_state_dict(shapes, 1986, dit.SYNTH_GAINS)
+        ref.load_state_dict(sd, strict=True)
+        token, ptok, pfeat, emb = cases.flow_case()
+        N, P = token.shape[1], ptok.shape[1]
+        outs = {}
+        for name, streaming, finalize in (("offline", False, True), ("stream_final", True, True), ("stream_chunk", True, False)):
+            if tag == "full" and name == "stream_final":
+                continue
+            r, _ = ref.inference(token=token, token_len=torch.tensor([N]), prompt_token=ptok,
+                                 prompt_token_len=torch.tensor([P]), prompt_feat=pfeat,
+                                 prompt_feat_len=torch.tensor([2 * P]), embedding=emb, streaming=streaming, finalize=finalize)
+            o = dit.inference(sd, token, ptok, pfeat, emb, depth, streaming=streaming, finalize=finalize)
+            print(f"  {tag}/{name}: max|oracle-ref| {(r - o).abs().max():.3g}  (|mel| max {r.abs().max():.3g})")
+            outs["mel_" + name] = r.numpy()
+        x, mask, mu, t, spks, cond = cases.estimator_case(T=130)     # 130 frames: three 50-frame chunks in streaming mode
+        for streaming in (False, True):
+            r = ref.decoder.estimator(x, mask, mu, t, spks, cond, streaming=streaming)
+            o = dit.estimator(sd, x, mask, mu, t, spks, cond, depth, streaming)
+            print(f"  {tag}/estimator streaming={streaming}: max|oracle-ref| {(r - o).abs().max():.3g}  (|out| max {r.abs().max():.3g})")
+            outs["est_stream" if streaming else "est_offline"] = r.numpy()
+        save("dit_" + tag, **outs)
+
+
+@torch.inference_mode()
 def gen_lm():
     print("lm")
     for tag, NL in (("l2", 2), ("l24", 24)):
@@ -305,6 +339,6 @@ def gen_stream():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "flow", "lm", "bistream", "sampling", "mel", "masks", "stream"]
+    which = sys.argv[1:] or ["hift", "flow", "dit", "lm", "bistream", "sampling", "mel", "masks", "stream"]
     for w in which:
         globals()["gen_" + w]()

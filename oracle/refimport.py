@@ -73,6 +73,48 @@ class _GELU(nn.Module):
         return F.gelu(self.proj(x), approximate=self.approximate)
 
 
+# --------------------------------------------------------------------------- x_transformers restatement (CosyVoice3 DiT)
+class _RotaryEmbedding(nn.Module):
+    """x_transformers==2.11.24 ``RotaryEmbedding`` (requirements.txt:39) as used by cosyvoice/flow/DiT/dit.py:128,159:
+    ``inv_freq = base**-(arange(0, dim, 2)/dim)``; ``forward_from_seq_len(n)`` -> ``forward(arange(n))`` -> freqs [1, n, dim] with
+    every frequency duplicated in ADJACENT positions (``stack((f, f), -1)`` flattened), scale 1.0 (no xpos).  Restated from the
+    published source: the package is not installed offline, so parity of this class and of ``apply_rotary_pos_emb`` is unpinned."""
+
+    def __init__(self, dim, base=10000, interpolation_factor=1.0, **kw):
+        super().__init__()
+        self.register_buffer("inv_freq", 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim)), persistent=False)
+        self.interpolation_factor = interpolation_factor
+
+    def forward_from_seq_len(self, seq_len):
+        return self.forward(torch.arange(seq_len, device=self.inv_freq.device))
+
+    def forward(self, t):
+        if t.ndim == 1:
+            t = t[None, :]
+        freqs = torch.einsum("b i , j -> b i j", t.type_as(self.inv_freq), self.inv_freq) / self.interpolation_factor
+        freqs = torch.stack((freqs, freqs), dim=-1).flatten(-2)
+        return freqs, 1.0
+
+
+def _rotate_half(x):
+    x = x.reshape(*x.shape[:-1], -1, 2)
+    x1, x2 = x.unbind(dim=-1)
+    return torch.stack((-x2, x1), dim=-1).flatten(-2)
+
+
+def _apply_rotary_pos_emb(t, freqs, scale=1):
+    """x_transformers==2.11.24 ``apply_rotary_pos_emb``: partial rotary over the first ``freqs.shape[-1]`` channels of the LAST
+    dimension (the DiT applies it to the un-split [b, n, heads*dim_head] projections, so only the first head's 64 channels rotate,
+    cosyvoice/flow/DiT/modules.py:368-373), interleaved pairs (GPT-J style)."""
+    rot_dim, seq_len, orig_dtype = freqs.shape[-1], t.shape[-2], t.dtype
+    freqs = freqs[:, -seq_len:, :]
+    if t.ndim == 4 and freqs.ndim == 3:
+        freqs = freqs[:, None]
+    t, t_unrotated = t[..., :rot_dim], t[..., rot_dim:]
+    t = (t * freqs.cos() * scale) + (_rotate_half(t) * freqs.sin() * scale)
+    return torch.cat((t, t_unrotated), dim=-1).type(orig_dtype)
+
+
 class _Unused(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
@@ -143,6 +185,11 @@ def install():
         _mod("diffusers.models.lora", LoRACompatibleLinear=nn.Linear)
         _mod("diffusers.utils")
         _mod("diffusers.utils.torch_utils", maybe_allow_in_graph=lambda c: c)
+    try:
+        importlib.import_module("x_transformers.x_transformers")
+    except Exception:
+        _mod("x_transformers")
+        _mod("x_transformers.x_transformers", RotaryEmbedding=_RotaryEmbedding, apply_rotary_pos_emb=_apply_rotary_pos_emb)
     # matcha/utils/__init__.py imports hydra/lightning/rich; only audio.py is needed
     import logging
     mu = _mod("matcha.utils")
@@ -258,3 +305,29 @@ def _pin_forward_one_step(enc):
                           use_cache=True, past_key_values=cache.dc if isinstance(cache, _CacheView) else cache)
         return outs.hidden_states[-1], _CacheView(outs.past_key_values)
     enc.forward_one_step = types.MethodType(forward_one_step, enc)
+
+
+def build_dit(depth=22):
+    """Reference DiT estimator with the cosyvoice3.yaml hyper-parameters (depth reducible for fast tests)."""
+    install()
+    from cosyvoice.flow.DiT.dit import DiT
+    return DiT(dim=1024, depth=depth, heads=16, dim_head=64, ff_mult=2, mel_dim=80, mu_dim=80, spk_dim=80, out_channels=80,
+               static_chunk_size=50, num_decoding_left_chunks=-1).eval()
+
+
+def build_flow3(depth=22):
+    """Reference CausalMaskedDiffWithDiT (CosyVoice3 flow) with the cosyvoice3.yaml hyper-parameters."""
+    install()
+    from cosyvoice.flow.flow import CausalMaskedDiffWithDiT
+    from cosyvoice.flow.flow_matching import CausalConditionalCFM
+    from cosyvoice.transformer.upsample_encoder import PreLookaheadLayer
+    cfm = CausalConditionalCFM(in_channels=240, n_spks=1, spk_emb_dim=80,
+                               cfm_params=_DictConfig(dict(sigma_min=1e-6, solver="euler", t_scheduler="cosine",
+                                                           training_cfg_rate=0.2, inference_cfg_rate=0.7,
+                                                           reg_loss_type="l1")),
+                               estimator=build_dit(depth))
+    flow = CausalMaskedDiffWithDiT(input_size=80, output_size=80, spk_embed_dim=192, output_type="mel", vocab_size=6561,
+                                   input_frame_rate=25, only_mask_loss=True, token_mel_ratio=2, pre_lookahead_len=3,
+                                   pre_lookahead_layer=PreLookaheadLayer(in_channels=80, channels=1024, pre_lookahead_len=3),
+                                   decoder=cfm)
+    return flow.eval()
