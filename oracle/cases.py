@@ -19,6 +19,17 @@ def hift_case(B=2, T=24, seed=0):
     return mel, noise, rand_ini
 
 
+def hift_causal_case(T=24, seed=5):
+    """CosyVoice3 vocoder case: mel [1,80,T] and the 'stored noise' of the causal source module (SineGen2.rand_ini [1,9] with
+    column 0 zero, SineGen2.sine_waves [1,480T,9] uniform like the reference's torch.rand, generator.py:223-226)."""
+    g = _g(1000 + seed)
+    mel = torch.randn(1, 80, T, generator=g) * 2 - 5
+    rand_ini = torch.rand(1, 9, generator=g)
+    rand_ini[:, 0] = 0
+    sine_noise = torch.rand(1, T * 480, 9, generator=g)
+    return mel, rand_ini, sine_noise
+
+
 def flow_case(N=31, P=20, seed=1):
     g = _g(2000 + seed)
     token = torch.randint(0, 6561, (1, N), dtype=torch.int32, generator=g)

@@ -84,6 +84,35 @@ def gen_hift():
 
 
 @torch.inference_mode()
+def gen_hift_causal():
+    """CosyVoice3 vocoder: cosyvoice/hifigan/generator.py:572-726 (CausalHiFTGenerator), offline and one streaming call."""
+    print("hift_causal")
+    from . import hift_causal as hc
+    ref = refimport.build_hift_causal()
+    shapes = hc.param_shapes()
+    rsd = ref.state_dict()
+    assert list(rsd.keys()) == list(shapes.keys())
+    assert all(tuple(rsd[k].shape) == tuple(shapes[k]) for k in shapes)
+    sd = weights.synth_state_dict(shapes, 1986, hc.SYNTH_GAINS)
+    ref.load_state_dict(sd, strict=True)
+    mel, rand_ini, sine_noise = cases.hift_causal_case()
+    # the reference's constructor-time random tensors (not in the state_dict) are replaced by the case's tensors
+    ref.m_source.l_sin_gen.rand_ini = rand_ini.clone()
+    ref.m_source.l_sin_gen.sine_waves = sine_noise.clone()
+    out = {}
+    for name, finalize in (("final", True), ("chunk", False)):
+        rwav, rs = ref.inference(speech_feat=mel, finalize=finalize)
+        ref.f0_predictor.to(torch.float64)
+        rf0 = ref.f0_predictor(mel.to(torch.float64), finalize=finalize).float()
+        wav, s = hc.inference(sd, mel, rand_ini, sine_noise, finalize)
+        print("  %s: max|oracle-ref| wav %.3g source %.3g f0 %.3g  (wav %s, |wav| max %.3g)" % (
+            name, (wav - rwav).abs().max(), (s - rs).abs().max(), (hc.f0_predict(sd, mel, finalize) - rf0).abs().max(),
+            tuple(rwav.shape), rwav.abs().max()))
+        out.update({f"wav_{name}": rwav.numpy(), f"source_{name}": rs.numpy(), f"f0_{name}": rf0.numpy()})
+    save("hift_causal", **out)
+
+
+@torch.inference_mode()
 def gen_flow():
     print("flow")
     for tag, kw in (("small", dict(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2)),
@@ -339,6 +368,6 @@ def gen_stream():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "flow", "dit", "lm", "bistream", "sampling", "mel", "masks", "stream"]
+    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "bistream", "sampling", "mel", "masks", "stream"]
     for w in which:
         globals()["gen_" + w]()

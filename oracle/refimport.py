@@ -331,3 +331,20 @@ def build_flow3(depth=22):
                                    pre_lookahead_layer=PreLookaheadLayer(in_channels=80, channels=1024, pre_lookahead_len=3),
                                    decoder=cfm)
     return flow.eval()
+
+
+def build_hift_causal():
+    """Reference CausalHiFTGenerator with the cosyvoice3.yaml hyper-parameters.  (The constructor draws ~260 MB of 'stored
+    noise' from the global RNG; the golden generator overwrites it with explicit tensors.)"""
+    install()
+    from cosyvoice.hifigan.generator import CausalHiFTGenerator
+    from cosyvoice.hifigan.f0_predictor import CausalConvRNNF0Predictor
+    m = CausalHiFTGenerator(in_channels=80, base_channels=512, nb_harmonics=8, sampling_rate=24000,
+                            nsf_alpha=0.1, nsf_sigma=0.003, nsf_voiced_threshold=10,
+                            upsample_rates=[8, 5, 3], upsample_kernel_sizes=[16, 11, 7],
+                            istft_params={"n_fft": 16, "hop_len": 4},
+                            resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                            source_resblock_kernel_sizes=[7, 7, 11], source_resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                            lrelu_slope=0.1, audio_limit=0.99, conv_pre_look_right=4,
+                            f0_predictor=CausalConvRNNF0Predictor(num_class=1, in_channels=80, cond_channels=512))
+    return m.eval()
