@@ -60,6 +60,14 @@ def lm_case(n_text=7, n_prompt_text=4, n_prompt_speech=9, seed=3, n_uniform=400)
     return text, ptext, ptok, U
 
 
+def lm3_case():
+    """CosyVoice3LM case: lm_case with the <|endofprompt|> id (151646, llm.py:478-479) closing the prompt text."""
+    text, ptext, ptok, U = lm_case(seed=7)
+    ptext = ptext.clone()
+    ptext[0, -1] = 151646
+    return text, ptext, ptok, U
+
+
 def bistream_case(seed=11, n_uniform=400):
     """Text-streaming LM case: prompt text 6 ids, prompt speech 22 tokens (one full 5:15 block + 7 left over, first forced fill
     after 8 generated tokens), text arriving in chunks of 3 / 4 / 2 / 5 / 3 ids."""

@@ -236,3 +236,56 @@ def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, unifor
         yielded.append(top)
         lm_input = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
     return (yielded, out_tokens) if return_trace else yielded
+
+
+# ------------------------------------------------------------------------------------------------ CosyVoice3LM (llm.py:664-705)
+V_OUT3 = SPEECH_TOKENS + 200
+SOS3, EOS3, TASK3, FILL3 = 6561, 6562, 6563, 6564
+STOP_IDS3 = tuple(range(SPEECH_TOKENS, SPEECH_TOKENS + 200))
+
+
+def param_shapes3(num_layers=24):
+    """CosyVoice3LM: no llm_embedding (sos / task_id are rows 6561 / 6563 of speech_embedding), head 896 -> 6761 WITHOUT bias."""
+    s = param_shapes(num_layers, with_lm_head=False)
+    for k in ("llm_embedding.weight", "llm_decoder.bias"):
+        s.pop(k)
+    s["llm_decoder.weight"] = (V_OUT3, D)
+    s["speech_embedding.weight"] = (V_OUT3, D)
+    return s
+
+
+def synth_state_dict3(num_layers=24, seed=1986, cool=0.8):
+    from .weights import synth_state_dict as _s
+    sd = _s(param_shapes3(num_layers), seed, SYNTH_GAINS)
+    sd["llm.model.lm_head.weight"] = sd["llm.model.model.embed_tokens.weight"]
+    # 200 of the 6761 output ids stop the decode (llm.py:704) and only one of them is masked before min_len: with an untrained
+    # head the loop would end after ~10 tokens.  Cooling the stop rows keeps the synthetic utterance long enough to exercise
+    # the repetition window (cool = 0.8: the golden runs to max_len); cool = 1.0 gives the second golden, which ends on a
+    # sampled stop id before min_len.
+    sd["llm_decoder.weight"][SPEECH_TOKENS + 1:] *= cool
+    return sd
+
+
+def inference3(sd, text, prompt_text, prompt_speech_token, uniforms, num_layers=24, min_ratio=2.0, max_ratio=20.0):
+    """Qwen2LM.inference (llm.py:458-549) as inherited by CosyVoice3LM: prompt [speech_embedding[6561], embed(prompt_text ++
+    text), speech_embedding[6563], speech_embedding(prompt tokens)]; ``ignore_eos`` masks index speech_token_size = 6561 exactly
+    as the shared sampling_ids does (llm.py:156-157; in CosyVoice3 that index is the sos id, the eos id 6562 stays drawable);
+    any id in 6561..6760 stops the loop (llm.py:544)."""
+    t = torch.cat([prompt_text, text], dim=1).long()
+    assert 151646 in t, "<|endofprompt|> not detected in CosyVoice3 text or prompt_text"       # llm.py:478-479
+    text_emb = F.embedding(t, sd["llm.model.model.embed_tokens.weight"])
+    sos = sd["speech_embedding.weight"][SOS3].reshape(1, 1, -1)
+    task = sd["speech_embedding.weight"][TASK3].reshape(1, 1, -1)
+    sp = F.embedding(prompt_speech_token.long(), sd["speech_embedding.weight"]) if prompt_speech_token.shape[1] else torch.zeros(1, 0, D)
+    lm_in = torch.cat([sos, text_emb, task, sp], dim=1)
+    min_len, max_len = length_bounds(text.shape[1], min_ratio, max_ratio)
+    out, past = [], None
+    for i in range(max_len):
+        y, past = qwen2_forward(sd, lm_in, past, num_layers)
+        logp = F.log_softmax(F.linear(y[:, -1], sd["llm_decoder.weight"]), dim=-1).squeeze(0)
+        top = sampling.ras_sample(logp.numpy(), out, float(uniforms[i, 0]), float(uniforms[i, 1]), ignore_eos=i < min_len)
+        if top in STOP_IDS3:
+            break
+        out.append(top)
+        lm_in = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
+    return out

@@ -226,6 +226,36 @@ def gen_lm():
              logp_rows=rlogp[-4:, ::41].numpy(), logp_step0_top=np.sort(logps[0].numpy())[-32:])
 
 
+def gen_lm3():
+    """CosyVoice3LM.inference (llm.py:664-705 + inherited :458-549)."""
+    print("lm (CosyVoice3LM)")
+    NL = 2
+    ref = refimport.build_llm3(num_layers=NL)
+    for tag, cool in (("lm3_l2", 0.8), ("lm3_l2_stop", 1.0)):
+        sd = lm.synth_state_dict3(NL, cool=cool)
+        rsd = ref.state_dict()
+        assert set(rsd.keys()) == set(sd.keys()), set(rsd.keys()) ^ set(sd.keys())
+        ref.load_state_dict(sd, strict=True)
+        text, ptext, ptok, U = cases.lm3_case()
+        st = {"i": 0, "c": 0}
+
+        def get_u():
+            u = float(U[st["i"], min(st["c"], 1)])
+            st["c"] += 1
+            return u
+        ids = []
+        with patched_multinomial(get_u):
+            for tok in ref.inference(text=text, text_len=torch.tensor([text.shape[1]], dtype=torch.int32), prompt_text=ptext,
+                                     prompt_text_len=torch.tensor([ptext.shape[1]], dtype=torch.int32), prompt_speech_token=ptok,
+                                     prompt_speech_token_len=torch.tensor([ptok.shape[1]], dtype=torch.int32), embedding=torch.zeros(0, 192)):
+                ids.append(int(tok))
+                st["i"] += 1
+                st["c"] = 0
+        o = lm.inference3(sd, text, ptext, ptok, U, NL)
+        print(f"  {tag}: {len(ids)} ids, oracle == reference: {o == ids}")
+        save(tag, ids=np.array(ids, dtype=np.int32))
+
+
 def gen_bistream():
     """cosyvoice/llm/llm.py:551-661 (Qwen2LM.inference_bistream) with the text arriving in chunks."""
     print("lm bistream")
@@ -368,6 +398,6 @@ def gen_stream():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "bistream", "sampling", "mel", "masks", "stream"]
+    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "lm3", "bistream", "sampling", "mel", "masks", "stream"]
     for w in which:
         globals()["gen_" + w]()

@@ -348,3 +348,24 @@ def build_hift_causal():
                             lrelu_slope=0.1, audio_limit=0.99, conv_pre_look_right=4,
                             f0_predictor=CausalConvRNNF0Predictor(num_class=1, in_channels=80, cond_channels=512))
     return m.eval()
+
+
+def build_llm3(num_layers=24, tmpdir=None):
+    """Reference CosyVoice3LM (cosyvoice3.yaml) over a random-init HF Qwen2ForCausalLM of Qwen2.5-0.5B shape."""
+    install()
+    import tempfile
+    from functools import partial
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    from cosyvoice.llm.llm import CosyVoice3LM, Qwen2Encoder
+    from cosyvoice.utils.common import ras_sampling
+    cfg = dict(QWEN_CFG)
+    cfg["num_hidden_layers"] = num_layers
+    d = tmpdir or tempfile.mkdtemp(prefix="qwen_blank_")
+    with torch.device("cpu"):
+        Qwen2ForCausalLM(Qwen2Config(**cfg)).save_pretrained(d)
+    enc = Qwen2Encoder(d)
+    lm = CosyVoice3LM(llm_input_size=896, llm_output_size=896, speech_token_size=6561, llm=enc,
+                      sampling=partial(ras_sampling, top_p=0.8, top_k=25, win_size=10, tau_r=0.1),
+                      length_normalized_loss=True, lsm_weight=0, mix_ratio=[5, 15])
+    _pin_forward_one_step(enc)
+    return lm.eval()
