@@ -14,7 +14,15 @@ Contents
                     own state_dict names (no pretrained weights exist offline).
 * ``hift``/``flow``/``lm``/``mel``/``sampling`` – plain torch-fp32 restatements
                     of the reference algorithm, each function citing the
-                    reference file:line it follows.
+                    reference file:line it follows (``lm`` also holds the
+                    text-streaming ``inference_bistream`` and the CosyVoice3LM
+                    variant).
+* ``dit``/``hift_causal``/``model3`` – the CosyVoice3 stack (DiT flow, causal
+                    vocoder with the fp64 f0 predictor, CosyVoice3Model glue),
+                    pinned the same way; the x_transformers rotary embedding
+                    used by the DiT is not installed offline and is restated
+                    from its published algorithm (parity unpinned for that
+                    piece, see ``refimport._RotaryEmbedding``).
 
 Parity pin: the reference ships no golden vectors.  The
 restatement is pinned against outputs of the reference itself, imported in the

@@ -397,7 +397,66 @@ def gen_stream():
     save("stream_tts", **out)
 
 
+def gen_stream3():
+    """cosyvoice/cli/model.py:397-450 (CosyVoice3Model: inherited tts + its own token2wav, which re-runs the causal vocoder over
+    the whole mel so far and emits the new samples), stream=False and stream=True, on small CosyVoice3 modules."""
+    print("stream3 (reference CosyVoice3Model.tts)")
+    refimport.install()
+    from cosyvoice.cli.model import CosyVoice3Model
+    from . import dit, hift_causal as hc
+    NL, depth = 2, 2
+    llm = refimport.build_llm3(num_layers=NL)
+    llm.load_state_dict(lm.synth_state_dict3(NL), strict=True)
+    fl = refimport.build_flow3(depth)
+    fl.load_state_dict(weights.synth_state_dict(dit.flow_param_shapes(depth), 1986, dit.SYNTH_GAINS), strict=True)
+    hf = refimport.build_hift_causal()
+    hf.load_state_dict(weights.synth_state_dict(hc.param_shapes(), 1986, hc.SYNTH_GAINS), strict=True)
+    text, ptext, ptok, U = cases.lm3_case()
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    pfeat = pfeat[:, :18]
+    _, rand_ini, sine_noise = cases.hift_causal_case(T=400)
+    hf.m_source.l_sin_gen.rand_ini = rand_ini.clone()
+    hf.m_source.l_sin_gen.sine_waves = sine_noise.clone()
+    out = {}
+    for mode, stream in (("offline", False), ("stream", True)):
+        model = CosyVoice3Model(llm, fl, hf, fp16=False)
+        st = {"i": 0, "c": 0}
+
+        def get_u():
+            u = float(U[st["i"], min(st["c"], 1)])
+            st["c"] += 1
+            return u
+        orig_mn = torch.Tensor.multinomial
+
+        def fake_mn(t, n, replacement=False, generator=None):
+            return torch.tensor([sampling.draw_index(t.detach().numpy(), get_u())])
+        orig_infer = llm.sampling_ids
+
+        def sampling_ids(weighted_scores, decoded_tokens, sampling_, ignore_eos=True):
+            st["i"], st["c"] = len(decoded_tokens), 0
+            return orig_infer(weighted_scores, decoded_tokens, sampling_, ignore_eos)
+        llm.sampling_ids = sampling_ids
+        torch.Tensor.multinomial = fake_mn
+        try:
+            chunks = [o["tts_speech"] for o in model.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                         llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                         stream=stream)]
+        finally:
+            torch.Tensor.multinomial = orig_mn
+            llm.sampling_ids = orig_infer
+        print(f"  {mode}: {len(chunks)} chunks, lengths {[c.shape[1] for c in chunks]}, hop_len after = {model.token_hop_len}")
+        out[mode + "_lens"] = np.array([c.shape[1] for c in chunks], dtype=np.int64)
+        out[mode + "_wav"] = torch.cat(chunks, 1).numpy()
+    # the oracle pipeline reproduces the offline run
+    ids = lm.inference3(lm.synth_state_dict3(NL), text, ptext, ptok, U, NL)
+    mel = dit.inference(weights.synth_state_dict(dit.flow_param_shapes(depth), 1986, dit.SYNTH_GAINS),
+                        torch.tensor([ids], dtype=torch.int32), ptok, pfeat, emb, depth)
+    wav, _ = hc.inference(weights.synth_state_dict(hc.param_shapes(), 1986, hc.SYNTH_GAINS), mel, rand_ini, sine_noise, True)
+    print(f"  oracle pipeline vs reference offline: max|d| {np.abs(wav.numpy() - out['offline_wav']).max():.3g}")
+    save("stream3_tts", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "lm3", "bistream", "sampling", "mel", "masks", "stream"]
+    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "lm3", "bistream", "sampling", "mel", "masks", "stream", "stream3"]
     for w in which:
         globals()["gen_" + w]()
