@@ -21,6 +21,11 @@ void flow_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device);
 void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg);
 cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context);
 void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s);
+void dit_build(cvk_ctx* ctx, const int* cfg, int ncfg);
+void dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
+                   int B, int streaming, float* out, cudaStream_t st);
+void flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
+                     const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, cudaStream_t st);
 void llm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const int* text_lens, const int32_t* speech,
                  const int* speech_lens, int B, cudaStream_t st);
 void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len, const int32_t* max_len,
@@ -188,6 +193,7 @@ int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg) {
   std::string s(stage ? stage : "");
   if (s == "hift") hift_build(ctx);
   else if (s == "flow") flow_build(ctx, cfg, ncfg);
+  else if (s == "flow3") dit_build(ctx, cfg, ncfg);
   else if (s == "llm") llm_build(ctx, cfg, ncfg);
   else if (s == "mel") mel_init(ctx);
   else throw CvkError(CVK_ERR_INVALID, "unknown stage: " + s);
@@ -371,6 +377,23 @@ int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device)
 }
 
 // ---------------------------------------------------------------------------------------------- LM
+int cvk_dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond,
+                      const int* lens_host, int B, int streaming, float* out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(x && mu && t && spks && cond && lens_host && out && B > 0, "cvk_dit_estimator: bad arguments");
+  dit_estimator(ctx, x, mu, t, spks, cond, lens_host, B, streaming, out, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens_host, const float* prompt_feat,
+                        const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming, int finalize,
+                        float* mel, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(tokens && token_lens_host && prompt_feat_lens_host && embedding && mel && B > 0 && n_timesteps > 0,
+              "cvk_flow3_inference: bad arguments");
+  flow3_inference(ctx, tokens, token_lens_host, prompt_feat, prompt_feat_lens_host, embedding, B, n_timesteps, streaming, finalize, mel,
+                  (cudaStream_t)stream);
+  CVK_API_END
+}
 int cvk_lm_session_create(cvk_ctx* ctx, int max_batch, int max_context, cvk_lm_session** out) {
   CVK_API_BEGIN
   CVK_REQUIRE(out && max_batch > 0 && max_context > 0, "cvk_lm_session_create: bad arguments");

@@ -82,6 +82,7 @@ __device__ __forceinline__ float apply_act(int act, float x, float param, float 
     }
     case ACT_TANH: return tanhf(x);
     case ACT_ABS: return fabsf(x);
+    case ACT_GELU_TANH: return 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
     default: return x;
   }
 }
@@ -123,6 +124,10 @@ __device__ __forceinline__ float apply_act_fast(int act, float x, float param, f
     }
     case ACT_TANH: return fast_tanh(x);
     case ACT_ABS: return fabsf(x);
+    case ACT_GELU_TANH: {
+      const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+      return 0.5f * x * (1.f + fast_tanh(u));
+    }
     default: return x;
   }
 }
@@ -163,6 +168,10 @@ __device__ __forceinline__ void act16_fast(int act, float* v, float param, const
     case ACT_ABS:
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fabsf(v[i]);
+      break;
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(ACT_GELU_TANH, v[i], 0.f, 1.f);
       break;
     default: break;
   }

@@ -82,7 +82,8 @@ struct ConvW {
 };
 
 enum Act {
-  ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6, ACT_TANH = 7, ACT_ABS = 8
+  ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6, ACT_TANH = 7, ACT_ABS = 8,
+  ACT_GELU_TANH = 9   // F.gelu(approximate='tanh') (CosyVoice3 DiT feed-forward, flow/DiT/modules.py:514)
 };
 
 // Fused epilogue of the conv-GEMM kernels:
@@ -142,6 +143,7 @@ struct ProfRec {
 
 struct HiftModel;
 struct FlowModel;
+struct DitModel;
 struct LlmModel;
 
 struct cvk_ctx {
@@ -155,6 +157,7 @@ struct cvk_ctx {
   Arena arena;
   HiftModel* hift = nullptr;
   FlowModel* flow = nullptr;
+  DitModel* dit = nullptr;                  // CosyVoice3 flow (stage "flow3")
   LlmModel* llm = nullptr;
   void* mel_model = nullptr;
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point

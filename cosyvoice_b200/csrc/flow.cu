@@ -254,15 +254,16 @@ namespace {
 // token ids -> embedding rows (flow.py:252-254: clamp(min=0), padding mask), written as the Linear operand
 template <typename TO>
 __global__ void token_embed_kernel(const int32_t* __restrict__ tokens, const int* __restrict__ tok_off, const float* __restrict__ table,
-                                   const int* __restrict__ start, const int* __restrict__ len, TO* __restrict__ out, int ldo) {
+                                   const int* __restrict__ start, const int* __restrict__ len, TO* __restrict__ out, int ldo,
+                                   int width = D_ENC) {
   int b = blockIdx.y;
   int L = len[b];
   for (int t = blockIdx.x; t < L; t += gridDim.x) {
     int id = tokens[tok_off[b] + t];
     if (id < 0) id = 0;
-    const float* src = table + (size_t)id * D_ENC;
+    const float* src = table + (size_t)id * width;
     TO* dst = out + (size_t)(start[b] + t) * ldo;
-    for (int c = threadIdx.x; c < D_ENC; c += blockDim.x) dst[c] = from_f32<TO>(src[c]);
+    for (int c = threadIdx.x; c < width; c += blockDim.x) dst[c] = from_f32<TO>(src[c]);
   }
 }
 
@@ -690,13 +691,16 @@ void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& 
 }
 
 // mu, cond, x: fp32 [R1,80] (ld 80) in geometry s1; spks [B,80].  Runs n Euler steps in place on x.
+void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out);
+
+// `dit`: 0 = CosyVoice2 causal U-Net estimator, 1 = CosyVoice3 DiT (32 gap rows: its causal position convolution looks 30 rows back)
 void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* lens, const Mat& mu, const Mat& cond, const float* spks,
-                      const Mat& x, int n_timesteps, float cfg_rate, int streaming) {
+                      const Mat& x, int n_timesteps, float cfg_rate, int streaming, int dit = 0) {
   const int adt = ctx->act_dtype;
   const int B = s1.B;
   std::vector<int> lens2(2 * B);
   for (int b = 0; b < 2 * B; ++b) lens2[b] = lens[b % B];
-  Seqs s2 = make_seqs(ctx, lens2.data(), 2 * B, 8, 1, 0, st);
+  Seqs s2 = make_seqs(ctx, lens2.data(), 2 * B, dit ? 32 : 8, 1, 0, st);
   Mat in0 = arena_mat(ctx, adt, s2.R, 320);
   zero_mat(ctx, st, in0);
   Mat v = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
@@ -727,11 +731,291 @@ void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* 
       cfg_pack_kernel<bf16><<<dim3(bx, 2 * B), 96, 0, st>>>(x.f32(), mu.f32(), cond.f32(), spks, s1.d_start, s2.d_start, s1.d_len, B, in0.b16(), in0.ld);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
-    estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
+    if (dit) dit_estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
+    else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
     cfg_euler_kernel<<<dim3(bx, B), 96, 0, st>>>(x.f32(), v.f32(), v.ld, s1.d_start, s2.d_start, s1.d_len, B, dts[step], cfg_rate);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }
+}
+
+
+// ================================================================================================ CosyVoice3 DiT estimator
+// cosyvoice/flow/DiT/dit.py:104-176 + modules.py (TimestepEmbedding :606-616, CausalConvPositionEmbedding :115-145, DiTBlock
+// :500-533, AdaLayerNormZero :230-248, AdaLayerNormZero_Final :251-264, AttnProcessor :349-411), cosyvoice3.yaml: dim 1024,
+// depth 22, 16 heads x 64, ff_mult 2, static chunk 50.  Same packed time-major layout as the U-Net estimator: the CFG pair is
+// 2B sequences; AdaLN modulation vectors are per-SEQUENCE rows of one [2B, depth*6144 + 2048] matrix produced by ONE GEMM per
+// estimator call (the time embedding is shared by all blocks); the grouped causal position convolution (k31, 16 groups) is 16
+// conv-GEMMs on 64-column slices; the rotary embedding touches the first 64 channels of q and k only (x_transformers partial
+// rotary on the un-split projection, modules.py:368-373).
+constexpr int DIT_D = 1024, DIT_H = 16, DIT_FF = 2048, DIT_GROUPS = 16, DIT_CK = 31;
+
+struct DitBlockW {
+  ConvW qkv, out, ff1, ff2;
+};
+}  // namespace
+
+struct DitModel {
+  int depth = 22;
+  float* tok_emb = nullptr;        // [6561][80]
+  ConvW spk_affine, pre1, pre2;    // 192 -> 80; PreLookaheadLayer(80, 1024, 3)
+  ConvW t1, t2;                    // time MLP 256 -> 1024 -> 1024
+  ConvW in_proj;                   // 320 -> 1024, input columns permuted to the [x | mu | spks | cond] packing of cfg_pack_kernel
+  std::vector<ConvW> pos1, pos2;   // 16 groups each: [64][31][64]
+  ConvW mod_all;                   // [depth*6144 + 2048][1024]: every attn_norm.linear, then norm_out.linear
+  std::vector<DitBlockW> blocks;
+  ConvW proj_out;                  // 1024 -> 80
+};
+
+namespace {
+
+// modules.py:71-84 with dim 256, scale 1000: emb = exp(-i * ln(1e4)/(127)), [sin | cos]
+__global__ void dit_time_sincos_kernel(const float* __restrict__ t, float* __restrict__ out) {
+  const int b = blockIdx.x, half = 128;
+  const float k = logf(10000.0f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float a = 1000.f * t[b] * expf((float)i * -k);
+    out[(size_t)b * 256 + i] = sinf(a);
+    out[(size_t)b * 256 + half + i] = cosf(a);
+  }
+}
+
+// in_proj weight [1024][320] with reference column order [x | cond | mu | spks] (dit.py:91-97) -> [x | mu | spks | cond]
+__global__ void dit_permute_inproj_kernel(const float* __restrict__ w, float* __restrict__ o, int N) {
+  const size_t total = (size_t)N * 320;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / 320), c = (int)(i % 320);
+    const int blk = c / 80, j = c % 80;                  // destination block: 0 x, 1 mu, 2 spks, 3 cond
+    const int src = blk == 0 ? j : (blk == 1 ? 160 + j : (blk == 2 ? 240 + j : 80 + j));
+    o[i] = w[(size_t)n * 320 + src];
+  }
+}
+
+// LayerNorm(1024, no affine, eps 1e-6) followed by the per-sequence modulation  y = norm * (1 + scale[seq]) + shift[seq]
+// (modules.py:245-247, 262-263, 527); one warp per row, the row in registers (8 x float4 per lane)
+template <typename TO>
+__global__ void layernorm_mod_kernel(const float* __restrict__ x, int ldx, int rows, const int* __restrict__ row2seq,
+                                     const float* __restrict__ scale, const float* __restrict__ shift, int mod_ld, TO* __restrict__ out, int ldo) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int seq = row2seq[row];
+  TO* op = out + (size_t)row * ldo;
+  float v[32];
+  if (seq < 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  } else {
+    const float* xp = x + (size_t)row * ldx;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(xp + j * 128 + lane * 4);
+      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+    const float mean = warp_sum(s) * (1.f / DIT_D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] -= mean;
+      q = fmaf(v[i], v[i], q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / DIT_D) + 1e-6f);
+    const float* sc = scale + (size_t)seq * mod_ld;
+    const float* sh = shift + (size_t)seq * mod_ld;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(sc + j * 128 + lane * 4);
+      const float4 b = *reinterpret_cast<const float4*>(sh + j * 128 + lane * 4);
+      v[4 * j] = fmaf(v[4 * j] * rstd, 1.f + a.x, b.x);
+      v[4 * j + 1] = fmaf(v[4 * j + 1] * rstd, 1.f + a.y, b.y);
+      v[4 * j + 2] = fmaf(v[4 * j + 2] * rstd, 1.f + a.z, b.z);
+      v[4 * j + 3] = fmaf(v[4 * j + 3] * rstd, 1.f + a.w, b.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    TO* o = op + j * 128 + lane * 4;
+    o[0] = from_f32<TO>(v[4 * j]); o[1] = from_f32<TO>(v[4 * j + 1]); o[2] = from_f32<TO>(v[4 * j + 2]); o[3] = from_f32<TO>(v[4 * j + 3]);
+  }
+}
+
+// x[r, :] += gate[seq(r), :] * o[r, :]   (modules.py:526, 530; gap rows stay zero because o is masked there)
+__global__ void dit_gate_add_kernel(float* __restrict__ x, int ldx, const float* __restrict__ o, int ldo, int rows,
+                                    const int* __restrict__ row2seq, const float* __restrict__ gate, int gate_ld) {
+  const size_t total = (size_t)rows * (DIT_D / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (DIT_D / 4)), c = (int)(i % (DIT_D / 4)) * 4;
+    const int seq = row2seq[r];
+    if (seq < 0) continue;
+    const float4 g = *reinterpret_cast<const float4*>(gate + (size_t)seq * gate_ld + c);
+    const float4 a = *reinterpret_cast<const float4*>(o + (size_t)r * ldo + c);
+    float4 v = *reinterpret_cast<float4*>(x + (size_t)r * ldx + c);
+    v.x = fmaf(g.x, a.x, v.x); v.y = fmaf(g.y, a.y, v.y); v.z = fmaf(g.z, a.z, v.z); v.w = fmaf(g.w, a.w, v.w);
+    *reinterpret_cast<float4*>(x + (size_t)r * ldx + c) = v;
+  }
+}
+
+// x_transformers partial rotary on the first 64 channels of q (columns 0..63 of the fused qkv row) and k (columns 1024..1087):
+// freqs duplicated in adjacent channels, pairs (2i, 2i+1) -> (a cos - b sin, b cos + a sin), angle = position * 10000^(-2i/64)
+template <typename T>
+__global__ void dit_rope_kernel(T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len) {
+  const int b = blockIdx.y, L = len[b];
+  for (int t = blockIdx.x; t < L; t += gridDim.x) {
+    T* row = qkv + (size_t)(start[b] + t) * ld;
+    for (int e = threadIdx.x; e < 64; e += blockDim.x) {       // 32 pairs of q, 32 pairs of k
+      const int which = e >> 5, i = e & 31;
+      T* p = row + which * DIT_D + 2 * i;
+      const float ang = (float)t * exp2f(-(float)(2 * i) / 64.f * 13.287712379549449f);    // log2(10000)
+      const float c = cosf(ang), sn = sinf(ang);
+      const float a = to_f32(p[0]), bb = to_f32(p[1]);
+      p[0] = from_f32<T>(a * c - bb * sn);
+      p[1] = from_f32<T>(bb * c + a * sn);
+    }
+  }
+}
+
+// out[2t] = out[2t+1] = in[t]  (repeat_interleave(token_mel_ratio = 2, dim=1), flow.py:393)
+__global__ void repeat2_rows_kernel(const float* __restrict__ in, int ldi, const int* __restrict__ start_in, const int* __restrict__ len_in,
+                                    float* __restrict__ out, int ldo, const int* __restrict__ start_out, int C) {
+  const int b = blockIdx.y, L = len_in[b];
+  for (int t = blockIdx.x; t < L; t += gridDim.x) {
+    const float* src = in + (size_t)(start_in[b] + t) * ldi;
+    float* d0 = out + (size_t)(start_out[b] + 2 * t) * ldo;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      d0[c] = src[c];
+      d0[ldo + c] = src[c];
+    }
+  }
+}
+
+void ln_mod(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const Seqs& s, const float* scale, const float* shift, int mod_ld, const Mat& out) {
+  const int blocks = ceil_div(x.rows, 8);
+  if (out.dtype == DT_F32)
+    layernorm_mod_kernel<float><<<blocks, 256, 0, st>>>(x.f32(), x.ld, x.rows, s.d_row2seq, scale, shift, mod_ld, out.f32(), out.ld);
+  else
+    layernorm_mod_kernel<bf16><<<blocks, 256, 0, st>>>(x.f32(), x.ld, x.rows, s.d_row2seq, scale, shift, mod_ld, out.b16(), out.ld);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+void gate_add(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const Mat& o, const Seqs& s, const float* gate, int gate_ld) {
+  dit_gate_add_kernel<<<148 * 8, 256, 0, st>>>(x.f32(), x.ld, o.f32(), o.ld, x.rows, s.d_row2seq, gate, gate_ld);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+// in0: act [R,320] packed [x | mu | spks | cond]; t_dev [B]; out fp32 [R,80]
+void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out) {
+  DitModel* m = ctx->dit;
+  CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
+  const int adt = ctx->act_dtype;
+  const int chunk = streaming ? 2 * CHUNK_TOK : 0;
+  const size_t mark = ctx->arena.off;
+  Mat x = arena_mat(ctx, DT_F32, s.R, DIT_D), xn = arena_mat(ctx, adt, s.R, DIT_D), qkv = arena_mat(ctx, adt, s.R, 3 * DIT_D),
+      att = arena_mat(ctx, adt, s.R, DIT_D), ff = arena_mat(ctx, adt, s.R, DIT_FF), o = arena_mat(ctx, DT_F32, s.R, DIT_D);
+  // time embedding -> SiLU -> every modulation vector of the network in one GEMM
+  Mat sc = arena_mat(ctx, DT_F32, s.B, 256), te1 = arena_mat(ctx, DT_F32, s.B, DIT_D), te = arena_mat(ctx, DT_F32, s.B, DIT_D),
+      ste = arena_mat(ctx, DT_F32, s.B, DIT_D);
+  dit_time_sincos_kernel<<<s.B, 128, 0, st>>>(t_dev, sc.f32());
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  {
+    Epilogue e;
+    e.act1 = ACT_SILU;
+    e.out = te1;
+    conv_gemm_simt(ctx, st, sc, m->t1, e);
+  }
+  {
+    Epilogue e;
+    e.out = te;
+    e.act2 = ACT_SILU;            // AdaLayerNormZero: linear(silu(emb))
+    e.out2 = ste;
+    conv_gemm_simt(ctx, st, te1, m->t2, e);
+  }
+  const int mod_ld = m->depth * 6 * DIT_D + 2 * DIT_D;
+  Mat mod = arena_mat(ctx, DT_F32, s.B, mod_ld);
+  {
+    Epilogue e;
+    e.out = mod;
+    conv_gemm_simt(ctx, st, ste, m->mod_all, e);
+  }
+  // input embedding: proj + causal grouped position convolution (twice, Mish) + residual
+  {
+    Epilogue e;
+    e.row2seq = s.d_row2seq;
+    e.out = x;
+    conv_gemm(ctx, st, in0, m->in_proj, e);
+  }
+  Mat xa = x;
+  if (adt != DT_F32) {
+    xa = xn;                      // free at this point
+    convert_mat(ctx, st, x, xa);
+  }
+  Mat c1 = att;                   // act [R,1024], free at this point
+  for (int g = 0; g < DIT_GROUPS; ++g) {
+    Epilogue e;
+    e.act1 = ACT_MISH;
+    e.row2seq = s.d_row2seq;
+    e.out = c1.slice(g * 64, 64);
+    conv_gemm(ctx, st, xa.slice(g * 64, 64), m->pos1[g], e);
+  }
+  for (int g = 0; g < DIT_GROUPS; ++g) {
+    Epilogue e;
+    e.act1 = ACT_MISH;
+    e.resid = x.slice(g * 64, 64);
+    e.row2seq = s.d_row2seq;
+    e.out = x.slice(g * 64, 64);
+    conv_gemm(ctx, st, c1.slice(g * 64, 64), m->pos2[g], e);
+  }
+  const int bx = s.max_len < 1024 ? s.max_len : 1024;
+  for (int i = 0; i < m->depth; ++i) {
+    const DitBlockW& w = m->blocks[i];
+    const float* mb = mod.f32() + (size_t)i * 6 * DIT_D;   // [shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp]
+    ln_mod(ctx, st, x, s, mb + DIT_D, mb, mod_ld, xn);
+    {
+      Epilogue e;
+      e.row2seq = s.d_row2seq;
+      e.out = qkv;
+      conv_gemm(ctx, st, xn, w.qkv, e);
+    }
+    if (adt == DT_F32) dit_rope_kernel<float><<<dim3(bx, s.B), 64, 0, st>>>(qkv.f32(), qkv.ld, s.d_start, s.d_len);
+    else dit_rope_kernel<bf16><<<dim3(bx, s.B), 64, 0, st>>>(qkv.b16(), qkv.ld, s.d_start, s.d_len);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    attention_fwd(ctx, st, qkv.slice(0, DIT_D), qkv.slice(DIT_D, DIT_D), qkv.slice(2 * DIT_D, DIT_D), s, DIT_H, chunk, 0.125f, att);
+    {
+      Epilogue e;
+      e.row2seq = s.d_row2seq;
+      e.out = o;
+      conv_gemm(ctx, st, att, w.out, e);
+    }
+    gate_add(ctx, st, x, o, s, mb + 2 * DIT_D, mod_ld);
+    ln_mod(ctx, st, x, s, mb + 4 * DIT_D, mb + 3 * DIT_D, mod_ld, xn);
+    {
+      Epilogue e;
+      e.act1 = ACT_GELU_TANH;
+      e.row2seq = s.d_row2seq;
+      e.out = ff;
+      conv_gemm(ctx, st, xn, w.ff1, e);
+    }
+    {
+      Epilogue e;
+      e.row2seq = s.d_row2seq;
+      e.out = o;
+      conv_gemm(ctx, st, ff, w.ff2, e);
+    }
+    gate_add(ctx, st, x, o, s, mb + 5 * DIT_D, mod_ld);
+  }
+  const float* mf = mod.f32() + (size_t)m->depth * 6 * DIT_D;   // norm_out: [scale | shift] (modules.py:261)
+  ln_mod(ctx, st, x, s, mf, mf + DIT_D, mod_ld, xn);
+  {
+    Epilogue e;
+    e.row2seq = s.d_row2seq;
+    e.out = out;
+    conv_gemm(ctx, st, xn, m->proj_out, e);
+  }
+  ctx->arena.off = mark;
 }
 
 }  // namespace
@@ -839,5 +1123,167 @@ void flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, 
     CVK_LAUNCH_CHECK();
   }
   cfm_solve_packed(ctx, st, s2, mel_lens.data(), mu, cond, spk.f32(), x, n_timesteps, 0.7f, streaming);
+  unpack_rows_skip(ctx, st, x, s2, prompt_feat_lens, mel, N_MEL);
+}
+
+// ================================================================================================ CosyVoice3 entry points
+void dit_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
+  DitModel* m = new DitModel();
+  if (ncfg >= 1) m->depth = cfg[0];
+  const std::string P = "flow3.";
+  m->tok_emb = copy_param(ctx, P + "input_embedding.weight");
+  m->spk_affine = make_linear(ctx, P + "spk_embed_affine_layer.weight", P + "spk_embed_affine_layer.bias");
+  m->spk_affine.w16 = nullptr;
+  m->pre1 = make_conv_named(ctx, P + "pre_lookahead_layer.conv1.weight", P + "pre_lookahead_layer.conv1.bias", 1, 0);
+  m->pre2 = make_conv_named(ctx, P + "pre_lookahead_layer.conv2.weight", P + "pre_lookahead_layer.conv2.bias", 1, -2);
+  const std::string D = P + "decoder.estimator.";
+  m->t1 = make_linear(ctx, D + "time_embed.time_mlp.0.weight", D + "time_embed.time_mlp.0.bias");
+  m->t2 = make_linear(ctx, D + "time_embed.time_mlp.2.weight", D + "time_embed.time_mlp.2.bias");
+  m->t1.w16 = nullptr;
+  m->t2.w16 = nullptr;
+  {
+    const RawTensor& w = ctx->get_raw(D + "input_embed.proj.weight");
+    CVK_REQUIRE(w.shape[0] == DIT_D && w.shape[1] == 320, "input_embed.proj must be [1024, 320]");
+    float* perm = (float*)ctx->dmalloc((size_t)DIT_D * 320 * sizeof(float));
+    dit_permute_inproj_kernel<<<256, 256>>>(w.p, perm, DIT_D);
+    CVK_LAUNCH_CHECK();
+    CVK_CHECK_CUDA(cudaDeviceSynchronize());
+    m->in_proj = make_conv(ctx, perm, ctx->get_raw(D + "input_embed.proj.bias").p, DIT_D, 320, 1, 1, 0);
+  }
+  for (int c = 0; c < 2; ++c) {
+    const std::string n = D + "input_embed.conv_pos_embed.conv" + std::to_string(c + 1) + ".0.";
+    const RawTensor& w = ctx->get_raw(n + "weight");
+    const RawTensor& b = ctx->get_raw(n + "bias");
+    CVK_REQUIRE(w.shape[0] == DIT_D && w.shape[1] == DIT_D / DIT_GROUPS && w.shape[2] == DIT_CK, "conv_pos_embed must be [1024, 64, 31]");
+    for (int g = 0; g < DIT_GROUPS; ++g) {
+      ConvW cw = make_conv(ctx, w.p + (size_t)g * 64 * 64 * DIT_CK, b.p + g * 64, 64, 64, DIT_CK, 1, -(DIT_CK - 1));   // causal: 30 rows back
+      (c == 0 ? m->pos1 : m->pos2).push_back(cw);
+    }
+  }
+  std::vector<std::string> mw, mbias;
+  for (int i = 0; i < m->depth; ++i) {
+    const std::string b = D + "transformer_blocks." + std::to_string(i) + ".";
+    mw.push_back(b + "attn_norm.linear.weight");
+    mbias.push_back(b + "attn_norm.linear.bias");
+    DitBlockW w;
+    w.qkv = concat_linear(ctx, {b + "attn.to_q.weight", b + "attn.to_k.weight", b + "attn.to_v.weight"},
+                          {b + "attn.to_q.bias", b + "attn.to_k.bias", b + "attn.to_v.bias"});
+    w.out = make_linear(ctx, b + "attn.to_out.0.weight", b + "attn.to_out.0.bias");
+    w.ff1 = make_linear(ctx, b + "ff.ff.0.0.weight", b + "ff.ff.0.0.bias");
+    w.ff2 = make_linear(ctx, b + "ff.ff.2.weight", b + "ff.ff.2.bias");
+    m->blocks.push_back(w);
+  }
+  mw.push_back(D + "norm_out.linear.weight");
+  mbias.push_back(D + "norm_out.linear.bias");
+  m->mod_all = concat_linear(ctx, mw, mbias);
+  m->mod_all.w16 = nullptr;        // fp32 CUDA-core GEMM on 2B rows
+  m->proj_out = make_linear(ctx, D + "proj_out.weight", D + "proj_out.bias");
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  ctx->dit = m;
+}
+
+// dit.py:145-176 on dense inputs (same argument layout as cvk_cfm_estimator)
+void dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
+                   int B, int streaming, float* out, cudaStream_t st) {
+  CVK_REQUIRE(ctx->dit && ctx->dit->tok_emb, "flow3 stage not finalised");
+  ctx->arena.reset();
+  const int adt = ctx->act_dtype;
+  Seqs s = make_seqs(ctx, lens, B, 32, 1, 0, st);
+  Mat in0 = arena_mat(ctx, adt, s.R, 320);
+  zero_mat(ctx, st, in0);
+  int* off = upload(ctx, prefix(lens, B), st);
+  int bx = s.max_len < 1024 ? s.max_len : 1024;
+  if (adt == DT_F32) est_pack_kernel<float><<<dim3(bx, B), 96, 0, st>>>(x, mu, cond, spks, off, s.d_start, s.d_len, in0.f32(), in0.ld);
+  else est_pack_kernel<bf16><<<dim3(bx, B), 96, 0, st>>>(x, mu, cond, spks, off, s.d_start, s.d_len, in0.b16(), in0.ld);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  Mat v = arena_mat(ctx, DT_F32, s.R, N_MEL, N_MEL);
+  dit_estimator_forward(ctx, st, s, in0, t, streaming, v);
+  unpack_rows(ctx, st, v, s, 0, out, N_MEL);
+}
+
+// flow.py:369-414 CausalMaskedDiffWithDiT.inference, batched over ragged utterances
+void flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
+                     const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, cudaStream_t st) {
+  DitModel* m = ctx->dit;
+  CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
+  CVK_REQUIRE(ctx->flow && ctx->flow->noise, "cvk_cfm_set_noise has not been called");
+  ctx->arena.reset();
+  const int adt = ctx->act_dtype;
+  const int ctxl = finalize ? 0 : 3;
+  Mat en = arena_mat(ctx, DT_F32, B, 192), spk = arena_mat(ctx, DT_F32, B, N_MEL, N_MEL);
+  l2norm_kernel<<<B, 64, 0, st>>>(embedding, en.f32(), 192);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  {
+    Epilogue e;
+    e.out = spk;
+    conv_gemm_simt(ctx, st, en, m->spk_affine, e);
+  }
+  // token embedding (80 wide) -> PreLookaheadLayer(80, 1024, 3) -> + input (upsample_encoder.py:82-103)
+  Seqs sf = make_seqs(ctx, token_lens, B, 8, 1, 0, st);
+  Seqs s1 = ctxl > 0 ? shrink_seqs(ctx, sf, ctxl, st) : sf;
+  int* toff = upload(ctx, prefix(token_lens, B), st);
+  Mat emb = arena_mat(ctx, DT_F32, sf.R, N_MEL);
+  zero_mat(ctx, st, emb);
+  {
+    int bx = sf.max_len < 512 ? sf.max_len : 512;
+    token_embed_kernel<float><<<dim3(bx, B), 96, 0, st>>>(tokens, toff, m->tok_emb, sf.d_start, sf.d_len, emb.f32(), emb.ld, N_MEL);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  Mat emba = emb;
+  if (adt != DT_F32) {
+    emba = arena_mat(ctx, adt, sf.R, N_MEL);
+    convert_mat(ctx, st, emb, emba);
+  }
+  Mat c1 = arena_mat(ctx, adt, sf.R, DIT_D);
+  {
+    Epilogue e;
+    e.act1 = ACT_LRELU;
+    e.act1_param = 0.01f;
+    e.row2seq = s1.d_row2seq;
+    e.out = c1;
+    conv_gemm(ctx, st, emba, m->pre1, e);
+  }
+  Mat h = arena_mat(ctx, DT_F32, sf.R, N_MEL);
+  {
+    Epilogue e;
+    e.resid = emb;
+    e.row2seq = s1.d_row2seq;      // look-ahead context rows are dropped here
+    e.out = h;
+    conv_gemm(ctx, st, c1, m->pre2, e);
+  }
+  // mu = repeat_interleave(h, 2) in the mel geometry
+  Seqs s2 = scale_seqs(ctx, s1, 2, 0, st);
+  Mat mu = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
+  zero_mat(ctx, st, mu);
+  {
+    int bx = s1.max_len < 1024 ? s1.max_len : 1024;
+    repeat2_rows_kernel<<<dim3(bx, B), 96, 0, st>>>(h.f32(), h.ld, s1.d_start, s1.d_len, mu.f32(), mu.ld, s2.d_start, N_MEL);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  Mat cond = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
+  zero_mat(ctx, st, cond);
+  std::vector<int> mel_lens(B);
+  for (int b = 0; b < B; ++b) {
+    mel_lens[b] = s2.len[b];
+    CVK_REQUIRE(prompt_feat_lens[b] >= 0 && prompt_feat_lens[b] < mel_lens[b], "prompt_feat longer than the generated mel");
+  }
+  if (prompt_feat) {
+    Seqs sp = subseqs(ctx, s2, prompt_feat_lens, st);
+    pack_rows(ctx, st, prompt_feat, N_MEL, sp, cond);
+  }
+  Mat x = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
+  zero_mat(ctx, st, x);
+  CVK_REQUIRE(ctx->flow->noise_T >= s2.max_len, "the CFM noise tensor is too short");
+  {
+    int bx = s2.max_len < 1024 ? s2.max_len : 1024;
+    noise_init_kernel<<<dim3(bx, B), 96, 0, st>>>(ctx->flow->noise, ctx->flow->noise_T, s2.d_start, s2.d_len, x.f32());
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  cfm_solve_packed(ctx, st, s2, mel_lens.data(), mu, cond, spk.f32(), x, n_timesteps, 0.7f, streaming, 1);
   unpack_rows_skip(ctx, st, x, s2, prompt_feat_lens, mel, N_MEL);
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
     "cvk_cfm_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, _vp, _vp]),
     "cvk_flow_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_cfm_set_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "cvk_dit_estimator": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "cvk_flow3_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_lm_session_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "cvk_lm_session_destroy": (None, [_vp, _vp]),
     "cvk_lm_prefill": (ctypes.c_int, [_vp, _vp, _vp, _c_int_p, _vp, _c_int_p, ctypes.c_int, _vp]),
@@ -257,6 +259,28 @@ class Context:
         self._check(self.lib.cvk_cfm_estimator(self.h, _ptr(x), _ptr(mu), _ptr(t), _ptr(spks), _ptr(cond), _ints(lens), len(lens),
                                                int(streaming), _ptr(out), _stream()))
         return out
+
+    def dit_estimator(self, x, mu, t, spks, cond, lens, streaming=False):
+        """CosyVoice3 DiT estimator (stage "flow3"); same layout as cfm_estimator."""
+        x, mu, t, spks, cond = (_f32(a, self.device) for a in (x, mu, t, spks, cond))
+        out = torch.empty_like(x)
+        self._check(self.lib.cvk_dit_estimator(self.h, _ptr(x), _ptr(mu), _ptr(t), _ptr(spks), _ptr(cond), _ints(lens), len(lens),
+                                               int(streaming), _ptr(out), _stream()))
+        return out
+
+    def flow3_inference(self, tokens, token_lens, prompt_feat, prompt_feat_lens, embedding, n_timesteps=10, streaming=False,
+                        finalize=True):
+        """CosyVoice3 flow (CausalMaskedDiffWithDiT.inference); same layout as flow_inference."""
+        tokens = tokens.to(device=self.device, dtype=torch.int32).contiguous()
+        prompt_feat = _f32(prompt_feat, self.device) if prompt_feat is not None and prompt_feat.numel() else None
+        embedding = _f32(embedding, self.device)
+        ctxl = 0 if finalize else 3
+        out_lens = [2 * (int(n) - ctxl) - int(p) for n, p in zip(token_lens, prompt_feat_lens)]
+        mel = torch.empty(sum(out_lens), 80, device=self.device)
+        self._check(self.lib.cvk_flow3_inference(self.h, _ptr(tokens), _ints(token_lens), _ptr(prompt_feat), _ints(prompt_feat_lens),
+                                                 _ptr(embedding), len(token_lens), n_timesteps, int(streaming), int(finalize),
+                                                 _ptr(mel), _stream()))
+        return mel, out_lens
 
     def cfm_solve(self, mu, spks, cond, lens, z=None, n_timesteps=10, cfg_rate=0.7, streaming=False):
         mu, spks, cond = (_f32(a, self.device) for a in (mu, spks, cond))

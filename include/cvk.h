@@ -120,6 +120,20 @@ int cvk_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float*
 int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens_host, const float* prompt_feat,
                        const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming,
                        int finalize, float* mel, void* stream);
+
+/* ---- CosyVoice3 flow (stage "flow3", cvk_finalize cfg = {DiT depth}) -----------------------------------------------------------
+ * cosyvoice/flow/DiT/dit.py:145-176 (DiT.forward, the CFM estimator of CosyVoice3; TensorRT swap point flow_matching.py:126-153):
+ * same dense argument layout as cvk_cfm_estimator - x, mu, cond [sum T, 80] time-major, t [B], spks [B, 80] -> out [sum T, 80];
+ * streaming != 0 selects the static 50-frame block-causal mask (dit.py:165-166). */
+int cvk_dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond,
+                      const int* lens_host, int B, int streaming, float* out, void* stream);
+/* cosyvoice/flow/flow.py:369-414 CausalMaskedDiffWithDiT.inference for B utterances: tokens = prompt tokens followed by the new
+ * tokens of every utterance (token_lens_host), prompt_feat [sum Tp, 80], embedding [B, 192]; finalize == 0: the last 3 tokens of
+ * every utterance are look-ahead context (flow.py:389-392).  mel receives 2 * (tokens - context) - Tp frames per utterance.
+ * The CFM noise is the tensor given to cvk_cfm_set_noise. */
+int cvk_flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens_host, const float* prompt_feat,
+                        const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming, int finalize,
+                        float* mel, void* stream);
 /* the fixed noise tensor of CausalConditionalCFM (flow_matching.py:199-200) must be supplied once: [15000,80]
  * time-major (it is torch's seed-0 randn stream; the library does not re-implement torch's Philox/MT generator) */
 int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device);
