@@ -21,6 +21,10 @@ void flow_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device);
 void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg);
 cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context);
 void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s);
+void hift3_build(cvk_ctx* ctx);
+void hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_noise, long long n, int on_device);
+void hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, int finalize, float* wav, float* f0_out, float* source_out,
+                     cudaStream_t st);
 void dit_build(cvk_ctx* ctx, const int* cfg, int ncfg);
 void dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
                    int B, int streaming, float* out, cudaStream_t st);
@@ -194,6 +198,7 @@ int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg) {
   if (s == "hift") hift_build(ctx);
   else if (s == "flow") flow_build(ctx, cfg, ncfg);
   else if (s == "flow3") dit_build(ctx, cfg, ncfg);
+  else if (s == "hift3") hift3_build(ctx);
   else if (s == "llm") llm_build(ctx, cfg, ncfg);
   else if (s == "mel") mel_init(ctx);
   else throw CvkError(CVK_ERR_INVALID, "unknown stage: " + s);
@@ -377,6 +382,19 @@ int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device)
 }
 
 // ---------------------------------------------------------------------------------------------- LM
+int cvk_hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_noise, long long n, int on_device) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(rand_ini && sine_noise && n > 0, "cvk_hift3_set_noise: bad arguments");
+  hift3_set_noise(ctx, rand_ini, sine_noise, n, on_device);
+  CVK_API_END
+}
+int cvk_hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, int finalize, float* wav, float* f0_out,
+                        float* source_out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(mel && lens_host && wav && B > 0, "cvk_hift3_inference: bad arguments");
+  hift3_inference(ctx, mel, lens_host, B, finalize, wav, f0_out, source_out, (cudaStream_t)stream);
+  CVK_API_END
+}
 int cvk_dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond,
                       const int* lens_host, int B, int streaming, float* out, void* stream) {
   CVK_API_BEGIN

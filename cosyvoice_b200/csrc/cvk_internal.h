@@ -156,6 +156,8 @@ struct cvk_ctx {
   std::vector<void*> owned;                 // device allocations owned by the context
   Arena arena;
   HiftModel* hift = nullptr;
+  HiftModel* hift3 = nullptr;               // CosyVoice3 causal vocoder (stage "hift3"), same conv-GEMM body with causal weights
+  void* hift3_extra = nullptr;              // fp64 f0 predictor + stored source noise (hift.cu)
   FlowModel* flow = nullptr;
   DitModel* dit = nullptr;                  // CosyVoice3 flow (stage "flow3")
   LlmModel* llm = nullptr;

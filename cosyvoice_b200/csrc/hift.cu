@@ -443,8 +443,9 @@ static void run_resblock(cvk_ctx* ctx, cudaStream_t st, const ResBlockW& rb, con
 }
 
 // mel packed + source packed -> conv_post output [R3, 18] fp32 (ld 24)
-static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat& mel32, const float* src_packed) {
-  HiftModel* m = ctx->hift;
+static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat& mel32, const float* src_packed,
+                     const HiftModel* m = nullptr) {
+  if (!m) m = ctx->hift;
   const int adt = ctx->act_dtype;
   const Seqs& s0 = g.s0;
   // STFT of the source at the x120 rate
@@ -654,5 +655,287 @@ void hift_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, cons
     CVK_LAUNCH_CHECK();
   }
   Mat xp = hift_body(ctx, st, g, mel32, src);
+  hift_istft(ctx, st, g, lens, xp, wav);
+}
+
+
+// ================================================================================================ CosyVoice3 causal vocoder
+// cosyvoice/hifigan/generator.py:572-726 (CausalHiFTGenerator), f0_predictor.py:60-103 (CausalConvRNNF0Predictor, float64 per
+// generator.py:716-717), convolution.py:150-258 (causal convolutions), the causal branches of SineGen2 / SourceModuleHnNSF.
+// The vocoder BODY is the CosyVoice2 one with different weights: every centred convolution becomes a left-padded one (a different
+// row shift of the same conv-GEMM), conv_pre looks 4 frames to the right, the transposed convolutions become nearest-neighbour
+// up-sampling + causal convolution (again a 3-tap polyphase conv-GEMM whose [R, u*C] output is the next level's [u*R, C]), and
+// the strided source_downs pad left only.  The f0 predictor runs in float64 on CUDA cores (a few GFLOP per utterance; the
+// reference insists on float64 so that streaming and offline f0 agree), the harmonic source uses nearest-neighbour phase
+// up-sampling and the module's stored uniform noise instead of fresh Gaussian draws.
+// finalize == 0 (streaming chunk with look-ahead frames) is not built yet.
+namespace {
+
+struct F64Conv {
+  double* w = nullptr;      // [taps][K][N]  (n fastest: coalesced across the threads of a block)
+  double* bias = nullptr;   // [N]
+  int N = 0, K = 0, taps = 0, shift0 = 0;
+};
+struct Hift3Extra {
+  F64Conv conv[5];
+  double* cls_w = nullptr;  // [512]
+  double cls_b = 0.0;
+  float* rand_ini = nullptr;    // [9]  (SineGen2.rand_ini; without effect for upsample_scale 480, kept for the interface)
+  float* noise = nullptr;       // [n][9]  SineGen2.sine_waves
+  long long noise_n = 0;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// nn.Upsample(nearest, u) + left pad k-1 + Conv1d(k)  ==  3-tap polyphase conv on the un-upsampled input:
+//   out[u m + p, co] = sum_{jt<3} sum_ci x[m + jt - 2, ci] * W[p][co][jt][ci],  W[p][co][jt] = sum_{j: floor((p-k+1+j)/u) == jt-2} w[co][ci][j]
+__global__ void upsample_causal_poly_kernel(const float* __restrict__ w /*[Cout][Cin][k]*/, float* __restrict__ o /*[u*Cout][3][Cin]*/,
+                                            int Cin, int Cout, int k, int u) {
+  const size_t total = (size_t)u * Cout * 3 * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int jt = (int)((i / Cin) % 3);
+    const int n = (int)(i / ((size_t)Cin * 3));
+    const int p = n / Cout, co = n % Cout;
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j)
+      if (floor_div(p - (k - 1) + j, u) == jt - 2) acc += w[((size_t)co * Cin + ci) * k + j];
+    o[i] = acc;
+  }
+}
+
+// ConvW.w32 [N][taps][K] fp32 -> [taps][K][N] fp64
+__global__ void f64_weight_kernel(const float* __restrict__ w, double* __restrict__ o, int N, int taps, int K) {
+  const size_t total = (size_t)N * taps * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K), j = (int)((i / K) % taps), n = (int)(i / ((size_t)K * taps));
+    o[((size_t)j * K + k) * N + n] = (double)w[i];
+  }
+}
+__global__ void f64_copy_kernel(const float* __restrict__ a, double* __restrict__ o, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = (double)a[i];
+}
+
+// out[r, n] = ELU(bias[n] + sum_j sum_k A[r + shift0 + j, k] * w[j][k][n]) in float64; one block per row, rows outside every
+// sequence (row2seq < 0) stay zero so that they act as the zero padding of the next layer
+__global__ void conv_f64_kernel(const double* __restrict__ A, int K, const double* __restrict__ w, const double* __restrict__ bias, int N, int taps,
+                                int shift0, int rows, const int* __restrict__ row2seq, double* __restrict__ out) {
+  const int r = blockIdx.x;
+  const bool valid = row2seq[r] >= 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    double acc = 0.0;
+    if (valid) {
+      acc = bias[n];
+      for (int j = 0; j < taps; ++j) {
+        const int rr = r + shift0 + j;
+        if (rr < 0 || rr >= rows) continue;
+        const double* a = A + (size_t)rr * K;
+        const double* wp = w + (size_t)j * K * N + n;
+        for (int k = 0; k < K; ++k) acc = fma(a[k], wp[(size_t)k * N], acc);
+      }
+      acc = acc > 0.0 ? acc : expm1(acc);
+    }
+    out[(size_t)r * N + n] = acc;
+  }
+}
+// f0 = |x . w + b| (f0_predictor.py:103), written as float32
+__global__ void f0_head_f64_kernel(const double* __restrict__ x, const double* __restrict__ w, double b, int rows, const int* __restrict__ row2seq,
+                                   float* __restrict__ f0) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double acc = 0.0;
+  if (row2seq[r] >= 0)
+    for (int k = lane; k < 512; k += 32) acc = fma(x[(size_t)r * 512 + k], w[k], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) f0[r] = row2seq[r] >= 0 ? (float)fabs(acc + b) : 0.f;
+}
+
+// causal SineGen2 + SourceModuleHnNSF (generator.py:255-261 nearest up-sampling of the phase, :303-307 stored noise, :358-366)
+__global__ void source_causal_kernel(const float* __restrict__ f0, int f0_ld, const float* __restrict__ phase, const int* __restrict__ start,
+                                     const int* __restrict__ len, const float* __restrict__ noise /*[n][9], indexed from the utterance start*/,
+                                     const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ src) {
+  const int b = blockIdx.y;
+  const int T = len[b], s0 = start[b];
+  const int L = T * kUpscale;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    const int t = l / kUpscale;
+    const float f = f0[(size_t)(s0 + t) * f0_ld];
+    const float uv = f > 10.f ? 1.f : 0.f;
+    const float noise_amp = uv * 0.003f + (1.f - uv) * 0.1f / 3.f;
+    const float* p0 = phase + (size_t)(s0 + t) * 9;
+    const float* nz = noise + (size_t)l * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 9; ++h) acc += ((sinf(p0[h]) * 0.1f) * uv + noise_amp * nz[h]) * lw[h];
+    src[(size_t)s0 * kUpscale + l] = tanhf(acc + lb[0]);
+  }
+}
+
+ResBlockW build_resblock_causal(cvk_ctx* ctx, const std::string& p, int k) {
+  ResBlockW r;
+  for (int i = 0; i < 3; ++i) {
+    const int d = kDil[i];
+    r.c1[i] = wn_conv(ctx, p + ".convs1." + std::to_string(i), d, -(k - 1) * d);     // left padding (k-1)*d (convolution.py:172)
+    r.c2[i] = wn_conv(ctx, p + ".convs2." + std::to_string(i), 1, -(k - 1));
+    r.a1[i] = dev_copy_f32(ctx, ctx->get_raw(p + ".activations1." + std::to_string(i) + ".alpha").p, r.c1[i].K);
+    r.a2[i] = dev_copy_f32(ctx, ctx->get_raw(p + ".activations2." + std::to_string(i) + ".alpha").p, r.c1[i].K);
+  }
+  return r;
+}
+
+}  // namespace
+
+void hift3_build(cvk_ctx* ctx) {
+  init_consts();
+  HiftModel* m = new HiftModel();
+  Hift3Extra* x = ctx->hift3_extra ? (Hift3Extra*)ctx->hift3_extra : new Hift3Extra();
+  const std::string P = "hift3.";
+  // float64 f0 predictor: conv0 k4 looking RIGHT (f0_predictor.py:71), then four causal k3 convolutions
+  for (int i = 0; i < 5; ++i) {
+    ConvW c = wn_conv(ctx, P + "f0_predictor.condnet." + std::to_string(2 * i), 1, i == 0 ? 0 : -2);
+    CVK_CHECK_CUDA(cudaDeviceSynchronize());
+    F64Conv& f = x->conv[i];
+    f.N = c.N; f.K = c.K; f.taps = c.taps; f.shift0 = c.shift0;
+    f.w = (double*)ctx->dmalloc((size_t)c.N * c.taps * c.K * sizeof(double));
+    f.bias = (double*)ctx->dmalloc((size_t)c.N * sizeof(double));
+    f64_weight_kernel<<<256, 256>>>(c.w32, f.w, c.N, c.taps, c.K);
+    f64_copy_kernel<<<4, 256>>>(c.bias, f.bias, (size_t)c.N);
+    CVK_LAUNCH_CHECK();
+  }
+  {
+    const RawTensor& w = ctx->get_raw(P + "f0_predictor.classifier.weight");
+    const RawTensor& b = ctx->get_raw(P + "f0_predictor.classifier.bias");
+    x->cls_w = (double*)ctx->dmalloc(512 * sizeof(double));
+    f64_copy_kernel<<<2, 256>>>(w.p, x->cls_w, 512);
+    CVK_LAUNCH_CHECK();
+    float bh = 0.f;
+    CVK_CHECK_CUDA(cudaMemcpy(&bh, b.p, sizeof(float), cudaMemcpyDeviceToHost));
+    x->cls_b = (double)bh;
+  }
+  m->src_w = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.weight").p, 9);
+  m->src_b = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.bias").p, 1);
+  m->conv_pre = wn_conv(ctx, P + "conv_pre", 1, 0);          // k5, 4 frames of look-ahead (convolution.py:183-184 'right')
+  m->conv_post = wn_conv(ctx, P + "conv_post", 1, -6);       // k7 causal
+  for (int i = 0; i < 3; ++i) {
+    const std::string pre = P + "ups." + std::to_string(i);
+    float* w = fold_weight_norm(ctx, pre, nullptr);          // Conv1d layout [Cout][Cin][k]
+    const int Cin = kCh[i], Cout = kCh[i + 1], k = kUpK[i], u = kUps[i];
+    ConvW c;
+    c.N = u * Cout; c.K = Cin; c.taps = 3; c.dil = 1; c.shift0 = -2;
+    c.w32 = (float*)ctx->dmalloc((size_t)c.N * 3 * Cin * sizeof(float));
+    upsample_causal_poly_kernel<<<256, 256>>>(w, c.w32, Cin, Cout, k, u);
+    CVK_LAUNCH_CHECK();
+    c.bias = (float*)ctx->dmalloc((size_t)c.N * sizeof(float));
+    repeat_bias_kernel<<<ceil_div(c.N, 256), 256>>>(ctx->get_raw(pre + ".bias").p, c.bias, Cout, u);
+    CVK_LAUNCH_CHECK();
+    finish_convw(ctx, c);
+    m->ups[i] = c;
+  }
+  {
+    // CausalConv1dDownSample(k = 2*stride, stride): left pad stride-1 -> STFT frame stride*r - (stride-1) + j for tap j
+    const int ds[3] = {15, 3, 1}, dk[3] = {30, 6, 1};
+    for (int i = 0; i < 3; ++i) {
+      const std::string pre = P + "source_downs." + std::to_string(i);
+      const RawTensor& w = ctx->get_raw(pre + ".weight");
+      const int N = (int)w.shape[0], C = (int)w.shape[1], k = (int)w.shape[2];
+      CVK_REQUIRE(C == 18 && k == dk[i] && N == kCh[i + 1], "unexpected source_downs shape");
+      ConvW c;
+      c.N = N;
+      c.bias = dev_copy_f32(ctx, ctx->get_raw(pre + ".bias").p, N);
+      if (ds[i] == 1) {
+        c.K = kStftLd; c.taps = 1; c.dil = 1; c.shift0 = 0;
+        c.w32 = (float*)ctx->dmalloc((size_t)N * kStftLd * sizeof(float));
+        CVK_CHECK_CUDA(cudaMemset(c.w32, 0, (size_t)N * kStftLd * sizeof(float)));
+        CVK_CHECK_CUDA(cudaMemcpy2D(c.w32, kStftLd * sizeof(float), w.p, 18 * sizeof(float), 18 * sizeof(float), N, cudaMemcpyDeviceToDevice));
+      } else {
+        c.K = ds[i] * kStftLd; c.taps = 3; c.dil = 1; c.shift0 = -1;
+        const size_t n = (size_t)N * 3 * c.K;
+        c.w32 = (float*)ctx->dmalloc(n * sizeof(float));
+        CVK_CHECK_CUDA(cudaMemset(c.w32, 0, n * sizeof(float)));
+        strided_view_fill_kernel<<<64, 256>>>(w.p, c.w32, N, C, k, ds[i], ds[i]);   // level-3 row = s*r + j - ((s-1) + 1)
+        CVK_LAUNCH_CHECK();
+      }
+      finish_convw(ctx, c);
+      m->src_down[i] = c;
+    }
+  }
+  for (int i = 0; i < 3; ++i) m->src_rb[i] = build_resblock_causal(ctx, P + "source_resblocks." + std::to_string(i), kSrcRbK[i]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m->rb[i * 3 + j] = build_resblock_causal(ctx, P + "resblocks." + std::to_string(i * 3 + j), kRbK[j]);
+  CVK_CHECK_CUDA(cudaDeviceSynchronize());
+  ctx->hift3 = m;
+  ctx->hift3_extra = x;
+}
+
+// SineGen2.rand_ini [9] and SineGen2.sine_waves [n][9] (generator.py:223-226): module attributes, not state_dict entries
+void hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_noise, long long n, int on_device) {
+  Hift3Extra* x = ctx->hift3_extra ? (Hift3Extra*)ctx->hift3_extra : new Hift3Extra();
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  x->rand_ini = (float*)ctx->dmalloc(9 * sizeof(float));
+  CVK_CHECK_CUDA(cudaMemcpy(x->rand_ini, rand_ini, 9 * sizeof(float), kind));
+  x->noise = (float*)ctx->dmalloc((size_t)n * 9 * sizeof(float));
+  CVK_CHECK_CUDA(cudaMemcpy(x->noise, sine_noise, (size_t)n * 9 * sizeof(float), kind));
+  x->noise_n = n;
+  ctx->hift3_extra = x;
+}
+
+// generator.py:714-726 with finalize=True.  mel dense [sum T, 80]; wav [sum 480 T]; f0_out [sum T] / source_out [sum 480 T] optional
+void hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, int finalize, float* wav, float* f0_out, float* source_out,
+                     cudaStream_t st) {
+  const HiftModel* m = ctx->hift3;
+  Hift3Extra* x = (Hift3Extra*)ctx->hift3_extra;
+  CVK_REQUIRE(m && x && x->conv[0].w, "hift3 stage not finalised");
+  CVK_REQUIRE(x->noise != nullptr, "cvk_hift3_set_noise has not been called");
+  CVK_REQUIRE(finalize != 0, "cvk_hift3_inference: the streaming (finalize = 0) variant is not built yet");
+  ctx->arena.reset();
+  HiftGeom g = hift_geom(ctx, lens, B, st);
+  const Seqs& s0 = g.s0;
+  for (int b = 0; b < B; ++b) CVK_REQUIRE((long long)lens[b] * kUpscale <= x->noise_n, "stored source noise shorter than the utterance");
+  Mat mel32 = pack_mel(ctx, st, s0, mel);
+  // ---- f0 predictor in float64
+  double* a = (double*)ctx->arena.alloc(sizeof(double) * (size_t)s0.R * 512);
+  double* bb = (double*)ctx->arena.alloc(sizeof(double) * (size_t)s0.R * 512);
+  double* mel64 = (double*)ctx->arena.alloc(sizeof(double) * (size_t)s0.R * 80);
+  f64_copy_kernel<<<256, 256, 0, st>>>(mel32.f32(), mel64, (size_t)s0.R * 80);
+  ctx->launches++;
+  CVK_REQUIRE(mel32.ld == 80, "packed mel must be dense");
+  const double* cur = mel64;
+  for (int i = 0; i < 5; ++i) {
+    const F64Conv& f = x->conv[i];
+    double* o = (i & 1) ? bb : a;
+    conv_f64_kernel<<<s0.R, 128, 0, st>>>(cur, f.K, f.w, f.bias, f.N, f.taps, f.shift0, s0.R, s0.d_row2seq, o);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    cur = o;
+  }
+  Mat f0 = arena_mat(ctx, DT_F32, s0.R, 1, 1);
+  f0_head_f64_kernel<<<ceil_div(s0.R, 4), 128, 0, st>>>(cur, x->cls_w, x->cls_b, s0.R, s0.d_row2seq, f0.f32());
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  if (f0_out) {
+    gather_f0_kernel<<<dim3(ceil_div(s0.max_len, 128), B), 128, 0, st>>>(f0.f32(), 1, s0.d_start, s0.d_len, off, f0_out);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  // ---- harmonic source
+  float* phase = (float*)ctx->arena.alloc(sizeof(float) * 9 * (size_t)s0.R);
+  phase_kernel<<<s0.B, 32, 0, st>>>(f0.f32(), f0.ld, s0.d_start, s0.d_len, phase);
+  float* src = (float*)ctx->arena.alloc(sizeof(float) * (size_t)s0.R * kUpscale);
+  CVK_CHECK_CUDA(cudaMemsetAsync(src, 0, sizeof(float) * (size_t)s0.R * kUpscale, st));
+  {
+    int bx = ceil_div(s0.max_len * kUpscale, 256);
+    if (bx > 512) bx = 512;
+    source_causal_kernel<<<dim3(bx, s0.B), 256, 0, st>>>(f0.f32(), f0.ld, phase, s0.d_start, s0.d_len, x->noise, m->src_w, m->src_b, src);
+  }
+  ctx->launches += 2;
+  CVK_LAUNCH_CHECK();
+  if (source_out) {
+    copy_samples_kernel<<<dim3(256, B), 256, 0, st>>>(src, source_out, s0.d_start, s0.d_len, off, 0);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+  }
+  // ---- vocoder body (shared with CosyVoice2) + ISTFT
+  Mat xp = hift_body(ctx, st, g, mel32, src, m);
   hift_istft(ctx, st, g, lens, xp, wav);
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
     "cvk_cfm_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, _vp, _vp]),
     "cvk_flow_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_cfm_set_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "cvk_hift3_set_noise": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_int]),
+    "cvk_hift3_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "cvk_dit_estimator": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_flow3_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_lm_session_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -259,6 +261,23 @@ class Context:
         self._check(self.lib.cvk_cfm_estimator(self.h, _ptr(x), _ptr(mu), _ptr(t), _ptr(spks), _ptr(cond), _ints(lens), len(lens),
                                                int(streaming), _ptr(out), _stream()))
         return out
+
+    def hift3_set_noise(self, rand_ini, sine_noise):
+        """CosyVoice3 vocoder: SineGen2.rand_ini [9] and SineGen2.sine_waves [n,9] (module attributes of the reference)"""
+        rand_ini = _f32(rand_ini.reshape(-1), self.device)
+        sine_noise = _f32(sine_noise.reshape(-1, 9), self.device)
+        self._check(self.lib.cvk_hift3_set_noise(self.h, _ptr(rand_ini), _ptr(sine_noise), sine_noise.shape[0], 1))
+
+    def hift3_inference(self, mel, lens, finalize=True):
+        """CausalHiFTGenerator.inference: mel [sum T, 80] -> (wav [sum 480 T], f0 [sum T], source [sum 480 T])"""
+        mel = _f32(mel, self.device)
+        n = sum(int(l) for l in lens)
+        wav = torch.empty(n * 480, device=self.device)
+        f0 = torch.empty(n, device=self.device)
+        src = torch.empty(n * 480, device=self.device)
+        self._check(self.lib.cvk_hift3_inference(self.h, _ptr(mel), _ints(lens), len(lens), int(finalize), _ptr(wav), _ptr(f0), _ptr(src),
+                                                 _stream()))
+        return wav, f0, src
 
     def dit_estimator(self, x, mu, t, spks, cond, lens, streaming=False):
         """CosyVoice3 DiT estimator (stage "flow3"); same layout as cfm_estimator."""

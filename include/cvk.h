@@ -121,6 +121,17 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
                        const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming,
                        int finalize, float* mel, void* stream);
 
+/* ---- CosyVoice3 vocoder (stage "hift3") ------------------------------------------------------------------------------------
+ * cosyvoice/hifigan/generator.py:572-726 CausalHiFTGenerator (+ f0_predictor.py:60-103 in float64, generator.py:716-717).
+ * cvk_hift3_set_noise hands over the module's constructor-time random tensors, which are not state_dict entries
+ * (generator.py:223-226): rand_ini [9] (SineGen2.rand_ini) and sine_noise [n][9] (SineGen2.sine_waves, indexed from the start of
+ * every utterance).  cvk_hift3_inference = CausalHiFTGenerator.inference (:714-726) for B utterances: mel [sum T, 80] ->
+ * wav [sum 480 T]; f0_out [sum T] and source_out [sum 480 T] are optional (NULL).  Only finalize != 0 is built so far; the
+ * streaming variant (look-ahead frames consumed, tail dropped, :676-683, :709-710, :722-725) returns CVK_ERR_INVALID. */
+int cvk_hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_noise, long long n, int on_device);
+int cvk_hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, int finalize, float* wav, float* f0_out,
+                        float* source_out, void* stream);
+
 /* ---- CosyVoice3 flow (stage "flow3", cvk_finalize cfg = {DiT depth}) -----------------------------------------------------------
  * cosyvoice/flow/DiT/dit.py:145-176 (DiT.forward, the CFM estimator of CosyVoice3; TensorRT swap point flow_matching.py:126-153):
  * same dense argument layout as cvk_cfm_estimator - x, mu, cond [sum T, 80] time-major, t [B], spks [B, 80] -> out [sum T, 80];
