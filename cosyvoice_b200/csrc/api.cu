@@ -36,6 +36,7 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
                 int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host, cudaStream_t st);
 void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B, float* logp, cudaStream_t st);
 void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st);
+int llm_vocab(cvk_ctx* ctx);
 void llm_session_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, cudaStream_t st);
 void llm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids, const int32_t* kinds, int n, cudaStream_t st);
 void llm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, cudaStream_t st);
@@ -442,6 +443,7 @@ int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int 
   llm_forward_logp(ctx, embeds, lens, B, logp, (cudaStream_t)stream);
   CVK_API_END
 }
+int cvk_lm_vocab(cvk_ctx* ctx) { return ctx ? llm_vocab(ctx) : 0; }
 int cvk_lm_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, void* stream) {
   CVK_API_BEGIN
   CVK_REQUIRE(s != nullptr, "cvk_lm_begin: bad arguments");

@@ -15,6 +15,7 @@
 
 namespace {
 constexpr int D = 896, NH = 14, NKV = 2, HD = 64, DFF = 4864, VOUT = 6564, EOS = 6561;
+constexpr int VOUT3 = 6761, VOUT3_PAD = 6764;   // CosyVoice3LM head (llm.py:689), padded to a 16-byte row pitch
 constexpr int QKV_N = NH * HD + 2 * NKV * HD;   // 1152
 constexpr float ROPE_THETA = 1.0e6f, RMS_EPS = 1e-6f;
 constexpr int SAMPLER_THREADS = 256, TOPK = 25, WIN = 10;
@@ -28,6 +29,7 @@ struct LayerW {
 
 struct LlmModel {
   int num_layers = 24;
+  int vout = VOUT;               // width of the head / logits rows: 6564 (Qwen2LM) or 6764 (CosyVoice3LM: 6761 + 3 impossible pad ids)
   std::vector<LayerW> layers;
   float* final_norm = nullptr;
   float* text_emb = nullptr;     // [151936][896]
@@ -697,7 +699,7 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
     return;
   }
   // (7) stop / length logic (llm.py:544-549)
-  const bool stop = top >= EOS && top <= EOS + 2;
+  const bool stop = top >= EOS;      // Qwen2LM: 6561..6563 (llm.py:297); CosyVoice3LM: 6561..6760 (llm.py:704); nothing else exists above 6560
   if (!stop) {
     float ss = 0.f;
     for (int c = tid; c < D; c += SAMPLER_THREADS) {
@@ -868,9 +870,30 @@ void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
   if (ncfg >= 1) m->num_layers = cfg[0];
   const std::string P = "llm.";
   m->text_emb = copy_param(ctx, P + "llm.model.model.embed_tokens.weight");
-  m->llm_emb = copy_param(ctx, P + "llm_embedding.weight");
   m->speech_emb = copy_param(ctx, P + "speech_embedding.weight");
-  m->head = make_linear(ctx, P + "llm_decoder.weight", P + "llm_decoder.bias");
+  if (ctx->has_raw(P + "llm_embedding.weight")) {          // Qwen2LM (CosyVoice2)
+    m->llm_emb = copy_param(ctx, P + "llm_embedding.weight");
+    m->head = make_linear(ctx, P + "llm_decoder.weight", P + "llm_decoder.bias");
+  } else {
+    // CosyVoice3LM (llm.py:664-705): sos / task_id are rows 6561 / 6563 of speech_embedding; the head has 6761 outputs and no bias.
+    // The head is padded to 6764 rows (16-byte logits pitch for the TMA epilogues); the 3 pad ids get a bias of -1e30, i.e.
+    // probability exactly 0 after the softmax, so sampling, log-probs and the stop rule (id >= 6561) see the reference's vocabulary.
+    const RawTensor& se = ctx->get_raw(P + "speech_embedding.weight");
+    const RawTensor& hw = ctx->get_raw(P + "llm_decoder.weight");
+    CVK_REQUIRE(se.shape[0] == VOUT3 && hw.shape[0] == VOUT3 && hw.shape[1] == D, "CosyVoice3LM: speech_embedding / llm_decoder must have 6761 rows");
+    m->llm_emb = (float*)ctx->dmalloc(2 * D * sizeof(float));
+    CVK_CHECK_CUDA(cudaMemcpy(m->llm_emb, se.p + (size_t)EOS * D, D * sizeof(float), cudaMemcpyDeviceToDevice));               // sos = 6561
+    CVK_CHECK_CUDA(cudaMemcpy(m->llm_emb + D, se.p + (size_t)(EOS + 2) * D, D * sizeof(float), cudaMemcpyDeviceToDevice));     // task_id = 6563
+    float* wpad = (float*)ctx->dmalloc((size_t)VOUT3_PAD * D * sizeof(float));
+    CVK_CHECK_CUDA(cudaMemset(wpad, 0, (size_t)VOUT3_PAD * D * sizeof(float)));
+    CVK_CHECK_CUDA(cudaMemcpy(wpad, hw.p, (size_t)VOUT3 * D * sizeof(float), cudaMemcpyDeviceToDevice));
+    std::vector<float> hb(VOUT3_PAD, 0.f);
+    for (int i = VOUT3; i < VOUT3_PAD; ++i) hb[i] = -1.0e30f;
+    float* bpad = (float*)ctx->dmalloc(VOUT3_PAD * sizeof(float));
+    CVK_CHECK_CUDA(cudaMemcpy(bpad, hb.data(), VOUT3_PAD * sizeof(float), cudaMemcpyHostToDevice));
+    m->head = make_conv(ctx, wpad, bpad, VOUT3_PAD, D, 1, 1, 0);
+    m->vout = VOUT3_PAD;
+  }
   m->final_norm = copy_param(ctx, P + "llm.model.model.norm.weight");
   if (ctx->precision == CVK_PREC_BF16) skinny_tiled_weights(ctx, m->head);
   for (int i = 0; i < m->num_layers; ++i) {
@@ -925,7 +948,7 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->vcache = alloc(cache);
   s->ctx_len = (int*)alloc(sizeof(int) * max_batch);
   s->base_len = (int*)alloc(sizeof(int) * max_batch);
-  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT * (int)sizeof(float)));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT3_PAD * (int)sizeof(float)));
   CVK_REQUIRE((NH / NKV) * max_context * sizeof(float) <= 200 * 1024, "session context too long for the decode attention kernel");
   {
     // the limit is per function, not per session: never lower it for a smaller session created later
@@ -951,7 +974,7 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->live = (int*)alloc(sizeof(int));
   s->x = (float*)alloc(sizeof(float) * max_batch * D);
   s->hidden = (float*)alloc(sizeof(float) * max_batch * D);
-  s->logits = (float*)alloc(sizeof(float) * (size_t)max_batch * VOUT);
+  s->logits = (float*)alloc(sizeof(float) * (size_t)max_batch * VOUT3_PAD);   // large enough for either head
   s->xn = alloc(es * max_batch * D);
   s->qkv = alloc(es * max_batch * QKV_N);
   s->att = alloc(es * max_batch * D);
@@ -1034,14 +1057,14 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
   const bool fused = true;
   ctx->tl_seq = 0;
   Mat x(s->x, DT_F32, B, D, D), xn(s->xn, DT_BF16, B, D, D), att(s->att, DT_BF16, B, D, D), ffa(s->ffa, DT_BF16, B, DFF, DFF),
-      logits(s->logits, DT_F32, B, VOUT, VOUT);
+      logits(s->logits, DT_F32, B, m->vout, m->vout);
   {
     Epilogue e;
     e.out = logits;
     conv_gemm_skinny_ex(ctx, st, xn, m->head, e, s->scratch, s->scratch_floats, 0);
   }
   const bool pdl = ctx->pdl != 0;
-  launch_ex(ras_sampler_kernel, dim3(B), dim3(SAMPLER_THREADS), VOUT * sizeof(float), st, pdl, s->logits, VOUT, 1, s->g_uniforms, B, s->g_min,
+  launch_ex(ras_sampler_kernel, dim3(B), dim3(SAMPLER_THREADS), m->vout * sizeof(float), st, pdl, s->logits, m->vout, 1, s->g_uniforms, B, s->g_min,
             s->g_max, s->g_out_ids, s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, (const int*)s->base_len, s->live,
             (const float*)m->speech_emb, s->x, (const int32_t*)nullptr, 0, (const int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr,
             (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next());
@@ -1085,9 +1108,9 @@ static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
   const int B = s->g_B;
   const bool fused = false;
   Mat hid(s->hidden, DT_F32, B, D, D), x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N),
-      att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, VOUT, VOUT);
+      att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, m->vout, m->vout);
   head_logits(ctx, st, m, hid, xn, logits, s);
-  ras_sampler_kernel<<<B, SAMPLER_THREADS, VOUT * sizeof(float), st>>>(s->logits, VOUT, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, m->vout * sizeof(float), st>>>(s->logits, m->vout, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
                                                                        s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
                                                                        m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
                                                                        fused ? (bf16*)s->xn : nullptr, nullptr);
@@ -1210,7 +1233,7 @@ void llm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids, const int32_t
       gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF);
   for (int i = 0; i < n; ++i) {
     const int kind = kinds[i], id = ids[i];
-    CVK_REQUIRE((kind == 0 && id >= 0 && id < 151936) || (kind == 1 && id >= 0 && id < VOUT) || (kind == 2 && id >= 0 && id < 2),
+    CVK_REQUIRE((kind == 0 && id >= 0 && id < 151936) || (kind == 1 && id >= 0 && id < m->vout) || (kind == 2 && id >= 0 && id < 2),
                 "cvk_lm_feed: id out of range");
     feed_embed_kernel<<<1, 256, 0, st>>>(kind, id, B, m->text_emb, m->llm_emb, m->speech_emb, s->x);
     for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
@@ -1228,17 +1251,20 @@ void llm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, cudaStream_t st
   const LlmModel* m = ctx->llm;
   CVK_REQUIRE(m && s->B > 0 && s->fed > 0, "cvk_lm_feed must run before cvk_lm_next_logp");
   const int B = s->B;
-  Mat hid(s->hidden, DT_F32, B, D, D), xn(s->xn, s->kv_dtype, B, D, D), logits(s->logits, DT_F32, B, VOUT, VOUT);
+  Mat hid(s->hidden, DT_F32, B, D, D), xn(s->xn, s->kv_dtype, B, D, D), logits(s->logits, DT_F32, B, m->vout, m->vout);
   head_logits(ctx, st, m, hid, xn, logits, s);
-  logsoftmax_rows_kernel<<<B, SAMPLER_THREADS, 0, st>>>(s->logits, VOUT);
+  logsoftmax_rows_kernel<<<B, SAMPLER_THREADS, 0, st>>>(s->logits, m->vout);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
-  CVK_CHECK_CUDA(cudaMemcpyAsync(logp, s->logits, sizeof(float) * (size_t)B * VOUT, cudaMemcpyDeviceToDevice, st));
+  CVK_CHECK_CUDA(cudaMemcpyAsync(logp, s->logits, sizeof(float) * (size_t)B * m->vout, cudaMemcpyDeviceToDevice, st));
 }
+
+int llm_vocab(cvk_ctx* ctx) { return ctx->llm ? ctx->llm->vout : 0; }
 
 void llm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, cudaStream_t st) {
   CVK_REQUIRE(s->B > 0 && s->logits, "cvk_lm_last_logits: no decode step has run");
-  CVK_CHECK_CUDA(cudaMemcpyAsync(logits, s->logits, sizeof(float) * (size_t)s->B * VOUT, cudaMemcpyDeviceToDevice, st));
+  CVK_REQUIRE(ctx->llm, "llm stage not finalised");
+  CVK_CHECK_CUDA(cudaMemcpyAsync(logits, s->logits, sizeof(float) * (size_t)s->B * ctx->llm->vout, cudaMemcpyDeviceToDevice, st));
 }
 
 // teacher-forced log-probs for every position (parity tests)
@@ -1251,18 +1277,19 @@ void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B,
   zero_mat(ctx, st, x);
   pack_rows(ctx, st, embeds, D, s, x);
   forward_packed(ctx, st, s, x, nullptr);
-  Mat xn = arena_mat(ctx, ctx->act_dtype, s.R, D), logits = arena_mat(ctx, DT_F32, s.R, VOUT, VOUT);
+  Mat xn = arena_mat(ctx, ctx->act_dtype, s.R, D), logits = arena_mat(ctx, DT_F32, s.R, m->vout, m->vout);
   head_logits(ctx, st, m, x, xn, logits);
-  logsoftmax_rows_kernel<<<s.R, SAMPLER_THREADS, 0, st>>>(logits.f32(), VOUT);
+  logsoftmax_rows_kernel<<<s.R, SAMPLER_THREADS, 0, st>>>(logits.f32(), m->vout);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
-  unpack_rows(ctx, st, logits, s, 0, logp, VOUT);
+  unpack_rows(ctx, st, logits, s, 0, logp, m->vout);
 }
 
 void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st) {
   CVK_REQUIRE(V > EOS + 2 && V * sizeof(float) <= 200 * 1024, "vocabulary size out of range");
-  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V * (int)sizeof(float)));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (V > VOUT3_PAD ? V : VOUT3_PAD) * (int)sizeof(float)));   // per function, never lowered
   ras_sampler_kernel<<<B, SAMPLER_THREADS, V * sizeof(float), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                                                                     nullptr, nullptr, nullptr, nullptr, history, hist_ld, hist_count, ignore_eos,
                                                                     out_ids, nullptr, nullptr, nullptr);

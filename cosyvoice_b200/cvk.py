@@ -60,6 +60,7 @@ SIGNATURES = {
     "cvk_lm_decode": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _c_int_p, _vp]),
     "cvk_lm_forward_logp": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
     "cvk_lm_last_logits": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "cvk_lm_vocab": (ctypes.c_int, [_vp]),
     "cvk_lm_begin": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "cvk_lm_feed": (ctypes.c_int, [_vp, _vp, _c_int_p, _c_int_p, ctypes.c_int, _vp]),
     "cvk_lm_next_logp": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
@@ -346,9 +347,13 @@ class Context:
 
     def lm_forward_logp(self, embeds, lens):
         embeds = _f32(embeds, self.device)
-        out = torch.empty(embeds.shape[0], 6564, device=self.device)
+        out = torch.empty(embeds.shape[0], self.lm_vocab(), device=self.device)
         self._check(self.lib.cvk_lm_forward_logp(self.h, _ptr(embeds), _ints(lens), len(lens), _ptr(out), _stream()))
         return out
+
+    def lm_vocab(self):
+        """width of the LM's log-prob rows: 6564 (Qwen2LM) or 6764 (CosyVoice3LM, 3 impossible pad ids)"""
+        return int(self.lib.cvk_lm_vocab(self.h))
 
     def lm_begin(self, sess, B=1):
         self._check(self.lib.cvk_lm_begin(self.h, sess, B, _stream()))
@@ -358,12 +363,12 @@ class Context:
         self._check(self.lib.cvk_lm_feed(self.h, sess, _ints(ids), _ints(kinds), len(ids), _stream()))
 
     def lm_next_logp(self, sess, B=1):
-        out = torch.empty(B, 6564, device=self.device)
+        out = torch.empty(B, self.lm_vocab(), device=self.device)
         self._check(self.lib.cvk_lm_next_logp(self.h, sess, _ptr(out), _stream()))
         return out
 
     def lm_last_logits(self, sess, B):
-        out = torch.empty(B, 6564, device=self.device)
+        out = torch.empty(B, self.lm_vocab(), device=self.device)
         self._check(self.lib.cvk_lm_last_logits(self.h, sess, _ptr(out), _stream()))
         return out
 

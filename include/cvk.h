@@ -167,18 +167,22 @@ int cvk_lm_prefill(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* text, const i
 int cvk_lm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* uniforms, const int32_t* min_len,
                   const int32_t* max_len, int32_t* out_ids, int out_ld, int32_t* out_count, int32_t* done, int* live_host,
                   void* stream);
-/* teacher-forced log-probs for parity tests: embeds [sum L, 896] -> logp [sum L, 6564] */
+/* teacher-forced log-probs for parity tests: embeds [sum L, 896] -> logp [sum L, V], V = cvk_lm_vocab */
 int cvk_lm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens_host, int B, float* logp, void* stream);
+/* Width V of the log-prob / logits rows of the loaded LM: 6564 for Qwen2LM (llm.py:281), 6764 for CosyVoice3LM (llm.py:689: 6761
+ * outputs, padded by 3 ids whose probability is exactly 0); 0 before the "llm" stage is finalised.  The "llm" stage recognises a
+ * CosyVoice3LM state_dict by the absence of llm_embedding.weight. */
+int cvk_lm_vocab(cvk_ctx* ctx);
 /* Text-streaming LM (Qwen2LM.inference_bistream, llm.py:551-661: the caller interleaves 5 text : 15 speech embeddings and forces
  * fill tokens; cli/model.py:113-123 drives it when `text` is a generator).  cvk_lm_begin empties the session (B rows, normally 1);
  * cvk_lm_feed pushes n positions through the KV-cached decode path (llm.py:617-621 forward_one_step): ids_host / kinds_host are
  * HOST arrays, kind 0 = text id (embed_tokens), 1 = speech id (speech_embedding), 2 = llm_embedding row (0 sos, 1 task_id);
- * cvk_lm_next_logp writes log_softmax(llm_decoder(y_pred[:, -1])) (llm.py:622) of the last position to logp [B][6564] (device).
+ * cvk_lm_next_logp writes log_softmax(llm_decoder(y_pred[:, -1])) (llm.py:622) of the last position to logp [B][V] (device, V = cvk_lm_vocab).
  * The draw itself is cvk_ras_sample (llm.py:627 sampling_ids). */
 int cvk_lm_begin(cvk_ctx* ctx, cvk_lm_session* s, int B, void* stream);
 int cvk_lm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids_host, const int32_t* kinds_host, int n, void* stream);
 int cvk_lm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, void* stream);
-/* parity tests: the head logits [B][6564] (llm_decoder output, llm.py:542, before log_softmax) that the most recent decode step
+/* parity tests: the head logits [B][V] (llm_decoder output, llm.py:542, before log_softmax) that the most recent decode step
  * sampled from, copied to `logits` (device) */
 int cvk_lm_last_logits(cvk_ctx* ctx, cvk_lm_session* s, float* logits, void* stream);
 /* utils/common.py:138-167 + llm.py:150-160 as one kernel.  logp [B,V] (modified in place like the reference),
