@@ -2,7 +2,7 @@
 recognises the variant by its state_dict (no llm_embedding, 6761-way bias-free head) and pads the head by 3 impossible ids.
 Golden ids from the reference CosyVoice3LM.inference (tests/golden/lm3_l2*.npz).
 
-Written after the round's GPU budget was spent (see tests/test_hift3_gpu.py): xfail(strict=False) until the first GPU run."""
+Written after the round's GPU budget was spent (see tests/test_zz_hift3_gpu.py): xfail(strict=False) until the first GPU run."""
 import pytest
 import torch
 
