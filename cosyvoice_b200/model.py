@@ -394,11 +394,20 @@ class B200CosyVoice2Model:
             self.llm_end_dict[uuid] = True
             return
 
+        st = {"consumed": 0, "silent": 0}
+
         def progress(out_ids, out_count, live):
             n = int(out_count[0].item())
-            have = len(self.tts_speech_token_dict[uuid])
-            if n > have:
-                self.tts_speech_token_dict[uuid].extend(out_ids[0, have:n].tolist())
+            if n > st["consumed"]:
+                for tok in out_ids[0, st["consumed"]:n].tolist():
+                    if tok in self.silent_tokens:            # cli/model.py:121-127 (empty list for CosyVoice2: never taken)
+                        st["silent"] += 1
+                        if st["silent"] > 5:
+                            continue
+                    else:
+                        st["silent"] = 0
+                    self.tts_speech_token_dict[uuid].append(tok)
+                st["consumed"] = n
         self.lm_generate([text], [prompt_text], [llm_prompt_speech_token], steps_per_sync=8, on_progress=progress)
         self.llm_end_dict[uuid] = True
 

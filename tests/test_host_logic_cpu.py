@@ -78,3 +78,123 @@ def test_llm_job_generator_branch_collects_tokens(golden):
     m.tts_speech_token_dict, m.llm_end_dict = {"u": []}, {"u": False}
     m.llm_job(iter(chunks), ptext, ptok, torch.zeros(0, 192), "u")
     assert m.tts_speech_token_dict["u"] == g["ids"].tolist() and m.llm_end_dict["u"] is True
+
+
+# ------------------------------------------------------------------------------------------------ CosyVoice3Model glue
+class _DummyStream:
+    def synchronize(self):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+
+class _DummyEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+
+class FakeCtx3:
+    """the libcvk calls B200CosyVoice3Model makes (batched LM session API, flow3, hift3) on the CPU oracles"""
+
+    def __init__(self, lsd, fsd, hsd, depth, rand_ini, sine_noise):
+        from oracle import dit, hift_causal
+        self.lsd, self.fsd, self.hsd, self.depth = lsd, fsd, hsd, depth
+        self.rand_ini, self.sine_noise = rand_ini, sine_noise
+        self.dit, self.hc = dit, hift_causal
+        self.lock = threading.Lock()
+        self.flow_calls, self.hift_calls = [], []
+
+    # ---- LM: prefill stores the prompt, decode releases the oracle's ids n_steps at a time
+    def lm_session(self, B, ctx_len):
+        return {"ids": None, "emitted": 0}
+
+    def lm_prefill(self, sess, tt, tl, ss, sl):
+        sess.update(tt=tt.clone(), ss=ss.clone(), ids=None, emitted=0)
+
+    def _run(self, sess, U, min_len, max_len):
+        sd = self.lsd
+        emb = torch.nn.functional.embedding
+        lm_in = torch.cat([sd["speech_embedding.weight"][6561].reshape(1, 1, -1), emb(sess["tt"].long()[None], sd["llm.model.model.embed_tokens.weight"]),
+                           sd["speech_embedding.weight"][6563].reshape(1, 1, -1), emb(sess["ss"].long()[None], sd["speech_embedding.weight"])], 1)
+        out, past = [], None
+        for i in range(max_len):
+            y, past = lm.qwen2_forward(sd, lm_in, past, 2)
+            logp = torch.log_softmax(torch.nn.functional.linear(y[:, -1], sd["llm_decoder.weight"]), -1)[0]
+            top = sampling.ras_sample(logp.numpy(), out, float(U[i, 0, 0]), float(U[i, 0, 1]), ignore_eos=i < min_len)
+            if top >= 6561:
+                break
+            out.append(top)
+            lm_in = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
+        return out
+
+    def lm_decode(self, sess, n_steps, U, min_len, max_len, out_ids, out_count, done, want_live=True):
+        if sess["ids"] is None:
+            sess["ids"] = self._run(sess, U, int(min_len[0]), int(max_len[0]))
+        ids = sess["ids"]
+        sess["emitted"] = min(len(ids), sess["emitted"] + n_steps)
+        n = sess["emitted"]
+        out_ids[0, :n] = torch.tensor(ids[:n], dtype=torch.int32)
+        out_count[0] = n
+        finished = n == len(ids)
+        done[0] = int(finished)
+        return 0 if finished else 1
+
+    # ---- flow / vocoder
+    def flow3_inference(self, toks, tl, pf, pl, emb, n_timesteps=10, streaming=False, finalize=True):
+        P = self._P
+        self.flow_calls.append((int(tl[0]), bool(streaming), bool(finalize)))
+        mel = self.dit.inference(self.fsd, toks[None, P:], toks[None, :P], pf[None], emb, self.depth, n_timesteps, streaming, finalize)
+        return mel[0].t().contiguous(), [mel.shape[2]]
+
+    def hift3_inference(self, mel, lens, finalize=True):
+        self.hift_calls.append((int(lens[0]), bool(finalize)))
+        wav, src = self.hc.inference(self.hsd, mel.t()[None], self.rand_ini, self.sine_noise, finalize)
+        return wav[0], None, src.reshape(-1)
+
+
+def test_cosyvoice3_model_host_glue_matches_reference(golden, monkeypatch):
+    """B200CosyVoice3Model.tts / token2wav / llm_job (cli/model.py:397-450 + inherited :328-394) with the device primitives faked by
+    the oracle: the chunk schedule, the growing mel cache and the speech_offset bookkeeping reproduce the reference's own
+    CosyVoice3Model.tts (tests/golden/stream3_tts.npz), offline and streaming."""
+    from cosyvoice_b200.model3 import B200CosyVoice3Model
+    from oracle import dit, hift_causal as hc, weights
+    monkeypatch.setattr(torch.cuda, "Event", _DummyEvent)
+    g = golden("stream3_tts")
+    text, ptext, ptok, U = cases.lm3_case()
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    pfeat = pfeat[:, :18]
+    _, rand_ini, sine_noise = cases.hift_causal_case(T=400)
+    ctx = FakeCtx3(lm.synth_state_dict3(2), weights.synth_state_dict(dit.flow_param_shapes(2), 1986, dit.SYNTH_GAINS),
+                   weights.synth_state_dict(hc.param_shapes(), 1986, hc.SYNTH_GAINS), 2, rand_ini, sine_noise)
+    ctx._P = ptok.shape[1]
+    for mode, stream in (("offline", False), ("stream", True)):
+        m = object.__new__(B200CosyVoice3Model)
+        m.ctx, m.stream, m.device = ctx, _DummyStream(), torch.device("cpu")
+        m._sessions, m._lm_streams, m.lm_chains = {}, [_DummyStream()], 1
+        m.uniforms_override, m.noise_fn, m.generator = U[:, None, :], None, None
+        m.lock = threading.Lock()
+        m.tts_speech_token_dict, m.llm_end_dict, m.hift_cache_dict = {}, {}, {}
+        m.silent_tokens = [1, 2, 28, 29, 55, 248, 494, 2241, 2242, 2322, 2323]
+        m.token_hop_len, m.token_max_hop_len, m.stream_scale_factor = 25, 100, 2
+        m.min_token_text_ratio, m.max_token_text_ratio, m.n_timesteps = 2.0, 20.0, 10
+        ctx.flow_calls.clear()
+        ctx.hift_calls.clear()
+        chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                 llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                 stream=stream)]
+        assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
+        d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
+        assert d[:, :24000].max() < 2e-3 and d.max() < 1e-2
+        if stream:
+            # two streaming calls on growing prefixes (hop 25 padded to 41, then 50; 3 look-ahead tokens each) + the final
+            # non-streaming call on all 140 tokens (cli/model.py:346-373)
+            assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
+            assert [f for _, f in ctx.hift_calls] == [False, False, True]
+            assert m.token_hop_len == 100
