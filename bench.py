@@ -161,6 +161,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def stage_roofline(stats, inputs, pk, nfe=10):
+    """Per-stage roofline fractions from SURVEY.md §8(d)'s ALGORITHMIC work (not measured traffic) and the CUDA-event stage times
+    of the last timed step: LM decode = bf16 weight stream + KV reads per step over the HBM peak; flow = estimator + encoder dense
+    FLOPs over the bf16 tensor peak; HiFT = 2 * 306.2e6 FLOP per mel frame over the tensor peak."""
+    tokens, frames = stats["tokens"], stats["mel_frames"]
+    B = len(tokens)
+    L0 = [1 + int(i["prompt_text"].shape[1]) + int(i["text"].shape[1]) + 1 + int(i["llm_prompt_speech_token"].shape[1]) for i in inputs]
+    steps = max(tokens) if tokens else 0
+    lm_bytes = 0.0
+    for i in range(steps):
+        live = [b for b in range(B) if tokens[b] > i]
+        lm_bytes += 727.6e6 + sum(12288.0 * (L0[b] + i) for b in live) + len(live) * (896 + 6564) * 4
+    lm_roof_ms = lm_bytes / (pk["hbm_gbs"] * 1e9) * 1e3
+    flow_flop = 0.0
+    for b in range(B):
+        T = frames[b] + int(inputs[b]["prompt_speech_feat"].shape[1])            # total mel frames incl. the prompt
+        flow_flop += 2.0 * (66.09e6 + 57344.0 * T) * T * 2 * nfe                  # estimator, both CFG branches
+        flow_flop += 2.0 * 56.6e6 * (T // 2)                                      # encoder dense part
+    flow_roof_ms = flow_flop / (pk["tflops"] * 1e12) * 1e3
+    hift_flop = sum(2.0 * 306.2e6 * f for f in frames)
+    hift_roof_ms = hift_flop / (pk["tflops"] * 1e12) * 1e3
+    out = {}
+    for name, roof, meas, bound in (("lm", lm_roof_ms, stats["lm_ms"], "hbm"), ("flow", flow_roof_ms, stats["flow_ms"], "tensor"),
+                                    ("hift", hift_roof_ms, stats["hift_ms"], "tensor")):
+        out[name] = {"bound": bound, "roofline_ms": round(roof, 3), "measured_ms": round(meas, 3), "frac": round(roof / meas, 4) if meas > 0 else None}
+    out["lm"]["decode_steps"] = steps
+    return out
+
+
 # ================================================================================================ our arm (GPU)
 def run_ours(args):
     import torch
@@ -303,6 +332,10 @@ def run_ours(args):
                        "stage_ms_last_step": {k: stats[k] for k in ("lm_ms", "flow_ms", "hift_ms")}, "rtf": 1.0 / value},
             "e2e": {"value": e2e_v, "unit": "audio-sec/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_ms_per_step": wall_ms / args.steps}
+    try:                                                # per-stage view the north star asks for; never allowed to break the line
+        line["stage_roofline"] = stage_roofline(stats, inputs, pk)
+    except Exception as e:                              # noqa: BLE001
+        line["stage_roofline"] = {"error": repr(e)}
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
