@@ -150,10 +150,11 @@ __constant__ float c_sin[16];
 // start3[b] + f, columns [0,9) re, [9,18) im, [18,24) zero.
 template <typename TO>
 __global__ void stft16_kernel(const float* __restrict__ src, const int* __restrict__ start0, const int* __restrict__ len0,
-                              const int* __restrict__ start3, TO* __restrict__ out, int ldo) {
+                              const int* __restrict__ start3, TO* __restrict__ out, int ldo, const int* __restrict__ len_sig = nullptr) {
   int b = blockIdx.y;
-  int L = len0[b] * kUpscale;
-  int F = L / 4 + 1;
+  // len_sig (CosyVoice3 streaming call): the source is len_sig frames long, only the first len0*120 + 1 STFT frames are kept
+  int L = (len_sig ? len_sig[b] : len0[b]) * kUpscale;
+  int F = len_sig ? len0[b] * 120 + 1 : L / 4 + 1;
   const float* x = src + (size_t)start0[b] * kUpscale;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
     float xv[16];
@@ -186,7 +187,7 @@ __global__ void stft16_kernel(const float* __restrict__ src, const int* __restri
 // overlap-add / window-envelope, trim 8, clamp +-0.99 (generator.py:533-538, torch.istft center=True).
 // Block: 512 output samples, which need frames f_base-1 .. f_base+129.
 __global__ void istft16_kernel(const float* __restrict__ xp, int ldx, const int* __restrict__ start3, const int* __restrict__ len0,
-                               const int* __restrict__ out_off, float* __restrict__ wav, float limit) {
+                               const int* __restrict__ out_off, float* __restrict__ wav, float limit, int drop_tail = 0) {
   __shared__ float fr[131][17];   // frames f_base-1 .. f_base+129
   int b = blockIdx.y;
   int L = len0[b] * kUpscale;
@@ -224,7 +225,7 @@ __global__ void istft16_kernel(const float* __restrict__ xp, int ldx, const int*
   // output sample n (after trimming 8) lives at padded position p = n + 8; frames f with 4f <= p < 4f + 16
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     int n = f_base * 4 + i;
-    if (n >= L) break;
+    if (n >= L - drop_tail) break;        // drop_tail: samples of the last look-ahead frame are not emitted (generator.py:709-710)
     int p = n + 8;
     int f_hi = p >> 2;
     float acc = 0.f, env = 0.f;
@@ -444,7 +445,7 @@ static void run_resblock(cvk_ctx* ctx, cudaStream_t st, const ResBlockW& rb, con
 
 // mel packed + source packed -> conv_post output [R3, 18] fp32 (ld 24)
 static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat& mel32, const float* src_packed,
-                     const HiftModel* m = nullptr) {
+                     const HiftModel* m = nullptr, const int* d_len_sig = nullptr) {
   if (!m) m = ctx->hift;
   const int adt = ctx->act_dtype;
   const Seqs& s0 = g.s0;
@@ -456,8 +457,8 @@ static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat
     int F = s0.max_len * 120 + 1;
     int bx = ceil_div(F, 128);
     if (bx > 1024) bx = 1024;
-    if (adt == DT_F32) stft16_kernel<float><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.f32(), stft.ld);
-    else stft16_kernel<bf16><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.b16(), stft.ld);
+    if (adt == DT_F32) stft16_kernel<float><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.f32(), stft.ld, d_len_sig);
+    else stft16_kernel<bf16><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.b16(), stft.ld, d_len_sig);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }
@@ -541,11 +542,13 @@ static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat
   return xp;
 }
 
-static void hift_istft(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const int* lens, const Mat& xp, float* wav_dense) {
+// lens: frames per utterance that define the OUTPUT offsets (sum 480*lens samples); drop_tail samples at the end of every utterance
+// are not written (0 except for the CosyVoice3 streaming call)
+static void hift_istft(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const int* lens, const Mat& xp, float* wav_dense, int drop_tail = 0) {
   const Seqs& s0 = g.s0;
   int* ooff = upload_ints(ctx, prefix_offsets(lens, s0.B), st);
   int bx = ceil_div(s0.max_len * kUpscale, 512);
-  istft16_kernel<<<dim3(bx, s0.B), 128, 0, st>>>(xp.f32(), xp.ld, g.lv[2].d_start, s0.d_len, ooff, wav_dense, 0.99f);
+  istft16_kernel<<<dim3(bx, s0.B), 128, 0, st>>>(xp.f32(), xp.ld, g.lv[2].d_start, s0.d_len, ooff, wav_dense, 0.99f, drop_tail);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }
@@ -668,7 +671,6 @@ void hift_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, cons
 // the strided source_downs pad left only.  The f0 predictor runs in float64 on CUDA cores (a few GFLOP per utterance; the
 // reference insists on float64 so that streaming and offline f0 agree), the harmonic source uses nearest-neighbour phase
 // up-sampling and the module's stored uniform noise instead of fresh Gaussian draws.
-// finalize == 0 (streaming chunk with look-ahead frames) is not built yet.
 namespace {
 
 struct F64Conv {
@@ -879,19 +881,35 @@ void hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_nois
   ctx->hift3_extra = x;
 }
 
-// generator.py:714-726 with finalize=True.  mel dense [sum T, 80]; wav [sum 480 T]; f0_out [sum T] / source_out [sum 480 T] optional
+// generator.py:714-726.  mel dense [sum T, 80].  finalize: wav [sum 480 T], f0_out [sum T], source_out [sum 480 T] (optional);
+// streaming call (finalize = 0): wav [sum 480 (T-8)], f0_out [sum (T-3)], source_out [sum 480 (T-3)]
 void hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, int finalize, float* wav, float* f0_out, float* source_out,
                      cudaStream_t st) {
   const HiftModel* m = ctx->hift3;
   Hift3Extra* x = (Hift3Extra*)ctx->hift3_extra;
   CVK_REQUIRE(m && x && x->conv[0].w, "hift3 stage not finalised");
   CVK_REQUIRE(x->noise != nullptr, "cvk_hift3_set_noise has not been called");
-  CVK_REQUIRE(finalize != 0, "cvk_hift3_inference: the streaming (finalize = 0) variant is not built yet");
   ctx->arena.reset();
-  HiftGeom g = hift_geom(ctx, lens, B, st);
-  const Seqs& s0 = g.s0;
-  for (int b = 0; b < B; ++b) CVK_REQUIRE((long long)lens[b] * kUpscale <= x->noise_n, "stored source noise shorter than the utterance");
-  Mat mel32 = pack_mel(ctx, st, s0, mel);
+  // Geometry.  Offline: one geometry of T frames.  Streaming call (generator.py:676-683, 709-710, 722-725; f0_predictor.py:99-100):
+  // the f0 predictor consumes 3 frames of look-ahead (f0 / source have T-3 frames), conv_pre 4 more (the body runs on T-7
+  // frames, the source STFT is cut to its first 120(T-7)+1 frames) and the last 480 samples are dropped (480(T-8) returned).
+  // All geometries share the row starts of the T-frame one, so the look-ahead rows are simply read by the right-looking convs.
+  const int la_f0 = finalize ? 0 : 3, la_pre = finalize ? 0 : 4;
+  HiftGeom g;
+  Seqs sF = make_seqs(ctx, lens, B, 8, 1, 0, st);                         // all frames
+  Seqs s0 = la_f0 ? shrink_seqs(ctx, sF, la_f0, st) : sF;                 // f0 / source frames
+  g.s0 = la_f0 ? shrink_seqs(ctx, sF, la_f0 + la_pre, st) : sF;           // body frames
+  g.lv[0] = scale_seqs(ctx, g.s0, 8, 0, st);
+  g.lv[1] = scale_seqs(ctx, g.s0, 40, 0, st);
+  g.lv[2] = scale_seqs(ctx, g.s0, 120, 1, st);
+  std::vector<int> lens_src(B), lens_out(B);
+  for (int b = 0; b < B; ++b) {
+    CVK_REQUIRE(finalize || lens[b] >= 9, "cvk_hift3_inference: a streaming call needs at least 9 mel frames");
+    lens_src[b] = lens[b] - la_f0;
+    lens_out[b] = finalize ? lens[b] : lens[b] - 8;
+    CVK_REQUIRE((long long)lens_src[b] * kUpscale <= x->noise_n, "stored source noise shorter than the utterance");
+  }
+  Mat mel32 = pack_mel(ctx, st, sF, mel);
   // ---- f0 predictor in float64
   double* a = (double*)ctx->arena.alloc(sizeof(double) * (size_t)s0.R * 512);
   double* bb = (double*)ctx->arena.alloc(sizeof(double) * (size_t)s0.R * 512);
@@ -912,7 +930,7 @@ void hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, int
   f0_head_f64_kernel<<<ceil_div(s0.R, 4), 128, 0, st>>>(cur, x->cls_w, x->cls_b, s0.R, s0.d_row2seq, f0.f32());
   ctx->launches++;
   CVK_LAUNCH_CHECK();
-  int* off = upload_ints(ctx, prefix_offsets(lens, B), st);
+  int* off = upload_ints(ctx, prefix_offsets(lens_src.data(), B), st);
   if (f0_out) {
     gather_f0_kernel<<<dim3(ceil_div(s0.max_len, 128), B), 128, 0, st>>>(f0.f32(), 1, s0.d_start, s0.d_len, off, f0_out);
     ctx->launches++;
@@ -936,6 +954,6 @@ void hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens, int B, int
     CVK_LAUNCH_CHECK();
   }
   // ---- vocoder body (shared with CosyVoice2) + ISTFT
-  Mat xp = hift_body(ctx, st, g, mel32, src, m);
-  hift_istft(ctx, st, g, lens, xp, wav);
+  Mat xp = hift_body(ctx, st, g, mel32, src, m, finalize ? nullptr : s0.d_len);
+  hift_istft(ctx, st, g, lens_out.data(), xp, wav, finalize ? 0 : kUpscale);
 }

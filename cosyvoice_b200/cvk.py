@@ -270,12 +270,15 @@ class Context:
         self._check(self.lib.cvk_hift3_set_noise(self.h, _ptr(rand_ini), _ptr(sine_noise), sine_noise.shape[0], 1))
 
     def hift3_inference(self, mel, lens, finalize=True):
-        """CausalHiFTGenerator.inference: mel [sum T, 80] -> (wav [sum 480 T], f0 [sum T], source [sum 480 T])"""
+        """CausalHiFTGenerator.inference: mel [sum T, 80] -> (wav [sum 480 T], f0 [sum T], source [sum 480 T]); with finalize=False
+        (streaming call) wav [sum 480 (T-8)], f0 [sum T-3], source [sum 480 (T-3)]"""
         mel = _f32(mel, self.device)
-        n = sum(int(l) for l in lens)
-        wav = torch.empty(n * 480, device=self.device)
-        f0 = torch.empty(n, device=self.device)
-        src = torch.empty(n * 480, device=self.device)
+        # streaming call (finalize=False): 3 frames of f0 look-ahead, 4 of conv_pre look-ahead, the last frame's samples dropped
+        n_src = sum(int(l) - (0 if finalize else 3) for l in lens)
+        n_out = sum(int(l) - (0 if finalize else 8) for l in lens)
+        wav = torch.empty(n_out * 480, device=self.device)
+        f0 = torch.empty(n_src, device=self.device)
+        src = torch.empty(n_src * 480, device=self.device)
         self._check(self.lib.cvk_hift3_inference(self.h, _ptr(mel), _ints(lens), len(lens), int(finalize), _ptr(wav), _ptr(f0), _ptr(src),
                                                  _stream()))
         return wav, f0, src

@@ -5,9 +5,8 @@ tokens) and replaces token2wav: the flow is the DiT one (stage "flow3"), the voc
 of the CosyVoice2 mel / source / speech caches with a cross-fade it keeps ALL mel frames produced so far, re-runs the causal vocoder
 over them and emits the samples beyond ``speech_offset``.  This class follows that bookkeeping literally.
 
-Status (end of round 1): the flow stage is parity-green on the GPU; the LM variant and the vocoder's offline call are written but had
-their first GPU run only at the round-end test pass; the vocoder's streaming call (finalize=False) is not built in libcvk yet, so
-``tts(stream=True)`` raises from the library.  The class itself is checked on the CPU against the reference's own
+Status (end of round 1): the flow stage is parity-green on the GPU; the LM variant and the vocoder (offline and streaming call)
+are written but had their first GPU run only at the round-end test pass.  The class itself is checked on the CPU against the reference's own
 CosyVoice3Model.tts with the device primitives faked by the oracle (tests/test_host_logic_cpu.py)."""
 import torch
 

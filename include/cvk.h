@@ -126,8 +126,9 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
  * cvk_hift3_set_noise hands over the module's constructor-time random tensors, which are not state_dict entries
  * (generator.py:223-226): rand_ini [9] (SineGen2.rand_ini) and sine_noise [n][9] (SineGen2.sine_waves, indexed from the start of
  * every utterance).  cvk_hift3_inference = CausalHiFTGenerator.inference (:714-726) for B utterances: mel [sum T, 80] ->
- * wav [sum 480 T]; f0_out [sum T] and source_out [sum 480 T] are optional (NULL).  Only finalize != 0 is built so far; the
- * streaming variant (look-ahead frames consumed, tail dropped, :676-683, :709-710, :722-725) returns CVK_ERR_INVALID. */
+ * wav [sum 480 T]; f0_out [sum T] and source_out [sum 480 T] are optional (NULL).  finalize == 0 is the streaming call
+ * (:676-683, :709-710, :722-725): 3 + 4 mel frames of look-ahead are consumed and the last frame's samples dropped, i.e.
+ * wav [sum 480 (T-8)], f0_out [sum (T-3)], source_out [sum 480 (T-3)]; every utterance needs T >= 9. */
 int cvk_hift3_set_noise(cvk_ctx* ctx, const float* rand_ini, const float* sine_noise, long long n, int on_device);
 int cvk_hift3_inference(cvk_ctx* ctx, const float* mel, const int* lens_host, int B, int finalize, float* wav, float* f0_out,
                         float* source_out, void* stream);

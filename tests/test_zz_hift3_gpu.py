@@ -55,3 +55,16 @@ def test_hift3_ragged_batch_vs_oracle():
         assert maxdiff(src[o * 480:(o + T) * 480], osrc.reshape(-1)) < 3e-3
         assert maxdiff(wav[o * 480:(o + T) * 480], ow.reshape(-1)) < 5e-3
         o += T
+
+
+def test_hift3_streaming_call_golden(golden):
+    """finalize=False (generator.py:676-683, 709-710, 722-725): look-ahead frames consumed, tail dropped"""
+    g = golden("hift_causal")
+    mel, rand_ini, sine_noise = cases.hift_causal_case()
+    c = model("fp32")
+    c.hift3_set_noise(rand_ini, sine_noise[0])
+    wav, f0, src = c.hift3_inference(mel[0].t().contiguous(), [mel.shape[2]], finalize=False)
+    assert wav.numel() == g["wav_chunk"].shape[1] == (24 - 8) * 480
+    np.testing.assert_allclose(f0.cpu().numpy(), g["f0_chunk"][0], rtol=1e-5, atol=1e-3)
+    assert maxdiff(src, torch.from_numpy(g["source_chunk"]).reshape(-1)) < 2e-3
+    assert maxdiff(wav, torch.from_numpy(g["wav_chunk"]).reshape(-1)) < 2e-3
