@@ -198,3 +198,90 @@ def test_cosyvoice3_model_host_glue_matches_reference(golden, monkeypatch):
             assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
             assert [f for _, f in ctx.hift_calls] == [False, False, True]
             assert m.token_hop_len == 100
+
+
+# ------------------------------------------------------------------------------------------------ CosyVoice2Model glue
+class FakeCtx2(FakeCtx3):
+    """libcvk calls of B200CosyVoice2Model (Qwen2LM session API, flow_inference, hift_inference with cache_source) on the oracles"""
+
+    def __init__(self, lsd, fsd, hsd, fcfg):
+        self.lsd, self.fsd, self.hsd, self.fcfg = lsd, fsd, hsd, fcfg
+        self.lock = threading.Lock()
+        self.flow_calls, self.hift_calls = [], []
+
+    def _run(self, sess, U, min_len, max_len):
+        sd = self.lsd
+        emb = torch.nn.functional.embedding
+        lm_in = torch.cat([sd["llm_embedding.weight"][0].reshape(1, 1, -1), emb(sess["tt"].long()[None], sd["llm.model.model.embed_tokens.weight"]),
+                           sd["llm_embedding.weight"][1].reshape(1, 1, -1), emb(sess["ss"].long()[None], sd["speech_embedding.weight"])], 1)
+        out, past = [], None
+        for i in range(max_len):
+            y, past = lm.qwen2_forward(sd, lm_in, past, 2)
+            top = sampling.ras_sample(lm.logprobs(sd, y[:, -1])[0].numpy(), out, float(U[i, 0, 0]), float(U[i, 0, 1]), ignore_eos=i < min_len)
+            if top in lm.STOP_IDS:
+                break
+            out.append(top)
+            lm_in = sd["speech_embedding.weight"][top].reshape(1, 1, -1)
+        return out
+
+    def flow_inference(self, toks, tl, pf, pl, emb, n_timesteps=10, streaming=False, finalize=True):
+        from oracle import flow
+        P = self._P
+        self.flow_calls.append((int(tl[0]), bool(streaming), bool(finalize)))
+        mel = flow.inference(self.fsd, toks[None, P:], toks[None, :P], pf[None], emb, self.fcfg, n_timesteps, streaming, finalize)
+        return mel[0].t().contiguous(), [mel.shape[2]]
+
+    def hift_inference(self, mel, lens, noise, cache_source=None, cache_lens=None):
+        from oracle import hift
+        self.hift_calls.append((int(lens[0]), 0 if cache_source is None else int(cache_source.numel())))
+        cs = cache_source.reshape(1, 1, -1) if cache_source is not None else None
+        wav, src = hift.inference(self.hsd, mel.t()[None], noise[None], None, cs)
+        return wav[0], src.reshape(-1)
+
+
+def test_cosyvoice2_model_host_glue_matches_reference(golden, monkeypatch):
+    """B200CosyVoice2Model.tts / token2wav / llm_job (cli/model.py:245-394) with the device primitives faked by the oracle:
+    chunk schedule, mel / source / speech caches and the hamming cross-fade reproduce the reference's own CosyVoice2Model.tts
+    (tests/golden/stream_tts.npz), offline and streaming.  (The same class over the real library: tests/test_model_gpu.py.)"""
+    from cosyvoice_b200.model import B200CosyVoice2Model
+    from oracle import flow, hift, weights
+    from oracle.make_golden import stream_noise
+    monkeypatch.setattr(torch.cuda, "Event", _DummyEvent)
+    g = golden("stream_tts")
+    text, ptext, ptok, U = cases.lm_case()
+    _, _, pfeat, emb = cases.flow_case(P=9)
+    pfeat = pfeat[:, :18]
+    fcfg = flow.FlowCfg(enc_blocks=2, enc_up_blocks=1, num_mid_blocks=2, n_blocks=2)
+    ctx = FakeCtx2(lm.synth_state_dict(2), weights.synth_state_dict(flow.param_shapes(fcfg), 1986, flow.SYNTH_GAINS),
+                   weights.synth_state_dict(hift.param_shapes(), 1986, hift.SYNTH_GAINS), fcfg)
+    ctx._P = ptok.shape[1]
+    for mode, stream in (("offline", False), ("stream", True)):
+        k = {"k": 0}
+
+        def noise_fn(n):
+            z = stream_noise(k["k"], n)
+            k["k"] += 1
+            return z
+        m = object.__new__(B200CosyVoice2Model)
+        m.ctx, m.stream, m.device = ctx, _DummyStream(), torch.device("cpu")
+        m._sessions, m._lm_streams, m.lm_chains = {}, [_DummyStream()], 1
+        m.uniforms_override, m.noise_fn, m.generator = U[:, None, :], noise_fn, None
+        m.lock = threading.Lock()
+        m.tts_speech_token_dict, m.llm_end_dict, m.hift_cache_dict = {}, {}, {}
+        m.silent_tokens = []
+        m.token_hop_len, m.token_max_hop_len, m.stream_scale_factor = 25, 100, 2
+        m.mel_cache_len, m.source_cache_len = 8, 8 * 480
+        m._window = torch.from_numpy(np.hamming(2 * 8 * 480)).float()
+        m.min_token_text_ratio, m.max_token_text_ratio, m.n_timesteps = 2.0, 20.0, 10
+        ctx.flow_calls.clear()
+        ctx.hift_calls.clear()
+        chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                 llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                 stream=stream)]
+        assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
+        d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
+        assert d[:, :24000].max() < 5e-3 and d.max() < 2e-2, (d[:, :24000].max(), d.max())
+        if stream:
+            assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
+            # every vocoder call after the first re-uses 8 cached mel frames and 3840 cached source samples (cli/model.py:305-318)
+            assert [c[1] for c in ctx.hift_calls] == [0, 3840, 3840]
