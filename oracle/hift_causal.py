@@ -127,7 +127,7 @@ def sine_source(sd, f0, rand_ini, sine_noise):
     return merged.transpose(1, 2)
 
 
-def decode(sd, mel, s, finalize=True):
+def decode(sd, mel, s, finalize=True, return_pre_istft=False):
     """generator.py:674-712.  finalize: mel [B,80,T], s [B,1,480T] -> wav [B,480T].  Streaming (finalize=False): the last
     LOOK_RIGHT mel frames are look-ahead for conv_pre only, the source STFT is cut accordingly and the last 480 samples of the
     waveform are dropped."""
@@ -162,6 +162,8 @@ def decode(sd, mel, s, finalize=True):
         x = xs / 3
     x = F.leaky_relu(x)
     x = causal_conv(x, _w(sd, "conv_post"), sd["conv_post.bias"])
+    if return_pre_istft:
+        return x
     mag = torch.exp(x[:, :N_FFT // 2 + 1])
     phase = torch.sin(x[:, N_FFT // 2 + 1:])
     y = istft16(mag, phase)
