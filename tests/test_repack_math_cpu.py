@@ -87,7 +87,7 @@ def conv_gemm_fast(A, W, shift0, dil=1, bias=None):
     return out if bias is None else out + bias
 
 
-def test_causal_vocoder_body_as_conv_gemms():
+def _causal_body(finalize):
     """The CosyVoice3 vocoder body exactly as cosyvoice_b200/csrc/hift.cu wires it (conv_pre looking right, three polyphase
     nearest-up-sampling conv-GEMMs whose [R, u*C] output is reinterpreted as [u*R, C], the reflected front row at the last level,
     strided source_downs on the [R/s, s*24] STFT view with the front-row offset, left-shifted dilated ResBlock convs, causal
@@ -96,11 +96,14 @@ def test_causal_vocoder_body_as_conv_gemms():
     sd32 = weights.synth_state_dict(hc.param_shapes(), 1986, hc.SYNTH_GAINS)
     sd = {k: v.double() for k, v in sd32.items()}
     g = torch.Generator().manual_seed(3)
-    T = 5
+    # streaming call: the vocoder receives the mel without the 3 f0 look-ahead frames (generator.py:725); conv_pre then uses 4 more
+    # frames as look-ahead, so the body runs on n_body = T - 4 rows while the source (and its STFT, before the cut) covers T rows
+    T = 5 if finalize else 10
     mel32 = torch.randn(1, 80, T, generator=g) * 2 - 5
     src32 = torch.tanh(torch.randn(1, 1, T * 480, generator=g))
     mel, src = mel32.double(), src32.double()
-    ref = hc.decode(sd32, mel32, src32, True, return_pre_istft=True)[0].t().double()        # [120T+1, 18], oracle in fp32
+    n_body = T if finalize else T - 4
+    ref = hc.decode(sd32, mel32, src32, finalize, return_pre_istft=True)[0].t().double()    # [120 n_body + 1, 18], oracle in fp32
 
     def wn(prefix):                                                                          # effective weight [out, in, k]
         return H._w(sd, prefix)
@@ -111,8 +114,10 @@ def test_causal_vocoder_body_as_conv_gemms():
     lrelu = torch.nn.functional.leaky_relu
     # STFT of the source, frames x 18, stored at level-3 rows f (front row included)
     re, im = H.stft16(src.squeeze(1).float())
-    stft = torch.cat([re, im], 1)[0].t().double()                                            # [120T+1, 18]
+    stft = torch.cat([re, im], 1)[0].t().double()[:120 * n_body + 1]                          # frames kept after the cut (generator.py:681-682)
+    # conv_pre over ALL rows (it looks 4 rows to the right, into the look-ahead rows of the same matrix)
     x = lrelu(conv_gemm_fast(mel[0].t(), as_gemm(wn("conv_pre")), 0, bias=sd["conv_pre.bias"]), 0.1)
+    x = x[:n_body]                       # later rows are masked to zero on the device and never read by the causal layers below
     ups, upk, ch = (8, 5, 3), (16, 11, 7), (512, 256, 128, 64)
     strides = (15, 3, 1)
     for i in range(3):
@@ -157,6 +162,16 @@ def test_causal_vocoder_body_as_conv_gemms():
         xu = xu + resblock(f"source_resblocks.{i}", si, (7, 7, 11)[i])
         xs = sum(resblock(f"resblocks.{i * 3 + j}", xu, kk) for j, kk in enumerate((3, 7, 11)))
         x = lrelu(xs / 3, 0.1 if i < 2 else 0.01)
-    out = conv_gemm_fast(x, as_gemm(wn("conv_post")), -6, bias=sd["conv_post.bias"])
-    assert out.shape == ref.shape
+    out = conv_gemm_fast(x, as_gemm(wn("conv_post")), -6, bias=sd["conv_post.bias"])[:ref.shape[0]]
     assert (out - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item()), ((out - ref).abs().max(), ref.abs().max())
+
+
+def test_causal_vocoder_body_as_conv_gemms():
+    _causal_body(True)
+
+
+def test_causal_vocoder_body_streaming_call():
+    """finalize=False: the body rows are a prefix of the mel rows (shared row starts), conv_pre reads its 4 look-ahead rows from the
+    same matrix, the STFT of the full source is cut to 120 n_body + 1 frames - everything downstream is causal, so the masked tail
+    rows never reach a kept output"""
+    _causal_body(False)
