@@ -285,3 +285,17 @@ def test_cosyvoice2_model_host_glue_matches_reference(golden, monkeypatch):
             assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
             # every vocoder call after the first re-uses 8 cached mel frames and 3840 cached source samples (cli/model.py:305-318)
             assert [c[1] for c in ctx.hift_calls] == [0, 3840, 3840]
+
+
+def test_padded_cosyvoice3_head_is_sampling_neutral():
+    """The CosyVoice3LM stage pads the 6761-way head to 6764 outputs whose bias is -1e30 (csrc/llm.cu): after the log-softmax the
+    pad ids have probability exactly 0, every real log-prob is bit-identical, and repetition-aware sampling draws the same ids."""
+    g = np.random.default_rng(5)
+    for temp in (0.7, 3.0, 8.0):
+        logits = (g.standard_normal(6761) * temp).astype(np.float32)
+        padded = np.concatenate([logits, np.full(3, -1.0e30, dtype=np.float32)])
+        lp, lpp = sampling.log_softmax_f32(logits), sampling.log_softmax_f32(padded)
+        assert np.array_equal(lp, lpp[:6761]) and np.all(np.exp(lpp[6761:].astype(np.float64)) == 0.0)
+        hist = [int(np.argmax(logits))] * 3
+        for u1, u2, ign in ((0.05, 0.9, True), (0.5, 0.5, False), (0.79, 0.01, True), (0.999, 0.999, False)):
+            assert sampling.ras_sample(lp, hist, u1, u2, ign) == sampling.ras_sample(lpp, hist, u1, u2, ign)
