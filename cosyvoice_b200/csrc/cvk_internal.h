@@ -186,6 +186,8 @@ struct cvk_ctx {
   std::vector<cudaEvent_t> event_pool;
   int pdl = 1;                              // LM decode chain: programmatic dependent launch (next kernel's prologue + weight prefetch overlap this kernel)
   int lm_fused = 1;                         // LM decode: fused finish+rmsnorm / rope+attention / SwiGLU-epilogue kernels
+  int lm_mega = 1;                          // LM decode: all layers of a step in one persistent cooperative kernel (llm_mega.cu)
+  int mega_coop = 1;                        // ... launched with the cooperative attribute (co-residency guaranteed by the driver)
   int use_skinny = 1;                       // LM decode GEMMs on the weight-streaming split-K kernel
   int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)
   int use_graph = 1;                        // LM decode step replayed as a CUDA graph

@@ -10,67 +10,10 @@
 // Batched over B independent rows (the reference decodes one utterance at a time).  One decode step for all rows is
 // captured into a CUDA graph; the sampler advances per-row counters on the device, so the host only polls the
 // number of live rows every few steps - no .item() style host round trip per token (common.py:155-161 has several).
-#include "common.cuh"
+#include "llm_decode_attn.cuh"
 #include <math.h>
 
-namespace {
-constexpr int D = 896, NH = 14, NKV = 2, HD = 64, DFF = 4864, VOUT = 6564, EOS = 6561;
-constexpr int VOUT3 = 6761, VOUT3_PAD = 6764;   // CosyVoice3LM head (llm.py:689), padded to a 16-byte row pitch
-constexpr int QKV_N = NH * HD + 2 * NKV * HD;   // 1152
-constexpr float ROPE_THETA = 1.0e6f, RMS_EPS = 1e-6f;
-constexpr int SAMPLER_THREADS = 256, TOPK = 25, WIN = 10;
-
-struct LayerW {
-  float *ln1, *ln2;
-  ConvW qkv, o, gate_up, down;
-  ConvW gate_up_il;   // rows interleaved (2i = gate_i, 2i+1 = up_i) for the SwiGLU epilogue of the decode GEMM
-};
-}  // namespace
-
-struct LlmModel {
-  int num_layers = 24;
-  int vout = VOUT;               // width of the head / logits rows: 6564 (Qwen2LM) or 6764 (CosyVoice3LM: 6761 + 3 impossible pad ids)
-  std::vector<LayerW> layers;
-  float* final_norm = nullptr;
-  float* text_emb = nullptr;     // [151936][896]
-  float* llm_emb = nullptr;      // [2][896]  sos, task_id
-  float* speech_emb = nullptr;   // [6564][896]
-  ConvW head;                    // llm_decoder 896 -> 6564
-  float inv_freq[HD / 2];
-  float* d_inv_freq = nullptr;
-};
-
-struct cvk_lm_session {
-  int max_batch = 0, max_ctx = 0, B = 0;
-  int kv_dtype = DT_F32;
-  void* kcache = nullptr;   // [layers][max_batch][NKV][max_ctx][HD]
-  void* vcache = nullptr;
-  int* ctx_len = nullptr;   // [max_batch] cache position of the token currently being fed
-  int* base_len = nullptr;  // [max_batch] prompt length L0
-  bool fresh = false;
-  int fed = 0;              // positions pushed by cvk_lm_feed since cvk_lm_begin
-  int64_t graph_kernels = 0;
-  int* count = nullptr;     // [max_batch] tokens generated so far
-  int* done = nullptr;      // [max_batch]
-  int* live = nullptr;      // [1]
-  float* x = nullptr;       // [max_batch][896] input embedding of the current step (fp32 residual stream)
-  float* hidden = nullptr;  // [max_batch][896] final-normed hidden of the last position
-  float* logits = nullptr;  // [max_batch][VOUT]
-  void* xn = nullptr;       // act [max_batch][896]
-  void* qkv = nullptr;      // act [max_batch][1152]
-  void* att = nullptr;      // act [max_batch][896]
-  void* gu = nullptr;       // act [max_batch][2*4864]
-  void* ffa = nullptr;      // act [max_batch][4864]
-  cudaGraphExec_t graph = nullptr;
-  // arguments baked into the captured graph
-  const float* g_uniforms = nullptr;
-  const int32_t *g_min = nullptr, *g_max = nullptr;
-  int32_t *g_out_ids = nullptr, *g_out_count = nullptr, *g_done = nullptr;
-  int g_out_ld = 0, g_B = 0, g_pdl = -1;
-  float* scratch = nullptr;      // split-K partial sums of the weight-streaming GEMM
-  size_t scratch_floats = 0;
-  std::vector<void*> owned;
-};
+using namespace lm;
 
 namespace {
 
@@ -278,176 +221,26 @@ __global__ void __launch_bounds__(D) finish_rms_kernel(const float* __restrict__
   tl_stamp(tl, 2);
 }
 
-// qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head).
-// The attention itself is flash-decoding on warp-level tensor-core MMAs (m16n8k16, bf16 in / fp32 accumulate): the 7 query heads
-// of the group are the M rows of the tile (7 of 16 used - tcgen05's M >= 64 would waste 9/10 of the tile and need TMEM), each of
-// the 16 warps walks its own 16-key blocks with an online softmax held in registers, K and V fragments come straight from the
-// cache with 4-byte loads (V's key pairs are formed with byte permutes, the output dims of a 16-dim block are assigned to the
-// two n-tiles as evens / odds so that each lane ends up with 4 consecutive dims), P never leaves registers (the QK^T accumulator
-// layout is the A-operand layout of the P V MMA), and the warps' partial (max, sum, O) are merged through shared memory.
+// qkv split-K reduction + bias + RoPE + KV-cache append + GQA decode attention; one CTA per (row, kv head): see
+// llm_decode_attn.cuh (the same unit runs inside the persistent decode kernel, llm_mega.cu).
 // The CUDA-core version this replaces spent 6.8 + 4.7 us in QK^T / P V at 215 keys (bf16->fp32 conversion + FMA per element, per
 // head), a third of the whole decode step.
 constexpr int AF_WARPS = 16;
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h2);
-}
-__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {   // A rows 8..15 are zero
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-}
 __global__ void __launch_bounds__(32 * AF_WARPS)
 attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int splits, int rows, const float* __restrict__ bias,
                   bf16* __restrict__ kc, bf16* __restrict__ vc, const int* __restrict__ ctx_len, int max_ctx,
-                  const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo, long long* __restrict__ tl, long long* __restrict__ ph) {
+                  const float* __restrict__ inv_freq, bf16* __restrict__ out, int ldo, long long* __restrict__ tl) {
   extern __shared__ float sm_all[];            // [G+2][64] staging | [WARPS][8][2] max/sum | [WARPS][G][64] partial O
-  constexpr int G = NH / NKV;
   const int b = blockIdx.x, kvh = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* stage = sm_all;
-  float* ml = stage + (G + 2) * HD;
-  float* po = ml + AF_WARPS * 8 * 2;
   pdl_trigger();
   tl_stamp(tl, 0);
   pdl_wait();
   tl_stamp(tl, 1);
-#define AF_PHASE(i) do { if (ph && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); ph[1000 + (i)] = t_; } } while (0)
-  AF_PHASE(0);
-  const int pos = ctx_len[b];
-  for (int e = threadIdx.x; e < (G + 2) * HD; e += blockDim.x) {
-    const int vec = e / HD, d = e % HD;
-    const int col = vec < G ? (kvh * G + vec) * HD + d : (vec == G ? NH * HD + kvh * HD + d : NH * HD + NKV * HD + kvh * HD + d);
-    float acc = bias[col];
-    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * rows + b) * QKV_N + col];
-    stage[e] = acc;
-  }
-  __syncthreads();
-  AF_PHASE(1);
-  for (int e = threadIdx.x; e < (G + 1) * (HD / 2); e += blockDim.x) {     // rotate the G query heads and k
-    const int vec = e / (HD / 2), i = e % (HD / 2);
-    const float fr = (float)pos * inv_freq[i];
-    const float c = cosf(fr), sn = sinf(fr);
-    float* p = stage + vec * HD;
-    const float x1 = p[i], x2 = p[i + HD / 2];
-    p[i] = x1 * c - x2 * sn;
-    p[i + HD / 2] = x2 * c + x1 * sn;
-  }
-  __syncthreads();
-  AF_PHASE(2);
   bf16* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
   bf16* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
-  if (pos < max_ctx && threadIdx.x < 2 * HD) {
-    const int d = threadIdx.x % HD;
-    if (threadIdx.x < HD) kb[(size_t)pos * HD + d] = __float2bfloat16_rn(stage[G * HD + d]);
-    else vb[(size_t)pos * HD + d] = __float2bfloat16_rn(stage[(G + 1) * HD + d]);
-  }
-  __syncthreads();
-  AF_PHASE(3);
-  const int L = min(pos + 1, max_ctx);
-  const int g = lane >> 2, tid = lane & 3;       // MMA fragment coordinates: row / column group
-  uint32_t qa[4][2];                             // Q as the A operand: [k step][dims tid*2.. | +8]; row g = query head g (row 7 unused)
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-    for (int hv = 0; hv < 2; ++hv) {
-      const int d = kk * 16 + hv * 8 + tid * 2;
-      qa[kk][hv] = g < G ? pack_bf16x2(__bfloat162float(__float2bfloat16_rn(stage[g * HD + d])) * 0.125f,
-                                       __bfloat162float(__float2bfloat16_rn(stage[g * HD + d + 1])) * 0.125f)
-                         : 0u;
-    }
-  float o[4][2][4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[q][t][e] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  for (int j0 = warp * 16; j0 < L; j0 += AF_WARPS * 16) {
-    // every load of the block is issued before the first use: one memory round trip per 16 keys.  Rows past the end are
-    // clamped to the last valid row (finite data), their probabilities are forced to zero below.
-    uint32_t kf[2][4][2], vw[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (size_t)min(j0 + nt * 8 + g, L - 1) * HD);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        kf[nt][kk][0] = kr[kk * 8 + tid];
-        kf[nt][kk][1] = kr[kk * 8 + 4 + tid];
-      }
-    }
-    {
-      const uint32_t* v0 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + tid * 2, L - 1) * HD);
-      const uint32_t* v1 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + tid * 2 + 1, L - 1) * HD);
-      const uint32_t* v2 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 8 + tid * 2, L - 1) * HD);
-      const uint32_t* v3 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 9 + tid * 2, L - 1) * HD);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        vw[q][0] = v0[q * 8 + g];
-        vw[q][1] = v1[q * 8 + g];
-        vw[q][2] = v2[q * 8 + g];
-        vw[q][3] = v3[q * 8 + g];
-      }
-    }
-    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      mma_16816(s0, qa[kk][0], qa[kk][1], kf[0][kk][0], kf[0][kk][1]);
-      mma_16816(s1, qa[kk][0], qa[kk][1], kf[1][kk][0], kf[1][kk][1]);
-    }
-    // this lane: head g, keys j0 + 2 tid + {0,1} (s0) and j0 + 8 + 2 tid + {0,1} (s1)
-    const int ka = j0 + tid * 2;
-    const bool va0 = ka < L, va1 = ka + 1 < L, vb0 = ka + 8 < L, vb1 = ka + 9 < L;
-    float mx = fmaxf(fmaxf(va0 ? s0[0] : -INFINITY, va1 ? s0[1] : -INFINITY), fmaxf(vb0 ? s1[0] : -INFINITY, vb1 ? s1[1] : -INFINITY));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    const float m_new = fmaxf(m_run, mx);          // finite: key j0 itself is valid
-    const float corr = __expf(m_run - m_new);      // exp(-inf) = 0 on the first block
-    const float p0 = va0 ? __expf(s0[0] - m_new) : 0.f, p1 = va1 ? __expf(s0[1] - m_new) : 0.f;
-    const float p2 = vb0 ? __expf(s1[0] - m_new) : 0.f, p3 = vb1 ? __expf(s1[1] - m_new) : 0.f;
-    l_run = l_run * corr + ((p0 + p1) + (p2 + p3));
-    m_run = m_new;
-    const uint32_t pa0 = pack_bf16x2(p0, p1), pa2 = pack_bf16x2(p2, p3);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      o[q][0][0] *= corr; o[q][0][1] *= corr;
-      o[q][1][0] *= corr; o[q][1][1] *= corr;
-      // n-tile 0: even dims of the 16-dim block, n-tile 1: odd dims (low / high halves of the loaded words)
-      mma_16816(o[q][0], pa0, pa2, __byte_perm(vw[q][0], vw[q][1], 0x5410), __byte_perm(vw[q][2], vw[q][3], 0x5410));
-      mma_16816(o[q][1], pa0, pa2, __byte_perm(vw[q][0], vw[q][1], 0x7632), __byte_perm(vw[q][2], vw[q][3], 0x7632));
-    }
-  }
-  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-  if (g < G) {
-    if (tid == 0) {
-      ml[(warp * 8 + g) * 2] = m_run;
-      ml[(warp * 8 + g) * 2 + 1] = l_run;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)     // dims 16 q + 4 tid .. + 3
-      *reinterpret_cast<float4*>(po + ((size_t)warp * G + g) * HD + q * 16 + tid * 4) = make_float4(o[q][0][0], o[q][1][0], o[q][0][1], o[q][1][1]);
-  }
-  __syncthreads();
-  AF_PHASE(5);
-  for (int e = threadIdx.x; e < G * HD; e += blockDim.x) {
-    const int hq = e / HD, d = e % HD;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w2 = 0; w2 < AF_WARPS; ++w2) M = fmaxf(M, ml[(w2 * 8 + hq) * 2]);
-    float num = 0.f, den = 0.f;
-#pragma unroll
-    for (int w2 = 0; w2 < AF_WARPS; ++w2) {
-      const float wgt = __expf(ml[(w2 * 8 + hq) * 2] - M);    // warps without keys: exp(-inf) = 0
-      den = fmaf(wgt, ml[(w2 * 8 + hq) * 2 + 1], den);
-      num = fmaf(wgt, po[((size_t)w2 * G + hq) * HD + d], num);
-    }
-    out[(size_t)b * ldo + (kvh * G + hq) * HD + d] = __float2bfloat16_rn(num / den);
-  }
-  AF_PHASE(6);
+  decode_attn_unit<AF_WARPS, 0>(sm_all, threadIdx.x, partial, splits, rows, b, kvh, bias, kb, vb, ctx_len[b], max_ctx, inv_freq,
+                                out + (size_t)b * ldo);
   tl_stamp(tl, 2);
-#undef AF_PHASE
 }
 
 __global__ void interleave_rows_kernel(const float* __restrict__ gu /*[2*F][K]: gate rows then up rows*/, float* __restrict__ out, int F, int K) {
@@ -927,6 +720,7 @@ void llm_build(cvk_ctx* ctx, const int* cfg, int ncfg) {
   CVK_CHECK_CUDA(cudaMemcpy(m->d_inv_freq, m->inv_freq, sizeof(m->inv_freq), cudaMemcpyHostToDevice));
   CVK_CHECK_CUDA(cudaDeviceSynchronize());
   ctx->llm = m;
+  if (ctx->precision == CVK_PREC_BF16) lm_mega_build(ctx, m);
 }
 
 cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context) {
@@ -982,6 +776,7 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->ffa = alloc(es * (size_t)max_batch * DFF);
   s->scratch_floats = skinny_scratch_floats(max_batch, 2 * DFF);
   s->scratch = (float*)alloc(s->scratch_floats * sizeof(float));
+  lm_mega_session_init(ctx, s);
   return s;
 }
 
@@ -990,6 +785,7 @@ void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s) {
   cudaDeviceSynchronize();
   if (s->graph) cudaGraphExecDestroy(s->graph);
   for (void* p : s->owned) cudaFree(p);
+  lm_mega_session_free(s);
   delete s;
 }
 
@@ -1070,6 +866,10 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
             (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next());
   ctx->launches++;
   CVK_LAUNCH_CHECK();
+  if (lm_mega_usable(ctx, s, B)) {     // all layers in one persistent cooperative kernel (llm_mega.cu)
+    lm_mega_layers(ctx, st, s, B);
+    return;
+  }
   const size_t attn_smem = ((NH / NKV + 2) * HD + AF_WARPS * 8 * 2 + AF_WARPS * (NH / NKV) * HD) * sizeof(float);
   for (int li = 0; li < m->num_layers; ++li) {
     const LayerW& w = m->layers[li];
@@ -1078,7 +878,7 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
     Epilogue none;
     int sp = conv_gemm_skinny_ex(ctx, st, xn, w.qkv, none, s->scratch, s->scratch_floats, 1);
     launch_ex(attn_fused_kernel, dim3(B, NKV), dim3(32 * AF_WARPS), attn_smem, st, pdl, (const float*)s->scratch, sp, B,
-              (const float*)w.qkv.bias, kc, vc, (const int*)s->ctx_len, s->max_ctx, (const float*)m->d_inv_freq, att.b16(), att.ld, ctx->tl_next(), (long long*)ctx->dbg);
+              (const float*)w.qkv.bias, kc, vc, (const int*)s->ctx_len, s->max_ctx, (const float*)m->d_inv_freq, att.b16(), att.ld, ctx->tl_next());
     ctx->launches++;
     CVK_LAUNCH_CHECK();
     sp = conv_gemm_skinny_ex(ctx, st, att, w.o, none, s->scratch, s->scratch_floats, 1);
@@ -1132,14 +932,15 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     s->fresh = false;
   }
   bool same = s->g_out_count == out_count && s->g_done == done && s->g_out_ids == out_ids && s->g_uniforms == uniforms &&
-              s->g_min == min_len && s->g_max == max_len && s->g_out_ld == out_ld && s->g_B == B && s->g_pdl == ctx->pdl;
+              s->g_min == min_len && s->g_max == max_len && s->g_out_ld == out_ld && s->g_B == B && s->g_pdl == ctx->pdl &&
+              s->g_mega == ctx->lm_mega;
   if (!same) {
     if (s->graph) {
       cudaGraphExecDestroy(s->graph);
       s->graph = nullptr;
     }
     s->g_out_count = out_count; s->g_done = done; s->g_out_ids = out_ids; s->g_uniforms = uniforms; s->g_min = min_len; s->g_max = max_len;
-    s->g_out_ld = out_ld; s->g_B = B; s->g_pdl = ctx->pdl;
+    s->g_out_ld = out_ld; s->g_B = B; s->g_pdl = ctx->pdl; s->g_mega = ctx->lm_mega;
   }
   s->g_B = B;
   if (was_fresh && lm_fused_path(ctx, s)) {

@@ -31,9 +31,7 @@ def tm(x):          # [B,C,T] -> [B*T, C]
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("tag,depth", [
     ("small", 2),
-    # depth 2 ran green on B200 before the round's GPU budget ended; the 22-block case (same kernels, 1.3 GB of synthetic weights)
-    # runs for the first time at the round-end test pass
-    pytest.param("full", 22, marks=pytest.mark.xfail(strict=False, reason="first GPU run of the depth-22 case happens at round end")),
+    ("full", 22),
 ])
 def test_dit_estimator_golden(precision, tag, depth, golden):
     g = golden("dit_" + tag)

@@ -1,10 +1,8 @@
 """GPU: CosyVoice3 causal vocoder through the C ABI against the committed outputs of the reference
 CausalHiFTGenerator (tests/golden/hift_causal.npz, made by oracle/make_golden.py::gen_hift_causal).
 
-These kernels were written after the round's GPU budget was spent: the file compiles and the CPU oracle is pinned, but the first
-run on a B200 happens at the round-end test pass.  They are therefore marked xfail(strict=False): a pass is reported as XPASS,
-a failure does not turn the suite red; round 2 starts by removing the marker.  The file name sorts last so that even a
-CUDA fault in an unvalidated kernel cannot disturb the validated tests that share the process."""
+First GPU run: round-1 driver test pass (green, GPUTEST_r01.json); the first-run xfail marker was removed in round 2.  The
+file name still sorts last so that a CUDA fault here cannot disturb the tests that share the process."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +10,7 @@ import torch
 from gpu_util import ctx, maxdiff
 from oracle import cases, hift_causal as hc, weights
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the causal vocoder happens at round end")]
+pytestmark = pytest.mark.gpu
 _loaded = set()
 
 

@@ -2,7 +2,7 @@
 recognises the variant by its state_dict (no llm_embedding, 6761-way bias-free head) and pads the head by 3 impossible ids.
 Golden ids from the reference CosyVoice3LM.inference (tests/golden/lm3_l2*.npz).
 
-Written after the round's GPU budget was spent (see tests/test_zz_hift3_gpu.py): xfail(strict=False) until the first GPU run."""
+First GPU run: round-1 driver test pass (green); the first-run xfail markers were removed in round 2."""
 import pytest
 import torch
 
@@ -10,7 +10,7 @@ from gpu_util import ctx
 from oracle import cases, lm
 from test_lm_gpu import _decode
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the CosyVoice3LM variant happens at round end")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("tag,cool", [("lm3_l2", 0.8), ("lm3_l2_stop", 1.0)])
