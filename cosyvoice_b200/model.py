@@ -52,6 +52,12 @@ def cfm_rand_noise():
 
 
 class B200CosyVoice2Model:
+    # text-streaming LM constants: Qwen2LM (llm.py:275-277: eos = speech_token_size, fill = speech_token_size + 2, whole
+    # prompt text goes into the text cache).  B200CosyVoice3Model overrides them (CosyVoice3LM, llm.py:681-684, 583-588).
+    bistream_fill_token = 6563
+    bistream_eos_token = 6561
+    bistream_eop_token = None
+
     def __init__(self, llm=None, flow=None, hift=None, fp16=False, precision="bf16", device=0, workspace_gb=24.0):
         # attribute names follow cli/model.py:245-275
         self.device = torch.device("cuda", device)
@@ -201,10 +207,17 @@ class B200CosyVoice2Model:
         cvk_lm_begin / cvk_lm_feed / cvk_lm_next_logp / cvk_ras_sample.  uniforms [n,2]: row len(out_tokens) is consumed by the
         draw that produces that token (default: drawn from the model's generator)."""
         mix_text, mix_speech = 5, 15
-        fill_token, speech_vocab = 6563, 6561
+        fill_token, eos_token, speech_vocab = self.bistream_fill_token, self.bistream_eos_token, 6561
         TEXT, SPEECH, LLM = 0, 1, 2
         d = self.device
         ptext = [int(x) for x in prompt_text.reshape(-1).tolist()]
+        lm_prefix = []
+        if self.bistream_eop_token is not None:
+            # llm.py:583-588: the prompt text up to and including <|endofprompt|> is fed ahead of the 5:15 interleaving
+            if self.bistream_eop_token not in ptext:
+                raise AssertionError("<|endofprompt|> not detected in CosyVoice3 prompt_text, check your input!")
+            eop = ptext.index(self.bistream_eop_token)
+            lm_prefix, ptext = [(TEXT, t) for t in ptext[:eop + 1]], ptext[eop + 1:]
         pspeech = [int(x) for x in prompt_speech_token.reshape(-1).tolist()]
         max_ctx = 4096
         with torch.cuda.stream(self.stream), self.ctx.lock:
@@ -215,7 +228,7 @@ class B200CosyVoice2Model:
         # `lm_input` has the reference variable's exact life cycle (list of (kind, id) positions): every model call pushes ALL
         # of it, it is replaced after a yielded token and - like the reference - left untouched when a fill token ends a decode
         # burst, so a final phase entered right after a fill token pushes that last input a second time (llm.py:634-637, 643).
-        lm_input = [(LLM, 0)]
+        lm_input = [(LLM, 0)] + lm_prefix
         text_cache = list(ptext)
         out_tokens = []
         next_fill_index = (len(pspeech) // mix_speech + 1) * mix_speech - len(pspeech)
@@ -278,7 +291,7 @@ class B200CosyVoice2Model:
             top = sample(forward(want_logp=True), ignore_eos=False)
             out_tokens.append(top)
             if top >= speech_vocab:
-                if top == speech_vocab:
+                if top == eos_token:
                     break
                 raise ValueError(f"should not get token {top}")
             yield top

@@ -14,6 +14,11 @@ from .model import B200CosyVoice2Model, TOKEN_MEL_RATIO, _count
 
 
 class B200CosyVoice3Model(B200CosyVoice2Model):
+    # CosyVoice3LM (llm.py:681-684): sos 6561 / eos 6562 / task_id 6563 / fill 6564; <|endofprompt|> = 151646 (llm.py:585)
+    bistream_fill_token = 6564
+    bistream_eos_token = 6562
+    bistream_eop_token = 151646
+
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         # FSQ silent and breath tokens (cli/model.py:423)

@@ -79,6 +79,18 @@ def bistream_case(seed=11, n_uniform=400):
     return chunks, ptext, ptok, U
 
 
+def bistream3_case():
+    """CosyVoice3LM text-streaming case (llm.py:583-588): the bistream case with <|endofprompt|> (151646) as the third prompt-text
+    id - ids 0..2 are fed ahead of the 5:15 interleaving, ids 3..5 start the text cache.  Uniform stream chosen (seed 13) so that,
+    with oracle.lm.bistream_state_dict3(2, boost=2.6), no special id is drawn in the interleaved phase and eos (6562) ends the
+    final phase after 71 yielded ids and 3 forced fill tokens."""
+    chunks, ptext, ptok, _ = bistream_case()
+    _, _, _, U = bistream_case(seed=13)
+    ptext = ptext.clone()
+    ptext[0, 2] = 151646
+    return chunks, ptext, ptok, U
+
+
 def sampling_case(n=64, V=6564, seed=4):
     """Random log-prob vectors of varying peakiness + random decoded histories + uniforms."""
     g = _g(5000 + seed)

@@ -168,23 +168,40 @@ def bistream_state_dict(num_layers):
     return sd
 
 
-def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, uniforms, num_layers=24, return_trace=False):
-    """llm.py:551-661 (Qwen2LM branch).  text_chunks: list of int tensors [1,k] (the text generator); uniforms [n,2], row
-    len(out_tokens) is consumed by the draw that produces out_tokens[len(out_tokens)].  Returns the yielded ids (fill tokens are
-    kept in the internal history only) and optionally the list of out_tokens including fill tokens."""
+def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, uniforms, num_layers=24, return_trace=False, variant="qwen2"):
+    """llm.py:551-661 (Qwen2LM.inference_bistream, inherited by CosyVoice3LM).  text_chunks: list of int tensors [1,k] (the text
+    generator); uniforms [n,2], row len(out_tokens) is consumed by the draw that produces out_tokens[len(out_tokens)].  Returns
+    the yielded ids (fill tokens are kept in the internal history only) and optionally the list of out_tokens including fill
+    tokens.  variant "qwen2": sos / task_id = llm_embedding rows 0 / 1, fill 6563, eos 6561 (llm.py:275-277); variant "cv3"
+    (CosyVoice3LM, llm.py:681-684, 562-564, 583-588): sos / task_id = speech_embedding rows 6561 / 6563, fill 6564, eos 6562, head
+    without bias, and the prompt text up to and including <|endofprompt|> (151646) is fed before the 5:15 interleaving starts."""
     emb_t = lambda ids: F.embedding(ids.long(), sd["llm.model.model.embed_tokens.weight"])
-    sos = sd["llm_embedding.weight"][0].reshape(1, 1, -1)
-    task = sd["llm_embedding.weight"][1].reshape(1, 1, -1)
+    if variant == "cv3":
+        sos = sd["speech_embedding.weight"][SOS3].reshape(1, 1, -1)
+        task = sd["speech_embedding.weight"][TASK3].reshape(1, 1, -1)
+        fill_token, eos_token = FILL3, EOS3
+        head = lambda y: F.log_softmax(F.linear(y, sd["llm_decoder.weight"]), dim=-1)
+    else:
+        sos = sd["llm_embedding.weight"][0].reshape(1, 1, -1)
+        task = sd["llm_embedding.weight"][1].reshape(1, 1, -1)
+        fill_token, eos_token = FILL_TOKEN, 6561
+        head = lambda y: logprobs(sd, y)
     sp = F.embedding(prompt_speech_token.long(), sd["speech_embedding.weight"]) if prompt_speech_token.shape[1] else torch.zeros(1, 0, D)
     lm_input = sos
     out_tokens, yielded, past = [], [], None
+    if variant == "cv3":
+        flat = prompt_text.flatten().tolist()
+        assert 151646 in flat, "<|endofprompt|> not detected in CosyVoice3 prompt_text"        # llm.py:585
+        eop = flat.index(151646)
+        lm_input = torch.cat([lm_input, emb_t(prompt_text[:, :eop + 1])], dim=1)
+        prompt_text = prompt_text[:, eop + 1:]
     text_cache = emb_t(prompt_text)
     P = prompt_speech_token.shape[1]
     next_fill_index = (int(P / MIX_RATIO[1]) + 1) * MIX_RATIO[1] - P
 
     def step(lm_input, past, ignore_eos):
         y, past = qwen2_forward(sd, lm_input, past, num_layers)
-        logp = logprobs(sd, y[:, -1]).squeeze(0)
+        logp = head(y[:, -1]).squeeze(0)
         return logp, past
 
     for this_text in text_chunks:
@@ -196,10 +213,10 @@ def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, unifor
             else:
                 break
         if sp.shape[1] == 0:
-            if (len(out_tokens) != 0 and out_tokens[-1] == FILL_TOKEN) or (len(out_tokens) == 0 and lm_input.shape[1] == 1):
+            if (len(out_tokens) != 0 and out_tokens[-1] == fill_token) or (len(out_tokens) == 0 and lm_input.shape[1] == 1):
                 if text_cache.shape[1] >= MIX_RATIO[0]:
                     lm_input_text = text_cache[:, :MIX_RATIO[0]]
-                    if len(out_tokens) != 0 and out_tokens[-1] == FILL_TOKEN:
+                    if len(out_tokens) != 0 and out_tokens[-1] == fill_token:
                         lm_input = lm_input_text
                     else:
                         lm_input = torch.cat([lm_input, lm_input_text], dim=1)
@@ -209,16 +226,16 @@ def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, unifor
             while True:
                 logp, past = step(lm_input, past, True)
                 if next_fill_index != -1 and len(out_tokens) == next_fill_index:
-                    top = FILL_TOKEN
+                    top = fill_token
                     next_fill_index += MIX_RATIO[1] + 1
                 else:
                     i = len(out_tokens)
                     top = sampling.ras_sample(logp.numpy(), out_tokens, float(uniforms[i, 0]), float(uniforms[i, 1]), ignore_eos=True)
-                if top == FILL_TOKEN:
+                if top == fill_token:
                     next_fill_index = len(out_tokens) + MIX_RATIO[1] + 1
                 out_tokens.append(top)
                 if top >= 6561:
-                    if top == FILL_TOKEN:
+                    if top == fill_token:
                         break
                     raise ValueError(f"should not get token {top}")
                 yielded.append(top)
@@ -230,7 +247,7 @@ def inference_bistream(sd, text_chunks, prompt_text, prompt_speech_token, unifor
         top = sampling.ras_sample(logp.numpy(), out_tokens, float(uniforms[i, 0]), float(uniforms[i, 1]), ignore_eos=False)
         out_tokens.append(top)
         if top >= 6561:
-            if top == 6561:
+            if top == eos_token:
                 break
             raise ValueError(f"should not get token {top}")
         yielded.append(top)
@@ -263,6 +280,26 @@ def synth_state_dict3(num_layers=24, seed=1986, cool=0.8):
     # the repetition window (cool = 0.8: the golden runs to max_len); cool = 1.0 gives the second golden, which ends on a
     # sampled stop id before min_len.
     sd["llm_decoder.weight"][SPEECH_TOKENS + 1:] *= cool
+    return sd
+
+
+def bistream_state_dict3(num_layers, boost=2.6):
+    """Synthetic CosyVoice3LM weights for the text-streaming case.  inference_bistream raises on every id >= 6561 except the fill
+    token (interleaved phase) / the eos token (final phase) and has no length cap, and CosyVoice3LM's head has no bias to steer
+    with.  So a constant channel is planted: column 0 of every embedding row is a large constant (it survives the residual stream
+    and the final RMSNorm as a reliably positive feature), and column 0 of the head is zero for the speech ids, strongly negative
+    for the special ids and positive for eos (6562) - an emulated bias.  Nothing masks eos in the interleaved phase
+    (sampling_ids masks index 6561 only, llm.py:156-157 - the reference has the same hazard with a real model), so the boost is
+    set where eos sits at the edge of the top-25 nucleus (a few percent per draw) and cases.bistream3_case picks a uniform stream
+    on which the first eos draw falls in the final phase."""
+    sd = {k: v.clone() for k, v in synth_state_dict3(num_layers, cool=0.0).items()}
+    sd["llm.model.model.embed_tokens.weight"][:, 0] = 6.0
+    sd["speech_embedding.weight"][:, 0] = 6.0
+    sd["llm.model.lm_head.weight"] = sd["llm.model.model.embed_tokens.weight"]
+    w = sd["llm_decoder.weight"]
+    w[:, 0] = 0.0
+    w[SPEECH_TOKENS:, 0] = -4.0
+    w[EOS3, 0] = boost
     return sd
 
 

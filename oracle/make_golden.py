@@ -288,6 +288,39 @@ def gen_bistream():
     save("lm_bistream_l2", ids=np.array(ids, dtype=np.int32), trace=np.array(trace, dtype=np.int32))
 
 
+def gen_bistream3():
+    """cosyvoice/llm/llm.py:551-661 as inherited by CosyVoice3LM (:664-705): sos / task_id rows of speech_embedding, fill 6564,
+    eos 6562, prompt text split at <|endofprompt|>."""
+    print("lm bistream (CosyVoice3LM)")
+    NL = 2
+    ref = refimport.build_llm3(num_layers=NL)
+    sd = lm.bistream_state_dict3(NL)
+    ref.load_state_dict(sd, strict=True)
+    chunks, ptext, ptok, U = cases.bistream3_case()
+    st = {"i": 0, "c": 0}
+
+    def get_u():
+        u = float(U[st["i"], min(st["c"], 1)])
+        st["c"] += 1
+        return u
+    orig = ref.sampling_ids
+
+    def sampling_ids(weighted_scores, decoded_tokens, sampling_, ignore_eos=True):
+        st["i"], st["c"] = len(decoded_tokens), 0          # uniforms are indexed by the position in out_tokens
+        return orig(weighted_scores, decoded_tokens, sampling_, ignore_eos)
+    ref.sampling_ids = sampling_ids
+    ids = []
+    with patched_multinomial(get_u):
+        for tok in ref.inference_bistream(text=iter(chunks), prompt_text=ptext, prompt_text_len=torch.tensor([ptext.shape[1]], dtype=torch.int32),
+                                          prompt_speech_token=ptok, prompt_speech_token_len=torch.tensor([ptok.shape[1]], dtype=torch.int32),
+                                          embedding=torch.zeros(0, 192)):
+            ids.append(int(tok))
+    ref.sampling_ids = orig
+    o, trace = lm.inference_bistream(sd, chunks, ptext, ptok, U, NL, return_trace=True, variant="cv3")
+    print(f"  {len(ids)} ids yielded, {sum(1 for t in trace if t == lm.FILL3)} fill tokens, last {trace[-1]}, oracle == reference: {o == ids}")
+    save("lm3_bistream_l2", ids=np.array(ids, dtype=np.int32), trace=np.array(trace, dtype=np.int32))
+
+
 def gen_sampling():
     print("sampling")
     refimport.install()
@@ -457,6 +490,6 @@ def gen_stream3():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "lm3", "bistream", "sampling", "mel", "masks", "stream", "stream3"]
+    which = sys.argv[1:] or ["hift", "hift_causal", "flow", "dit", "lm", "lm3", "bistream", "bistream3", "sampling", "mel", "masks", "stream", "stream3"]
     for w in which:
         globals()["gen_" + w]()

@@ -69,6 +69,47 @@ def test_bistream_host_logic_matches_reference(golden):
     assert all(n in (1, 5, 33) for n in ctx.fed)
 
 
+class FakeLm3Context(FakeLmContext):
+    """the same primitives for a CosyVoice3LM state_dict: llm_embedding rows 0 / 1 of the C ABI are rows 6561 / 6563 of
+    speech_embedding (csrc/llm.cu llm_build), the head has no bias"""
+
+    def lm_feed(self, sess, ids, kinds):
+        emb = []
+        for i, k in zip(ids, kinds):
+            if k == 2:
+                emb.append(self.sd["speech_embedding.weight"][(6561, 6563)[i]])
+            else:
+                emb.append(self.sd[{0: "llm.model.model.embed_tokens.weight", 1: "speech_embedding.weight"}[k]][i])
+        self.fed.append(len(ids))
+        y, self.past = lm.qwen2_forward(self.sd, torch.stack(emb)[None], self.past, self.nl)
+        self.hidden = y[:, -1]
+
+    def lm_next_logp(self, sess, B=1):
+        return torch.log_softmax(torch.nn.functional.linear(self.hidden, self.sd["llm_decoder.weight"]), -1)
+
+
+def test_bistream3_host_logic_matches_reference(golden):
+    """CosyVoice3LM text-streaming constants (llm.py:681-684: fill 6564, eos 6562) and the <|endofprompt|> split (llm.py:583-588)
+    in B200CosyVoice3Model.lm_generate_bistream: ids identical to the reference CosyVoice3LM.inference_bistream."""
+    from cosyvoice_b200.model3 import B200CosyVoice3Model
+    g = golden("lm3_bistream_l2")
+    chunks, ptext, ptok, U = cases.bistream3_case()
+    ctx = FakeLm3Context(lm.bistream_state_dict3(2), 2)
+    m = object.__new__(B200CosyVoice3Model)
+    m.ctx, m.stream, m.device = ctx, None, torch.device("cpu")
+    m._sessions, m.uniforms_override, m.generator = {}, None, None
+    ids = list(m.lm_generate_bistream(iter(chunks), ptext, ptok, uniforms=U))
+    assert ids == g["ids"].tolist() and int(g["trace"][-1]) == 6562
+    # first model call: sos + the 3 prompt-text ids up to <|endofprompt|> + (5 text, 15 speech) + (5 text, 7 speech)
+    assert ctx.fed[0] == 1 + 3 + (5 + 15) + (5 + 7)
+    # without <|endofprompt|> the reference asserts (llm.py:585)
+    try:
+        list(m.lm_generate_bistream(iter(chunks), ptext.clamp(max=151645), ptok, uniforms=U))
+        raise RuntimeError("no assertion")
+    except AssertionError:
+        pass
+
+
 def test_llm_job_generator_branch_collects_tokens(golden):
     """cli/model.py:113-128: generator text -> bi-stream decode -> tokens appended to the session list, end flag set"""
     g = golden("lm_bistream_l2")

@@ -23,3 +23,15 @@ def test_cosyvoice3lm_decode_ids_match_reference_fp32(tag, cool, golden):
     text, ptext, ptok, U = cases.lm3_case()
     ids = _decode(c, [text], [ptext], [ptok], U[:, None, :])[0]
     assert ids == g["ids"].tolist()
+
+
+def test_cosyvoice3lm_bistream_ids_match_reference_fp32(golden):
+    """§8 a7 for CosyVoice3LM (llm.py:551-661 as inherited by :664-705): fill 6564 / eos 6562, prompt text split at <|endofprompt|>,
+    sos / task_id rows of speech_embedding behind cvk_lm_feed's kind 2 - ids identical to the reference's inference_bistream."""
+    from cosyvoice_b200.model3 import B200CosyVoice3Model
+    g = golden("lm3_bistream_l2")
+    chunks, ptext, ptok, U = cases.bistream3_case()
+    m = B200CosyVoice3Model(precision="fp32", device=0, workspace_gb=2.0)
+    m.ctx.load_state_dict("llm", lm.bistream_state_dict3(2), [2])            # LM stage only
+    ids = list(m.lm_generate_bistream(iter(chunks), ptext, ptok, uniforms=U))
+    assert ids == g["ids"].tolist()
