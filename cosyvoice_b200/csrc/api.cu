@@ -101,7 +101,8 @@ void cvk_destroy(cvk_ctx* ctx) {
 }
 
 const char* cvk_last_error(cvk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
-int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+thread_local int cvk_in_capture = 0;
+int64_t cvk_launch_count(cvk_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 double cvk_last_op_ms(cvk_ctx* ctx) { return ctx ? ctx->op_ms : 0.0; }
 int cvk_debug_read(cvk_ctx* ctx, long long* out, int n) {
   if (ctx && ctx->tl && out && n == 4096) {   // LM-chain timeline

@@ -10,6 +10,7 @@
 #include <map>
 #include <unordered_map>
 #include <stdexcept>
+#include <atomic>
 
 #include "../../include/cvk.h"
 
@@ -112,6 +113,10 @@ struct Epilogue {
 };
 
 // ------------------------------------------------------------------------------------------------ context
+// set while the calling thread captures the LM decode step into a CUDA graph (per thread: an LM session call and a workspace
+// call - flow / vocoder - may run concurrently on two host threads, see include/cvk.h)
+extern thread_local int cvk_in_capture;
+
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0, high = 0;
@@ -163,7 +168,7 @@ struct cvk_ctx {
   LlmModel* llm = nullptr;
   void* mel_model = nullptr;
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
-  int64_t launches = 0;                     // kernels launched by this library (bench.py gpu_launches)
+  std::atomic<int64_t> launches{0};         // kernels launched by this library (bench.py gpu_launches); LM-session calls and workspace calls may run on two threads
   int op_out_bf16 = 0;                      // cvk_op_conv1d: bf16 output matrix (the estimator's usual epilogue) instead of fp32
   int op_iters = 0;                         // cvk_op_conv1d: repeat the GEMM launch this many times and time it
   double op_ms = 0.0;
@@ -180,7 +185,6 @@ struct cvk_ctx {
     return p;
   }
   int prof_on = 0;
-  int in_capture = 0;
   std::vector<ProfRec> prof;
   std::unordered_map<const void*, void*> tiled;   // bf16 weight -> streaming (pre-tiled, pre-swizzled) copy for the skinny GEMM
   std::vector<cudaEvent_t> event_pool;
@@ -282,7 +286,7 @@ struct ProfScope {
   cudaStream_t st;
   ProfRec rec;
   bool on;
-  ProfScope(cvk_ctx* c, cudaStream_t s, int family, double work, double bytes) : ctx(c), st(s), on(c->prof_on && !c->in_capture) {
+  ProfScope(cvk_ctx* c, cudaStream_t s, int family, double work, double bytes) : ctx(c), st(s), on(c->prof_on && !cvk_in_capture) {
     if (!on) return;
     auto get = [&]() {
       cudaEvent_t e;

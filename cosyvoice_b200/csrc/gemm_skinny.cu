@@ -300,7 +300,7 @@ void launch(cudaStream_t st, dim3 grid, const bf16* tw, const CUtensorMap& tx, c
 const bf16* skinny_tiled_weights(cvk_ctx* ctx, const ConvW& W) {
   auto it = ctx->tiled.find(W.w16);
   if (it != ctx->tiled.end()) return (const bf16*)it->second;
-  CVK_REQUIRE(!ctx->in_capture, "skinny_tiled_weights: weight was not pre-tiled before graph capture");
+  CVK_REQUIRE(!cvk_in_capture, "skinny_tiled_weights: weight was not pre-tiled before graph capture");
   const int tiles = ceil_div(W.N, SK_BM), kchunks = ceil_div(W.K, SK_BK);
   bf16* out = (bf16*)ctx->dmalloc((size_t)tiles * kchunks * SK_BM * SK_BK * sizeof(bf16));
   tile_weights_kernel<<<148 * 8, 256>>>(W.w16, out, W.N, W.K, tiles, kchunks);

@@ -782,7 +782,8 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
 
 void llm_session_destroy(cvk_ctx* ctx, cvk_lm_session* s) {
   cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
+  // the caller guarantees that no call on this session is in flight on the host; device work still queued on the caller's
+  // stream is drained by cudaFree (it synchronises the device implicitly) before the buffers go away
   if (s->graph) cudaGraphExecDestroy(s->graph);
   for (void* p : s->owned) cudaFree(p);
   lm_mega_session_free(s);
@@ -953,12 +954,12 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     int64_t before = ctx->launches;
     cudaGraph_t graph = nullptr;
     CVK_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    ctx->in_capture = 1;
+    cvk_in_capture = 1;
     try {
       decode_step(ctx, st, s);
-      ctx->in_capture = 0;
+      cvk_in_capture = 0;
     } catch (...) {
-      ctx->in_capture = 0;
+      cvk_in_capture = 0;
       cudaStreamEndCapture(st, &graph);
       if (graph) cudaGraphDestroy(graph);
       throw;
@@ -967,7 +968,7 @@ void llm_decode(cvk_ctx* ctx, cvk_lm_session* s, int n_steps, const float* unifo
     CVK_CHECK_CUDA(cudaGraphInstantiate(&s->graph, graph, 0));
     cudaGraphDestroy(graph);
     s->graph_kernels = ctx->launches - before;
-    ctx->launches = before;
+    ctx->launches -= s->graph_kernels;
   }
   for (int i = 0; i < n_steps; ++i) {
     if (can_graph && s->graph) {

@@ -35,8 +35,10 @@ __host__ __device__ constexpr int decode_attn_smem_floats() { return (NH / NKV +
 
 // tid / warp / lane: coordinates inside the group of NW warps that runs the unit (all NW*32 threads must call).
 // partial [splits][rows][1152] fp32 split-K sums of the qkv projection of row b; kb / vb: this (row, kv head)'s cache
-// [max_ctx][64]; out: bf16 [.. ldo], this row's attention output (columns of the kv group's 7 query heads)
-template <int NW, int BAR_ID>
+// [max_ctx][64]; out: bf16 [.. ldo], this row's attention output (columns of the kv group's 7 query heads).
+// SPLITS > 0: compile-time split count - every partial-sum load of a thread is issued before the first add (ONE memory round
+// trip instead of one per in-order add), read with ld.global.cg (the producers are other SMs of the same kernel).
+template <int NW, int BAR_ID, int SPLITS = 0>
 __device__ __forceinline__ void decode_attn_unit(float* __restrict__ sm_all, int tid, const float* __restrict__ partial, int splits, int rows,
                                                  int b, int kvh, const float* __restrict__ bias, bf16* __restrict__ kb, bf16* __restrict__ vb,
                                                  int pos, int max_ctx, const float* __restrict__ inv_freq, bf16* __restrict__ out_row) {
@@ -46,21 +48,47 @@ __device__ __forceinline__ void decode_attn_unit(float* __restrict__ sm_all, int
   float* stage = sm_all;
   float* ml = stage + (G + 2) * HD;
   float* po = ml + NW * 8 * 2;
-  for (int e = tid; e < (G + 2) * HD; e += NT) {
-    const int vec = e / HD, d = e % HD;
-    const int col = vec < G ? (kvh * G + vec) * HD + d : (vec == G ? NH * HD + kvh * HD + d : NH * HD + NKV * HD + kvh * HD + d);
-    const float* p = partial + (size_t)b * QKV_N + col;
+  if (SPLITS > 0) {
+    constexpr int PER = ((G + 2) * HD + NT - 1) / NT;
+    constexpr int S = SPLITS > 0 ? SPLITS : 1;
+    float ld[PER][S], bs[PER];
     const size_t stride = (size_t)rows * QKV_N;
-    float a0 = bias[col], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {      // independent loads in flight
-      a0 += p[(size_t)s * stride];
-      a1 += p[(size_t)(s + 1) * stride];
-      a2 += p[(size_t)(s + 2) * stride];
-      a3 += p[(size_t)(s + 3) * stride];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = tid + i * NT;
+      const bool ok = e < (G + 2) * HD;
+      const int vec = ok ? e / HD : 0, d = e % HD;
+      const int col = vec < G ? (kvh * G + vec) * HD + d : (vec == G ? NH * HD + kvh * HD + d : NH * HD + NKV * HD + kvh * HD + d);
+      const float* p = partial + (size_t)b * QKV_N + col;
+      bs[i] = bias[col];
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) ld[i][s2] = ok ? __ldcg(p + (size_t)s2 * stride) : 0.f;
     }
-    for (; s < splits; ++s) a0 += p[(size_t)s * stride];
-    stage[e] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = tid + i * NT;
+      float a = bs[i];
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) a += ld[i][s2];
+      if (e < (G + 2) * HD) stage[e] = a;
+    }
+  } else {
+    for (int e = tid; e < (G + 2) * HD; e += NT) {
+      const int vec = e / HD, d = e % HD;
+      const int col = vec < G ? (kvh * G + vec) * HD + d : (vec == G ? NH * HD + kvh * HD + d : NH * HD + NKV * HD + kvh * HD + d);
+      const float* p = partial + (size_t)b * QKV_N + col;
+      const size_t stride = (size_t)rows * QKV_N;
+      float a0 = bias[col], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int s = 0;
+      for (; s + 4 <= splits; s += 4) {      // independent loads in flight
+        a0 += p[(size_t)s * stride];
+        a1 += p[(size_t)(s + 1) * stride];
+        a2 += p[(size_t)(s + 2) * stride];
+        a3 += p[(size_t)(s + 3) * stride];
+      }
+      for (; s < splits; ++s) a0 += p[(size_t)s * stride];
+      stage[e] = (a0 + a1) + (a2 + a3);
+    }
   }
   attn_bar<BAR_ID, NT>();
   for (int e = tid; e < (G + 1) * (HD / 2); e += NT) {     // rotate the G query heads and k (half-split RoPE, theta 1e6)

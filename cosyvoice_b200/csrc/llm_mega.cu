@@ -19,6 +19,7 @@
 // down GEMM | +res, RMSNorm.
 #include "llm_decode_attn.cuh"
 #include <algorithm>
+#include <type_traits>
 
 using namespace lm;
 
@@ -127,10 +128,22 @@ __device__ __forceinline__ long long gtime() {
   return t;
 }
 
+// static schedule constants shared by the host-side table builder and the kernel (compile-time split counts let every
+// partial-sum load of a reduction be issued before the first add)
+constexpr int MG_CPU_QKV = 2, MG_CPU_O = 2, MG_CPU_DOWN = 8;        // K chunks per unit
+constexpr int MG_SPL_QKV = MG_KCH / MG_CPU_QKV;                      // 7
+constexpr int MG_SPL_O = MG_KCH / MG_CPU_O;                          // 7
+constexpr int MG_SPL_DOWN = (DFF / MG_BK + MG_CPU_DOWN - 1) / MG_CPU_DOWN;   // 10
+constexpr int MG_MAX_LAYERS = 32;
+
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int BPAD>
 __global__ void __launch_bounds__(MG_THREADS, 1)
-lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant__ CUtensorMap tm_att,
-               const __grid_constant__ CUtensorMap tm_ffa, const MegaParams p) {
+lm_mega_kernel(const MegaParams p) {
   constexpr int NST = BPAD == 32 ? 10 : 7;
   constexpr uint32_t ACT_CHUNK = BPAD * 128;     // one 64-wide K chunk of the activations: [BPAD rows][128 B], SWIZZLE_128B
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BPAD >> 3) << 17) | ((uint32_t)(MG_BM >> 4) << 24);
@@ -138,15 +151,17 @@ lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MG_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MG_MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_act;
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[16];
+  __shared__ MegaUnit s_units[MG_PH];
+  __shared__ MegaLayerDev s_layers[MG_MAX_LAYERS];
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t ring = sbase, act = sbase + NST * MG_BLK;
-  float* attn_sm = reinterpret_cast<float*>(sptr + NST * MG_BLK);       // aliases the activation buffer (disjoint phases)
+  uint8_t* act_ptr = sptr + NST * MG_BLK;
+  float* attn_sm = reinterpret_cast<float*>(act_ptr);       // aliases the activation buffer (disjoint phases)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int B = p.B;
@@ -156,10 +171,11 @@ lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant_
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_act), 1);
     mbar_init(smem_u32(&bar_acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + MG_PH) s_units[threadIdx.x - 64] = p.units[(threadIdx.x - 64) * G + cta];
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + p.num_layers) s_layers[threadIdx.x - 128] = p.layers[threadIdx.x - 128];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)BPAD) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -188,43 +204,66 @@ lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant_
     // ---------------------------------------------------------------------------------------- workers
     const int wt = threadIdx.x - 32;
     const int ww = warp - 1;
-    unsigned bar_target = p.bar[1];
+    unsigned bar_target = __ldcg(p.bar + 1);
     const unsigned gen0 = bar_target;
-    uint32_t act_par = 0, acc_par = 0;
+    uint32_t acc_par = 0;
     int mma_it = 0, tl_i = 0;
     const bool stamp = p.tl != nullptr && cta == 0 && wt == 0;
     if (stamp) p.tl[tl_i++] = gtime();
 
+    // grid-wide barrier: every worker's global writes happen-before (bar.sync) the release-add of thread 0; the acquire-load that
+    // sees the last arrival happens-before (bar.sync) every worker's following reads (which use ld.global.cg: L2 is the
+    // coherence point, stale L1 lines of the previous layer's activations are never consulted)
     auto grid_sync = [&]() {
       bar_target += (unsigned)G;
       worker_bar();
       if (wt == 0) {
-        __threadfence();
-        atomicAdd(p.bar, 1u);
+        red_release_add(p.bar, 1u);
         const long long t0 = clock64();
         while ((int)(ld_acquire(p.bar) - bar_target) < 0) {
           if (clock64() - t0 > 4000000000ll) __trap();
         }
-        __threadfence();
         if (stamp) p.tl[tl_i++] = gtime();
       }
       worker_bar();
     };
 
-    // one GEMM phase: this CTA's unit = tile u.nt of the weight, K chunks [kc0, kc0 + nblk).
-    // mode 0: fp32 partial sums -> out_f32[(split * B + b) * N + n]; mode 1: SwiGLU on interleaved gate/up rows -> ffa
-    auto gemm_phase = [&](int ph, const CUtensorMap* tmap, float* out_f32, int N, int mode) {
-      const MegaUnit u = p.units[ph * G + cta];
+    // one GEMM phase: this CTA's unit = tile u.nt of the weight, K chunks [kc0, kc0 + nblk) of the activation matrix `actg`
+    // [B][K] bf16.  mode 0: fp32 partial sums -> out_f32[(split * B + b) * N + n]; mode 1: SwiGLU on interleaved gate/up rows -> ffa
+    auto gemm_phase = [&](int ph, const bf16* actg, int K, float* out_f32, int N, int mode) {
+      const MegaUnit u = s_units[ph];
       if (u.nblk <= 0) return;
-      if (warp == 2 && lane == 0) {
-        fence_proxy_async();
-        const uint32_t ab = smem_u32(&bar_act);
-        mbar_expect_tx(ab, (uint32_t)u.nblk * ACT_CHUNK);
-        for (int j = 0; j < u.nblk; ++j) tma_load_2d(act + j * ACT_CHUNK, tmap, ab, (u.kc0 + j) * MG_BK, 0);
+      {
+        // activations -> shared memory in the K-major SWIZZLE_128B operand layout (what a TMA box {64, BPAD} would write): row b,
+        // 16-byte chunk c of K chunk j at j*ACT_CHUNK + b*128 + ((c ^ (b & 7)) << 4).  All loads of a thread are issued before the
+        // first store.  Rows >= B are left as they are: column b of the accumulator depends on row b only and is never stored.
+        const int items = u.nblk * B * 8;
+        constexpr int UN = 4;
+        for (int i0 = wt; i0 < items; i0 += MG_WORKERS * UN) {
+          uint4 v[UN];
+#pragma unroll
+          for (int q = 0; q < UN; ++q) {
+            const int i = i0 + q * MG_WORKERS;
+            if (i < items) {
+              const int c = i & 7, b = (i >> 3) % B, j = (i >> 3) / B;
+              v[q] = __ldcg(reinterpret_cast<const uint4*>(actg + (size_t)b * K + (size_t)(u.kc0 + j) * MG_BK) + c);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < UN; ++q) {
+            const int i = i0 + q * MG_WORKERS;
+            if (i < items) {
+              const int c = i & 7, b = (i >> 3) % B, j = (i >> 3) / B;
+              *reinterpret_cast<uint4*>(act_ptr + j * ACT_CHUNK + b * 128 + ((c ^ (b & 7)) << 4)) = v[q];
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the MMA (async proxy)
+        worker_bar();
       }
       if (warp == 1) {
         if (lane == 0) {
-          mbar_wait(smem_u32(&bar_act), act_par);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int j = 0; j < u.nblk; ++j) {
             const int it = mma_it + j;
             const int s = it % NST;
@@ -269,35 +308,35 @@ lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant_
             }
           }
         }
-        if (mode == 1) fence_proxy_async();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      act_par ^= 1u;
       acc_par ^= 1u;
       mma_it += u.nblk;
     };
 
-    // x[b] += sum_s part[s][b]; xn[b] = bf16(gamma * rmsnorm(x[b]))   (one row per CTA; fixed summation order)
-    auto reduce_norm = [&](const float* part, int splits, const float* gamma) {
+    // x[b] += sum_s part[s][b]; xn[b] = bf16(gamma * rmsnorm(x[b]))   (one row per CTA; fixed summation order; every load of a
+    // thread in flight at once)
+    auto reduce_norm = [&](const float* part, auto splits_tag, const float* gamma) {
+      constexpr int S = decltype(splits_tag)::value;
       for (int b = cta; b < B; b += G) {
-        float v[2] = {0.f, 0.f};
-        float ss = 0.f;
+        float ld[2][S + 1];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int n = wt + h * MG_WORKERS;
+          const bool ok = n < D;
+          ld[h][0] = ok ? __ldcg(p.x + (size_t)b * D + n) : 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) ld[h][s + 1] = ok ? __ldcg(part + ((size_t)s * B + b) * D + n) : 0.f;
+        }
+        float v[2], ss = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float a = 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) a += ld[h][s + 1];
+          v[h] = ld[h][0] + a;
+          const int n = wt + h * MG_WORKERS;
           if (n < D) {
-            const float* pp = part + (size_t)b * D + n;
-            const size_t stride = (size_t)B * D;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int s = 0;
-            for (; s + 4 <= splits; s += 4) {
-              a0 += pp[(size_t)s * stride];
-              a1 += pp[(size_t)(s + 1) * stride];
-              a2 += pp[(size_t)(s + 2) * stride];
-              a3 += pp[(size_t)(s + 3) * stride];
-            }
-            for (; s < splits; ++s) a0 += pp[(size_t)s * stride];
-            v[h] = p.x[(size_t)b * D + n] + ((a0 + a1) + (a2 + a3));
             p.x[(size_t)b * D + n] = v[h];
             ss += v[h] * v[h];
           }
@@ -314,34 +353,46 @@ lm_mega_kernel(const __grid_constant__ CUtensorMap tm_xn, const __grid_constant_
           const int n = wt + h * MG_WORKERS;
           if (n < D) p.xn[(size_t)b * D + n] = __float2bfloat16_rn(gamma[n] * (v[h] * r));
         }
-        fence_proxy_async();
         worker_bar();
       }
     };
 
     for (int l = 0; l < p.num_layers; ++l) {
-      const MegaLayerDev Lw = p.layers[l];
-      gemm_phase(0, &tm_xn, p.part_qkv, QKV_N, 0);
+      const MegaLayerDev Lw = s_layers[l];
+      bf16* kc_l = p.kcache + (size_t)l * p.kv_layer_stride;
+      bf16* vc_l = p.vcache + (size_t)l * p.kv_layer_stride;
+      if (cta < B * NKV && warp >= 8) {
+        // this CTA's attention unit of the NEXT phase: pull its K / V rows (one 128-byte line per position) into L2 while the qkv
+        // projection runs (the caches of 24 layers x 32 rows do not stay L2-resident between steps)
+        const int b = cta / NKV, kvh = cta % NKV;
+        const int L = min(p.ctx_len[b], p.max_ctx);
+        const bf16* kb = kc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
+        const bf16* vb = vc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
+        for (int j = threadIdx.x - 256; j < L; j += MG_THREADS - 256) {
+          prefetch_l2(kb + (size_t)j * HD);
+          prefetch_l2(vb + (size_t)j * HD);
+        }
+      }
+      gemm_phase(0, p.xn, D, p.part_qkv, QKV_N, 0);
       grid_sync();
       for (int u = cta; u < B * NKV; u += G) {
         const int b = u / NKV, kvh = u % NKV;
-        bf16* kb = p.kcache + (size_t)l * p.kv_layer_stride + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
-        bf16* vb = p.vcache + (size_t)l * p.kv_layer_stride + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
-        decode_attn_unit<MG_NW, 1>(attn_sm, wt, p.part_qkv, p.splits_qkv, B, b, kvh, Lw.qkv_bias, kb, vb, p.ctx_len[b], p.max_ctx,
-                                   p.inv_freq, p.att + (size_t)b * D);
-        fence_proxy_async();
+        bf16* kb = kc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
+        bf16* vb = vc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
+        decode_attn_unit<MG_NW, 1, MG_SPL_QKV>(attn_sm, wt, p.part_qkv, MG_SPL_QKV, B, b, kvh, Lw.qkv_bias, kb, vb, p.ctx_len[b], p.max_ctx,
+                                               p.inv_freq, p.att + (size_t)b * D);
         worker_bar();
       }
       grid_sync();
-      gemm_phase(1, &tm_att, p.part_o, D, 0);
+      gemm_phase(1, p.att, D, p.part_o, D, 0);
       grid_sync();
-      reduce_norm(p.part_o, p.splits_o, Lw.ln2);
+      reduce_norm(p.part_o, std::integral_constant<int, MG_SPL_O>(), Lw.ln2);
       grid_sync();
-      gemm_phase(2, &tm_xn, nullptr, 2 * DFF, 1);
+      gemm_phase(2, p.xn, D, nullptr, 2 * DFF, 1);
       grid_sync();
-      gemm_phase(3, &tm_ffa, p.part_down, D, 0);
+      gemm_phase(3, p.ffa, DFF, p.part_down, D, 0);
       grid_sync();
-      reduce_norm(p.part_down, p.splits_down, Lw.next_gamma);
+      reduce_norm(p.part_down, std::integral_constant<int, MG_SPL_DOWN>(), Lw.next_gamma);
       if (l + 1 < p.num_layers) grid_sync();
     }
     if (cta == 0 && wt == 0) {
@@ -363,30 +414,6 @@ __global__ void copy_blocks_kernel(const uint8_t* const* __restrict__ src, uint8
     uint4* d = reinterpret_cast<uint4*>(dst[i]);
     for (int e = threadIdx.x; e < (int)(MG_BLK / 16); e += blockDim.x) d[e] = s[e];
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-CUtensorMap act_map(cvk_ctx* ctx, const void* p, int rows, int K, int bpad) {
-  if (!ctx->encode_tiled) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CVK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    CVK_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    ctx->encode_tiled = fn;
-  }
-  CUtensorMap m;
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {MG_BK, (cuuint32_t)bpad};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p), dims, strides, box, es,
-                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CVK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(lm mega activations) failed: " + std::to_string((int)r));
-  return m;
 }
 
 template <int BPAD> constexpr size_t mega_smem() { return (size_t)(BPAD == 32 ? 10 : 7) * MG_BLK + (size_t)MG_KCH * BPAD * 128 + 1024; }
@@ -418,15 +445,16 @@ void lm_mega_build(cvk_ctx* ctx, LlmModel* m) {
   // (blocks per unit = serial MMAs; splits = partial sums the consumer must add) and only roughly balances bytes per CTA.
   struct Cfg { int tiles, kchunks, cpu /*chunks per unit*/, first; };
   const Cfg cfg[MG_PH] = {
-      {QKV_N / MG_BM, D / MG_BK, 2, 0},                 // qkv: 9 tiles x 7 splits = 63 units
-      {D / MG_BM, D / MG_BK, 2, 63},                    // o: 7 x 7 = 49 units
+      {QKV_N / MG_BM, D / MG_BK, MG_CPU_QKV, 0},        // qkv: 9 tiles x 7 splits = 63 units
+      {D / MG_BM, D / MG_BK, MG_CPU_O, 63},             // o: 7 x 7 = 49 units
       {2 * DFF / MG_BM, D / MG_BK, D / MG_BK, G - 76},  // gate|up (interleaved rows): 76 tiles, whole K (SwiGLU in the epilogue)
-      {D / MG_BM, DFF / MG_BK, 8, 0},                   // down: 7 tiles x 10 splits = 70 units
+      {D / MG_BM, DFF / MG_BK, MG_CPU_DOWN, 0},         // down: 7 tiles x 10 splits = 70 units
   };
   std::vector<MegaUnit> units((size_t)MG_PH * G, MegaUnit{0, 0, 0, 0});
   for (int ph = 0; ph < MG_PH; ++ph) {
     const int splits = ceil_div(cfg[ph].kchunks, cfg[ph].cpu);
     mg->splits[ph] = splits;
+    CVK_REQUIRE(ph == 2 || splits == (ph == 0 ? MG_SPL_QKV : ph == 1 ? MG_SPL_O : MG_SPL_DOWN), "lm mega: split constants out of sync");
     CVK_REQUIRE(cfg[ph].tiles * splits <= G, "lm mega: more units than CTAs in a phase");
     for (int t = 0; t < cfg[ph].tiles; ++t)
       for (int s = 0; s < splits; ++s) {
@@ -535,9 +563,8 @@ void lm_mega_layers(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s, int B) {
   const LlmModel* m = ctx->llm;
   const LmMega* mg = m->mega;
   const MegaSession* ms = (const MegaSession*)s->mega_state;
-  CVK_REQUIRE(mg && ms && B >= 1 && B <= 64, "lm mega: not initialised");
+  CVK_REQUIRE(mg && ms && B >= 1 && B <= 64 && m->num_layers <= MG_MAX_LAYERS, "lm mega: not initialised");
   const int bpad = B <= 32 ? 32 : 64;
-  const CUtensorMap tm_xn = act_map(ctx, s->xn, B, D, bpad), tm_att = act_map(ctx, s->att, B, D, bpad), tm_ffa = act_map(ctx, s->ffa, B, DFF, bpad);
   MegaParams p;
   p.wstream = mg->wstream; p.cta_off = mg->cta_off; p.cta_bpl = mg->cta_bpl; p.units = mg->units; p.layers = mg->layers;
   p.num_layers = m->num_layers; p.B = B; p.max_ctx = s->max_ctx;
@@ -559,7 +586,7 @@ void lm_mega_layers(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s, int B) {
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = ctx->mega_coop ? 1 : 0;
-  if (bpad == 32) CVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lm_mega_kernel<32>, tm_xn, tm_att, tm_ffa, p));
-  else CVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lm_mega_kernel<64>, tm_xn, tm_att, tm_ffa, p));
+  if (bpad == 32) CVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lm_mega_kernel<32>, p));
+  else CVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lm_mega_kernel<64>, p));
   ctx->launches++;
 }

@@ -78,7 +78,10 @@ class B200CosyVoice2Model:
         self.stream = torch.cuda.Stream(self.device)     # every library call of this model runs on this stream
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(1986)
-        self._sessions = {}
+        self._free_sessions = {}             # (B, ctx rounded to 256) -> idle cvk_lm_session handles (see _checkout_session)
+        self._session_lru = []               # keys of idle sessions, least recently returned first
+        self.max_idle_sessions = 4
+        self._pool_lock = threading.Lock()
         self._lm_streams = []
         self.lm_chains = 1                   # independent decode chains run concurrently (see lm_generate)
         self._window = torch.from_numpy(self.speech_window).float().to(self.device)
@@ -117,90 +120,122 @@ class B200CosyVoice2Model:
         raise RuntimeError("B200CosyVoice2Model has no vLLM path (the LM runs in libcvk)")
 
     # ---------------------------------------------------------------- LM (llm/llm.py:458-549), batched
-    def _session(self, B, ctx_len, chain=0):
-        key = (B, (ctx_len + 255) // 256 * 256, chain)
-        if key not in self._sessions:
-            self._sessions[key] = self.ctx.lm_session(key[0], key[1])
-        return self._sessions[key]
+    def _checkout_session(self, B, ctx_len):
+        """An LM session (KV cache + decode buffers + captured step graph) is owned by ONE generation from prefill to the last
+        token: the reference keeps per-request state keyed by uuid (cli/model.py:334-337) and serves overlapping tts() calls
+        from threads, so two requests of similar shape must never share a KV cache.  Idle sessions are kept for re-use
+        (creating one allocates hundreds of MB at batch 32) and the idle pool is bounded (LRU, cvk_lm_session_destroy)."""
+        key = (B, (ctx_len + 255) // 256 * 256)
+        with self._pool_lock:
+            free = self._free_sessions.get(key)
+            if free:
+                self._session_lru.remove(key)
+                return key, free.pop()
+        return key, self.ctx.lm_session(*key)
 
-    def lm_generate(self, texts, prompt_texts, prompt_speech_tokens, uniforms=None, steps_per_sync=32, on_progress=None):
+    def _new_lm_stream(self):
+        return torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def _checkin_session(self, key, sess):
+        evict = []
+        with self._pool_lock:
+            self._free_sessions.setdefault(key, []).append(sess)
+            self._session_lru.append(key)
+            while len(self._session_lru) > self.max_idle_sessions:
+                k = self._session_lru.pop(0)
+                evict.append(self._free_sessions[k].pop(0))
+        for e in evict:
+            self.ctx.lm_session_destroy(e)
+
+    def lm_generate(self, texts, prompt_texts, prompt_speech_tokens, uniforms=None, steps_per_sync=32, on_progress=None, stream=None):
         """texts/prompt_texts/prompt_speech_tokens: lists of int32 tensors [1,n].  Returns a list of python id lists.
 
-        The decode step is latency-bound (small kernels on a fraction of the SMs), so the rows are split into
-        `self.lm_chains` independent groups, each with its own KV session, CUDA graph and stream: the chains' kernels
-        interleave on the GPU and hide each other's latencies.  Results are independent of the grouping (rows never
-        interact; every row consumes its own uniforms)."""
+        `stream`: CUDA stream for this generation (default: the model's stream).  Only the prefill uses the shared workspace and
+        takes `ctx.lock`; the decode calls touch nothing but their own session (include/cvk.h threading rules), so a request's
+        LM job on its own stream overlaps another request's - or its own - flow / vocoder calls like the reference's LM thread
+        does (cli/model.py:101-129, 268).
+
+        `self.lm_chains > 1` splits the rows into independent groups, each with its own KV session, CUDA graph and stream (an
+        experiment knob from the per-op decode chain; with the persistent decode kernel one chain is best).  Results are
+        independent of the grouping (rows never interact; every row consumes its own uniforms)."""
         B = len(texts)
         d = self.device
+        main = stream if stream is not None else self.stream
         chains = 1 if on_progress is not None else max(1, min(self.lm_chains, B))
         groups = [list(range(g, B, chains)) for g in range(chains)]
         mins = [int(t.shape[1] * self.min_token_text_ratio) for t in texts]      # llm.py:497-498
         maxs = [int(t.shape[1] * self.max_token_text_ratio) for t in texts]
         mx = max(maxs)
         st = []
-        with torch.cuda.stream(self.stream):
-            if uniforms is None and self.uniforms_override is not None:
-                uniforms = self.uniforms_override
-            if uniforms is None:
-                uniforms = torch.rand(mx + 1, B, 2, device=d, generator=self.generator)
-            uniforms = uniforms.to(d).float()
-            for g, rows in enumerate(groups):
-                tl = [int(texts[r].shape[1] + prompt_texts[r].shape[1]) for r in rows]
-                sl = [int(prompt_speech_tokens[r].shape[1]) for r in rows]
-                tt = torch.cat([torch.cat([prompt_texts[r].reshape(-1).to(d, non_blocking=True), texts[r].reshape(-1).to(d, non_blocking=True)])
-                                for r in rows]).to(torch.int32)
-                ss = torch.cat([prompt_speech_tokens[r].reshape(-1).to(d, non_blocking=True) for r in rows]).to(torch.int32) if sum(sl) \
-                    else torch.zeros(1, dtype=torch.int32, device=d)
-                c = dict(rows=rows, n=len(rows),
-                         min_len=torch.tensor([mins[r] for r in rows], dtype=torch.int32, device=d),
-                         max_len=torch.tensor([maxs[r] for r in rows], dtype=torch.int32, device=d),
-                         sess=self._session(len(rows), max(a + b2 for a, b2 in zip(tl, sl)) + 2 + mx + 8, g),
-                         out_ids=torch.zeros(len(rows), mx + 1, dtype=torch.int32, device=d),
-                         out_count=torch.zeros(len(rows), dtype=torch.int32, device=d),
-                         done=torch.zeros(len(rows), dtype=torch.int32, device=d),
-                         U=uniforms[:, rows, :].contiguous(), live=len(rows))
-                with self.ctx.lock:
-                    self.ctx.lm_prefill(c["sess"], tt, tl, ss, sl)        # prefills share the workspace arena: one stream, in order
-                st.append(c)
-            ready = torch.cuda.Event()
-            ready.record(self.stream)
-        while len(self._lm_streams) < chains:
-            self._lm_streams.append(torch.cuda.Stream(d))
-        n = 0
-        while True:
+        try:
+            with torch.cuda.stream(main):
+                if uniforms is None and self.uniforms_override is not None:
+                    uniforms = self.uniforms_override
+                if uniforms is None:
+                    with self.lock:                                  # one device generator shared by the request threads
+                        uniforms = torch.rand(mx + 1, B, 2, device=d, generator=self.generator)
+                uniforms = uniforms.to(d).float()
+                for g, rows in enumerate(groups):
+                    tl = [int(texts[r].shape[1] + prompt_texts[r].shape[1]) for r in rows]
+                    sl = [int(prompt_speech_tokens[r].shape[1]) for r in rows]
+                    tt = torch.cat([torch.cat([prompt_texts[r].reshape(-1).to(d, non_blocking=True), texts[r].reshape(-1).to(d, non_blocking=True)])
+                                    for r in rows]).to(torch.int32)
+                    ss = torch.cat([prompt_speech_tokens[r].reshape(-1).to(d, non_blocking=True) for r in rows]).to(torch.int32) if sum(sl) \
+                        else torch.zeros(1, dtype=torch.int32, device=d)
+                    key, sess = self._checkout_session(len(rows), max(a + b2 for a, b2 in zip(tl, sl)) + 2 + mx + 8)
+                    c = dict(rows=rows, n=len(rows), key=key, sess=sess,
+                             min_len=torch.tensor([mins[r] for r in rows], dtype=torch.int32, device=d),
+                             max_len=torch.tensor([maxs[r] for r in rows], dtype=torch.int32, device=d),
+                             out_ids=torch.zeros(len(rows), mx + 1, dtype=torch.int32, device=d),
+                             out_count=torch.zeros(len(rows), dtype=torch.int32, device=d),
+                             done=torch.zeros(len(rows), dtype=torch.int32, device=d),
+                             U=uniforms[:, rows, :].contiguous(), live=len(rows))
+                    st.append(c)
+                    with self.ctx.lock:
+                        self.ctx.lm_prefill(sess, tt, tl, ss, sl)         # prefills share the workspace arena: serialised
+                ready = torch.cuda.Event()
+                ready.record(main)
+            while len(self._lm_streams) < chains:
+                self._lm_streams.append(torch.cuda.Stream(d))
+            n = 0
+            while True:
+                for g, c in enumerate(st):
+                    if c["live"] == 0:
+                        continue
+                    s_g = main if chains == 1 else self._lm_streams[g]
+                    with torch.cuda.stream(s_g):
+                        if n == 0:
+                            s_g.wait_event(ready)
+                        self.ctx.lm_decode(c["sess"], steps_per_sync, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"],
+                                           want_live=False)
+                for g, c in enumerate(st):
+                    if c["live"] == 0:
+                        continue
+                    s_g = main if chains == 1 else self._lm_streams[g]
+                    with torch.cuda.stream(s_g):
+                        c["live"] = self.ctx.lm_decode(c["sess"], 0, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"])
+                n += steps_per_sync
+                if on_progress is not None:
+                    on_progress(st[0]["out_ids"], st[0]["out_count"], st[0]["live"])
+                if all(c["live"] == 0 for c in st) or n > mx + steps_per_sync:
+                    break
+            out = [None] * B
             for g, c in enumerate(st):
-                if c["live"] == 0:
-                    continue
-                stream = self.stream if chains == 1 else self._lm_streams[g]
-                with torch.cuda.stream(stream), self.ctx.lock:
-                    if n == 0:
-                        stream.wait_event(ready)
-                    self.ctx.lm_decode(c["sess"], steps_per_sync, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"],
-                                       want_live=False)
-            for g, c in enumerate(st):
-                if c["live"] == 0:
-                    continue
-                stream = self.stream if chains == 1 else self._lm_streams[g]
-                with torch.cuda.stream(stream), self.ctx.lock:
-                    c["live"] = self.ctx.lm_decode(c["sess"], 0, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"])
-            n += steps_per_sync
-            if on_progress is not None:
-                on_progress(st[0]["out_ids"], st[0]["out_count"], st[0]["live"])
-            if all(c["live"] == 0 for c in st) or n > mx + steps_per_sync:
-                break
-        out = [None] * B
-        for g, c in enumerate(st):
-            with torch.cuda.stream(self.stream if chains == 1 else self._lm_streams[g]):
-                cnt = c["out_count"].cpu().tolist()
-                ids = c["out_ids"].cpu()
-            for i, r in enumerate(c["rows"]):
-                out[r] = ids[i, :cnt[i]].tolist()
-        if chains > 1:
-            for g in range(chains):
-                self.stream.wait_stream(self._lm_streams[g])
-        return out
+                with torch.cuda.stream(main if chains == 1 else self._lm_streams[g]):
+                    cnt = c["out_count"].cpu().tolist()
+                    ids = c["out_ids"].cpu()
+                for i, r in enumerate(c["rows"]):
+                    out[r] = ids[i, :cnt[i]].tolist()
+            if chains > 1:
+                for g in range(chains):
+                    main.wait_stream(self._lm_streams[g])
+            return out
+        finally:
+            main.synchronize()                     # the session goes back to the pool only when its last kernel has finished
+            for c in st:
+                self._checkin_session(c["key"], c["sess"])
 
-    def lm_generate_bistream(self, text, prompt_text, prompt_speech_token, uniforms=None):
+    def lm_generate_bistream(self, text, prompt_text, prompt_speech_token, uniforms=None, stream=None):
         """llm/llm.py:551-661 (Qwen2LM.inference_bistream): `text` is a generator of int32 [1,k] chunks; speech ids are yielded
         as soon as they are decoded.  The interleaving (5 text : 15 speech), the forced / sampled fill tokens and the final
         'decode until eos' phase are the reference's control flow line for line; the arithmetic runs on the device through
@@ -220,8 +255,9 @@ class B200CosyVoice2Model:
             lm_prefix, ptext = [(TEXT, t) for t in ptext[:eop + 1]], ptext[eop + 1:]
         pspeech = [int(x) for x in prompt_speech_token.reshape(-1).tolist()]
         max_ctx = 4096
-        with torch.cuda.stream(self.stream), self.ctx.lock:
-            sess = self._session(1, max_ctx - 8, chain=-1)
+        lm_stream = stream if stream is not None else self.stream
+        key, sess = self._checkout_session(1, max_ctx - 8)
+        with torch.cuda.stream(lm_stream):
             self.ctx.lm_begin(sess, 1)
         if uniforms is None and self.uniforms_override is not None:
             uniforms = self.uniforms_override[:, 0, :]
@@ -236,7 +272,7 @@ class B200CosyVoice2Model:
 
         def forward(want_logp):
             """llm.py:617-622: push lm_input through the cached model; log-probs of the next id"""
-            with torch.cuda.stream(self.stream), self.ctx.lock:
+            with torch.cuda.stream(lm_stream):
                 fed[0] += len(lm_input)
                 if fed[0] >= max_ctx - 16:
                     raise RuntimeError("text-streaming LM: session context exhausted")
@@ -245,57 +281,66 @@ class B200CosyVoice2Model:
 
         def sample(logp, ignore_eos):
             """llm.py:627 / 650 sampling_ids"""
-            with torch.cuda.stream(self.stream), self.ctx.lock:
+            with torch.cuda.stream(lm_stream):
                 i = len(out_tokens)
-                u = uniforms[i].reshape(1, 2) if uniforms is not None else torch.rand(1, 2, device=d, generator=self.generator)
+                if uniforms is not None:
+                    u = uniforms[i].reshape(1, 2)
+                else:
+                    with self.lock:
+                        u = torch.rand(1, 2, device=d, generator=self.generator)
                 hist = torch.tensor([out_tokens[-16:] or [0]], dtype=torch.int32)
                 top = self.ctx.ras_sample(logp, hist, torch.tensor([min(len(out_tokens), 16)], dtype=torch.int32), u,
                                           torch.tensor([1 if ignore_eos else 0], dtype=torch.int32))
                 return int(top.item())
 
-        for this_text in text:
-            text_cache += [int(x) for x in this_text.reshape(-1).tolist()]
-            while pspeech:                                            # llm.py:595-604
-                if len(text_cache) >= mix_text:
-                    lm_input = lm_input + [(TEXT, t) for t in text_cache[:mix_text]] + [(SPEECH, t) for t in pspeech[:mix_speech]]
-                    text_cache, pspeech = text_cache[mix_text:], pspeech[mix_speech:]
-                else:
-                    break
-            if not pspeech:                                           # llm.py:606-640
-                if (out_tokens and out_tokens[-1] == fill_token) or (not out_tokens and len(lm_input) == 1):
+        try:
+            for this_text in text:
+                text_cache += [int(x) for x in this_text.reshape(-1).tolist()]
+                while pspeech:                                            # llm.py:595-604
                     if len(text_cache) >= mix_text:
-                        lm_text = [(TEXT, t) for t in text_cache[:mix_text]]
-                        lm_input = lm_text if (out_tokens and out_tokens[-1] == fill_token) else lm_input + lm_text
-                        text_cache = text_cache[mix_text:]
+                        lm_input = lm_input + [(TEXT, t) for t in text_cache[:mix_text]] + [(SPEECH, t) for t in pspeech[:mix_speech]]
+                        text_cache, pspeech = text_cache[mix_text:], pspeech[mix_speech:]
                     else:
-                        continue
-                while True:
-                    forced = next_fill_index != -1 and len(out_tokens) == next_fill_index
-                    logp = forward(want_logp=not forced)              # the reference runs the model before overriding the draw
-                    if forced:
-                        top = fill_token
-                        next_fill_index += mix_speech + 1
-                    else:
-                        top = sample(logp, ignore_eos=True)
-                    if top == fill_token:
-                        next_fill_index = len(out_tokens) + mix_speech + 1
-                    out_tokens.append(top)
-                    if top >= speech_vocab:
+                        break
+                if not pspeech:                                           # llm.py:606-640
+                    if (out_tokens and out_tokens[-1] == fill_token) or (not out_tokens and len(lm_input) == 1):
+                        if len(text_cache) >= mix_text:
+                            lm_text = [(TEXT, t) for t in text_cache[:mix_text]]
+                            lm_input = lm_text if (out_tokens and out_tokens[-1] == fill_token) else lm_input + lm_text
+                            text_cache = text_cache[mix_text:]
+                        else:
+                            continue
+                    while True:
+                        forced = next_fill_index != -1 and len(out_tokens) == next_fill_index
+                        logp = forward(want_logp=not forced)              # the reference runs the model before overriding the draw
+                        if forced:
+                            top = fill_token
+                            next_fill_index += mix_speech + 1
+                        else:
+                            top = sample(logp, ignore_eos=True)
                         if top == fill_token:
-                            break
-                        raise ValueError(f"should not get token {top}")
-                    yield top
-                    lm_input = [(SPEECH, top)]
-        lm_input = lm_input + [(TEXT, t) for t in text_cache] + [(LLM, 1)]       # llm.py:643
-        while True:
-            top = sample(forward(want_logp=True), ignore_eos=False)
-            out_tokens.append(top)
-            if top >= speech_vocab:
-                if top == eos_token:
-                    break
-                raise ValueError(f"should not get token {top}")
-            yield top
-            lm_input = [(SPEECH, top)]
+                            next_fill_index = len(out_tokens) + mix_speech + 1
+                        out_tokens.append(top)
+                        if top >= speech_vocab:
+                            if top == fill_token:
+                                break
+                            raise ValueError(f"should not get token {top}")
+                        yield top
+                        lm_input = [(SPEECH, top)]
+            lm_input = lm_input + [(TEXT, t) for t in text_cache] + [(LLM, 1)]       # llm.py:643
+            while True:
+                top = sample(forward(want_logp=True), ignore_eos=False)
+                out_tokens.append(top)
+                if top >= speech_vocab:
+                    if top == eos_token:
+                        break
+                    raise ValueError(f"should not get token {top}")
+                yield top
+                lm_input = [(SPEECH, top)]
+        finally:
+            if lm_stream is not None:
+                lm_stream.synchronize()
+            self._checkin_session(key, sess)
 
     # ---------------------------------------------------------------- flow + vocoder
     def flow_batch(self, tokens, prompt_tokens, prompt_feats, embeddings, streaming=False, finalize=True):
@@ -396,7 +441,7 @@ class B200CosyVoice2Model:
         if hasattr(text, "__next__") or (hasattr(text, "__iter__") and not torch.is_tensor(text)):
             # cli/model.py:113-123: text generator -> bi-stream decoding, tokens appended one by one
             cur_silent, max_silent = 0, 5                  # cli/model.py:102,121-127 (silent_tokens is empty for CosyVoice2)
-            for tok in self.lm_generate_bistream(iter(text), prompt_text, llm_prompt_speech_token):
+            for tok in self.lm_generate_bistream(iter(text), prompt_text, llm_prompt_speech_token, stream=self._new_lm_stream()):
                 if tok in self.silent_tokens:
                     cur_silent += 1
                     if cur_silent > max_silent:
@@ -421,7 +466,10 @@ class B200CosyVoice2Model:
                         st["silent"] = 0
                     self.tts_speech_token_dict[uuid].append(tok)
                 st["consumed"] = n
-        self.lm_generate([text], [prompt_text], [llm_prompt_speech_token], steps_per_sync=8, on_progress=progress)
+        # the LM job decodes on its own stream (cli/model.py:103: `with self.llm_context`, a side stream) while token2wav runs on
+        # the model's stream
+        self.lm_generate([text], [prompt_text], [llm_prompt_speech_token], steps_per_sync=8, on_progress=progress,
+                         stream=self._new_lm_stream())
         self.llm_end_dict[uuid] = True
 
     def vc_job(self, source_speech_token, uuid):

@@ -10,8 +10,15 @@
  *    allocates it); the library owns only its repacked weights, KV arena and workspace, all inside cvk_ctx.
  *  - Activations cross the ABI as *ragged time-major* fp32 matrices: the B sequences are concatenated along
  *    rows without padding, `lens_host[b]` rows each, channels contiguous ([sum(lens), C]).
- *  - Every call takes an explicit cudaStream_t (passed as void*), never touches the default stream on its own
- *    and never calls cudaDeviceSynchronize.  Calls on one ctx must be serialised by the caller (one workspace).
+ *  - Every data-path call takes an explicit cudaStream_t (passed as void*), never touches the default stream on its own
+ *    and never calls cudaDeviceSynchronize (set-up calls - cvk_create / cvk_set_tensor / cvk_finalize / cvk_profile /
+ *    cvk_destroy - repack weights on the default stream and block until done).
+ *  - Threading: calls that use the ctx workspace (cvk_lm_prefill, cvk_lm_forward_logp, every flow / vocoder / mel / op
+ *    call) must be serialised by the caller.  Calls that only touch an LM session (cvk_lm_decode, cvk_lm_begin,
+ *    cvk_lm_feed, cvk_lm_next_logp, cvk_lm_last_logits) and cvk_ras_sample own no shared state: they may run
+ *    concurrently with workspace calls and with each other on DISTINCT sessions and streams - this is the reference's
+ *    own concurrency (LM side thread + side stream next to token2wav, cli/model.py:101-129, 268; several requests in
+ *    flight, runtime/python/grpc/server.py:69).  One session is never used by two host threads at once.
  *  - Return value: 0 on success, a negative cvk_status otherwise; cvk_last_error(ctx) holds the message.  No C++
  *    exception crosses the ABI.  There is NO CPU fallback: without a CUDA device cvk_create fails.
  */

@@ -12,6 +12,14 @@ import torch
 from oracle import cases, lm, sampling
 
 
+def _pool(m):
+    """session-pool attributes B200CosyVoice2Model.__init__ creates"""
+    m._free_sessions, m._session_lru, m.max_idle_sessions, m._pool_lock = {}, [], 4, threading.Lock()
+    if not hasattr(m, "lock"):
+        m.lock = threading.Lock()
+    return m
+
+
 class FakeLmContext:
     """cvk_lm_begin / cvk_lm_feed / cvk_lm_next_logp / cvk_ras_sample semantics on oracle.lm.qwen2_forward"""
 
@@ -23,6 +31,9 @@ class FakeLmContext:
 
     def lm_session(self, B, ctx_len):
         return object()
+
+    def lm_session_destroy(self, sess):
+        pass
 
     def lm_begin(self, sess, B=1):
         self.past, self.hidden = None, None
@@ -49,9 +60,9 @@ def _model_with(ctx):
     from cosyvoice_b200.model import B200CosyVoice2Model
     m = object.__new__(B200CosyVoice2Model)          # no device: only the attributes the host logic touches
     m.ctx, m.stream, m.device = ctx, None, torch.device("cpu")
-    m._sessions, m.uniforms_override, m.generator = {}, None, None
+    m.uniforms_override, m.generator = None, None
     m.silent_tokens = []
-    return m
+    return _pool(m)
 
 
 def test_bistream_host_logic_matches_reference(golden):
@@ -97,7 +108,8 @@ def test_bistream3_host_logic_matches_reference(golden):
     ctx = FakeLm3Context(lm.bistream_state_dict3(2), 2)
     m = object.__new__(B200CosyVoice3Model)
     m.ctx, m.stream, m.device = ctx, None, torch.device("cpu")
-    m._sessions, m.uniforms_override, m.generator = {}, None, None
+    m.uniforms_override, m.generator = None, None
+    _pool(m)
     ids = list(m.lm_generate_bistream(iter(chunks), ptext, ptok, uniforms=U))
     assert ids == g["ids"].tolist() and int(g["trace"][-1]) == 6562
     # first model call: sos + the 3 prompt-text ids up to <|endofprompt|> + (5 text, 15 speech) + (5 text, 7 speech)
@@ -155,6 +167,9 @@ class FakeCtx3:
     # ---- LM: prefill stores the prompt, decode releases the oracle's ids n_steps at a time
     def lm_session(self, B, ctx_len):
         return {"ids": None, "emitted": 0}
+
+    def lm_session_destroy(self, sess):
+        pass
 
     def lm_prefill(self, sess, tt, tl, ss, sl):
         sess.update(tt=tt.clone(), ss=ss.clone(), ids=None, emitted=0)
@@ -218,7 +233,8 @@ def test_cosyvoice3_model_host_glue_matches_reference(golden, monkeypatch):
     for mode, stream in (("offline", False), ("stream", True)):
         m = object.__new__(B200CosyVoice3Model)
         m.ctx, m.stream, m.device = ctx, _DummyStream(), torch.device("cpu")
-        m._sessions, m._lm_streams, m.lm_chains = {}, [_DummyStream()], 1
+        m._lm_streams, m.lm_chains = [_DummyStream()], 1
+        _pool(m)
         m.uniforms_override, m.noise_fn, m.generator = U[:, None, :], None, None
         m.lock = threading.Lock()
         m.tts_speech_token_dict, m.llm_end_dict, m.hift_cache_dict = {}, {}, {}
@@ -305,7 +321,8 @@ def test_cosyvoice2_model_host_glue_matches_reference(golden, monkeypatch):
             return z
         m = object.__new__(B200CosyVoice2Model)
         m.ctx, m.stream, m.device = ctx, _DummyStream(), torch.device("cpu")
-        m._sessions, m._lm_streams, m.lm_chains = {}, [_DummyStream()], 1
+        m._lm_streams, m.lm_chains = [_DummyStream()], 1
+        _pool(m)
         m.uniforms_override, m.noise_fn, m.generator = U[:, None, :], noise_fn, None
         m.lock = threading.Lock()
         m.tts_speech_token_dict, m.llm_end_dict, m.hift_cache_dict = {}, {}, {}

@@ -118,3 +118,40 @@ def test_tts_with_text_generator_bistream(golden):
     # first chunk: hop 25 + pad to a multiple of 25 of the 9 prompt tokens (cli/model.py:347-350) = 41 tokens minus the 8-frame
     # mel cache kept back (3840 samples)
     assert outs[0].shape[1] == 41 * 960 - 3840
+
+
+def test_overlapping_tts_requests_do_not_share_lm_sessions(golden):
+    """The reference serves tts() from one thread per request with per-request state keyed by uuid (cli/model.py:334-337).  Two
+    overlapping requests of the same shape must each own an LM session (KV cache + decode graph) from prefill to the last token:
+    run two tts() calls from two threads at once and require both to reproduce the reference's audio.  (Round 1 cached sessions
+    by shape, so the second prefill overwrote the first request's KV cache mid-decode.)"""
+    import threading
+    g = golden("stream_tts")
+    m = model()
+    req, U = request()
+    m.uniforms_override = U[:, None, :]
+    n = 140 * 960
+    m.noise_fn = lambda k: stream_noise(0, n).to(m.device) if k == n else torch.randn(k, 9, device=m.device)
+    outs, errs = {}, []
+
+    def run(i):
+        try:
+            outs[i] = torch.cat([o["tts_speech"] for o in m.tts(**req, stream=False)], 1)
+        except Exception as e:              # noqa: BLE001
+            errs.append(e)
+    try:
+        ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    finally:
+        m.uniforms_override, m.noise_fn = None, None
+    assert not errs, errs
+    ref = torch.from_numpy(g["offline_wav"])
+    for i in range(2):
+        assert outs[i].shape == ref.shape
+        assert maxdiff(outs[i][:, :24000], ref[:, :24000]) < 5e-3
+    # the idle pool holds both sessions now and stays bounded
+    assert sum(len(v) for v in m._free_sessions.values()) >= 2
+    assert len(m._session_lru) <= m.max_idle_sessions

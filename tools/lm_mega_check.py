@@ -99,4 +99,4 @@ if a.timeline:
     ch = t[:16]
     print("chain stamps (head, head_finish, sampler) entry/waited/end us rel:", [round((x - ch[0]) / 1e3, 2) if x else 0 for x in ch[:12]])
     if mg[0] and ch[0]:
-        print(f"sampler end -> mega start: {(mg[0] - ch[10]) / 1e3:.2f} us; step (head waited -> mega end): {(mg[7 * a.layers] - ch[1]) / 1e3:.1f} us")
+        print(f"sampler past pdl_wait -> mega first stamp: {(mg[0] - ch[9]) / 1e3:.2f} us; step (head waited -> mega end): {(mg[7 * a.layers] - ch[1]) / 1e3:.1f} us")
