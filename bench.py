@@ -7,7 +7,8 @@ the whole pipeline over one batch of 32 ragged utterances per GPU.
 
   python bench.py --gpus 1 --steps 3 --warmup 3            # ours (default)
   python bench.py --impl reference --steps 1 --warmup 0    # the reference's algorithm on the host CPU cores
-  torchrun --nnodes=1 --nproc-per-node N bench.py --gpus N ...   (N > 1: one rank per GPU, weak scaling)
+  torchrun --nnodes=1 --nproc-per-node N bench.py --gpus N ...   (N > 1: one rank per GPU; primary = the same 32 requests
+                                                                   sharded over the ranks, "weak" key = 32 requests per rank)
 
 Prints ONE JSON line on rank 0 (contract in the task statement): value = device-resident throughput, e2e = the same
 metric through the public API with host buffers (H2D of the request tensors, D2H of the waveforms inside the timed
@@ -204,7 +205,7 @@ def run_ours(args):
         dist = None
     from cosyvoice_b200 import synth
     from cosyvoice_b200.model import B200CosyVoice2Model
-    from cosyvoice_b200.parallel import broadcast_state_dicts, gather_waveforms
+    from cosyvoice_b200.parallel import broadcast_state_dicts, gather_flat, shard_lpt
     dev = torch.device("cuda", local)
     full = not args.small
     nl, fcfg = (24, (6, 4, 12, 4)) if full else (2, (2, 1, 2, 2))
@@ -221,19 +222,6 @@ def run_ours(args):
         k, v = kv.split("=")
         model.ctx.set_option(k, int(v))
     batch = args.batch
-    inputs = synth.batch32_zero_shot(batch, base=rank * batch)              # weak scaling: every rank its own 32 requests
-    h2d = sum(sum(v.numel() * v.element_size() for v in i.values()) for i in inputs)
-
-    def to_dev(i):
-        return {k: v.to(dev) for k, v in i.items()}
-    inputs_dev = [to_dev(i) for i in inputs]
-    pinned = [{k: v.pin_memory() for k, v in i.items()} for i in inputs]
-
-    def step_device():
-        return model.tts_batch(inputs_dev, to_host=False, return_stats=True)
-
-    def step_e2e():
-        return model.tts_batch(pinned, to_host=True, return_stats=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,101 +229,128 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    # ---- timed region 1: device-resident inputs, waveforms left in HBM
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    l0 = model.ctx.launch_count()
+    def measure(inputs, counts, want_clocks):
+        """K timed steps device-resident (`value`) + K timed steps end to end (`e2e`: pinned host inputs -> H2D inside the step ->
+        pipeline -> device-resident gather of every rank's waveform buffer on rank 0 -> one pinned D2H)."""
+        inputs_dev = [{k: v.to(dev) for k, v in i.items()} for i in inputs]
+        pinned = [{k: v.pin_memory() for k, v in i.items()} for i in inputs]
+        h2d = sum(sum(v.numel() * v.element_size() for v in i.values()) for i in inputs)
+        for _ in range(args.warmup):
+            model.tts_batch_device(inputs_dev)
+        # ---- timed region 1: inputs resident in HBM, waveforms left in HBM, no per-launch instrumentation
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0 and want_clocks:
+            sampler.start()
+        l0 = model.ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(model.stream)
+        audio_s, stats = 0.0, None
+        for _ in range(args.steps):
+            _, n, stats = model.tts_batch_device(inputs_dev)
+            audio_s += sum(n) / 24000.0
+        e1.record(model.stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        wall_ms = 1000 * (time.perf_counter() - t0)
+        launches = model.ctx.launch_count() - l0
+        clocks = sampler.stop() if (rank == 0 and want_clocks) else None
+        stats = model._stage_ms(stats)
+        # ---- timed region 2: end to end through the public API
+        with torch.cuda.stream(model.stream):
+            wav, n, _ = model.tts_batch_device(pinned)
+            gather_flat(wav, [k for k in n if k], dist, dev, counts)        # untimed: NCCL sets up its point-to-point channels on first use
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(model.stream)
+        audio_e2e, d2h = 0.0, 0
+        for _ in range(args.steps):
+            with torch.cuda.stream(model.stream):
+                wav, n, _ = model.tts_batch_device(pinned)
+                got = gather_flat(wav, [k for k in n if k], dist, dev, counts)
+            audio_e2e += sum(n) / 24000.0
+            if got is not None:
+                d2h = got[0].numel() * 4
+        f1.record(model.stream)
+        barrier()
+        e2e_ms = max(f0.elapsed_time(f1), 1000 * (time.perf_counter() - t0))
+        # ---- max over ranks, totals over ranks
+        tt = torch.tensor([dev_ms, e2e_ms, wall_ms], device=dev, dtype=torch.float64)
+        aa = torch.tensor([audio_s, audio_e2e, float(launches), float(h2d)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(aa, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, wall_ms = tt.tolist()
+        audio_s, audio_e2e, launches, h2d_all = aa.tolist()
+        return dict(value=audio_s / (dev_ms / 1000.0), e2e=audio_e2e / (e2e_ms / 1000.0), dev_ms=dev_ms, e2e_ms=e2e_ms, wall_ms=wall_ms,
+                    launches=int(launches), h2d=int(h2d_all), d2h=int(d2h), clocks=clocks, stats=stats, inputs=inputs)
+
+    # ---- primary: the contract's split - the SAME `batch` utterances sharded over the ranks (strong scaling), LPT on expected tokens
+    all_inputs = synth.batch32_zero_shot(batch)
+    plan = shard_lpt([int(i["text"].shape[1] * TOKEN_RATIO) for i in all_inputs], world)
+    strong = measure([all_inputs[i] for i in plan[rank]], [len(p) for p in plan], True)
+    # ---- one extra instrumented step (CUDA events around every GEMM / attention launch) for the per-family roofline
     model.ctx.profile(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(model.stream)
-    audio_s, stats = 0.0, None
-    for _ in range(args.steps):
-        wavs, stats = step_device()
-        audio_s += sum(w.shape[-1] for w in wavs) / 24000.0
-    e1.record(model.stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    wall_ms = 1000 * (time.perf_counter() - t0)
-    launches = model.ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    model.tts_batch_device([{k: v.to(dev) for k, v in i.items()} for i in strong["inputs"]])
+    torch.cuda.synchronize()
     prof = [model.ctx.profile_read(f) for f in range(3)]
     model.ctx.profile(0)
-    # ---- timed region 2: end to end through the public API (pinned host inputs in, waveforms out to host)
-    wavs, _ = step_e2e()
-    if dist is not None:
-        gather_waveforms(wavs, dist, dev)              # untimed: NCCL sets up its point-to-point channels on first use
-    barrier()
-    t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(model.stream)
-    audio_e2e, d2h = 0.0, 0
-    for _ in range(args.steps):
-        wavs, _ = step_e2e()
-        audio_e2e += sum(w.shape[-1] for w in wavs) / 24000.0
-        d2h = sum(w.numel() * 4 for w in wavs)
-        if dist is not None:
-            gather_waveforms(wavs, dist, dev)                                # NCCL gather of the results on rank 0
-    f1.record(model.stream)
-    barrier()
-    e2e_ms = max(f0.elapsed_time(f1), 1000 * (time.perf_counter() - t0))
-    # ---- max over ranks, totals over ranks
-    tt = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    aa = torch.tensor([audio_s, audio_e2e, float(launches)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(aa, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms = tt.tolist()
-    audio_s, audio_e2e, launches = aa.tolist()
+    # ---- secondary: weak scaling (every rank its own `batch` requests)
+    weak = measure(synth.batch32_zero_shot(batch, base=rank * batch), [batch] * world, False) if world > 1 else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     pk = peaks()
-    value = audio_s / (dev_ms / 1000.0)
-    e2e_v = audio_e2e / (e2e_ms / 1000.0)
-    # dominant kernel family = the one with the largest share of device time
-    fam_names = ["conv_gemm_tc (tcgen05 bf16)", "conv_gemm_simt (fp32 CUDA cores)", "attention (tcgen05 flash kernel; fp32-math CUDA-core kernel for rel-pos / fp32 mode)"]
+    value, e2e_v, dev_ms = strong["value"], strong["e2e"], strong["dev_ms"]
+    # dominant kernel family = the one with the largest share of device time (instrumented step)
+    fam_names = ["conv_gemm_tc (tcgen05 bf16)", "conv_gemm_simt (fp32 CUDA cores)", "attention (tcgen05 flash kernels; fp32-math CUDA-core kernel in fp32 mode)"]
     dom = max(range(3), key=lambda f: prof[f]["ms"])
     p = prof[dom]
-    if dom == 0:
-        ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
-    else:
-        # CUDA-core kernels: report against the tensor roof they should be moved to (frac shows the gap)
-        ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+    ach = p["flops"] / (p["ms"] / 1000.0) / 1e12 if p["ms"] > 0 else 0.0
+    roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
     traffic, traffic_note = None, "no ncu capture committed for this kernel"
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
-    if dom == 0 and os.path.exists(tpath):            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from `ncu --set full`
-        tj = json.load(open(tpath))
-        traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if dom == 0 and os.path.exists(tpath):            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from `ncu --set full`
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+            break
+    step_ms = dev_ms / args.steps
     roof.update({"traffic": traffic, "traffic_note": traffic_note, "kernel": fam_names[dom], "launches": p["launches"], "avg_launch_ms": p["ms"] / max(p["launches"], 1),
-                 "share_of_step": p["ms"] / dev_ms, "peak_source": pk["source"],
+                 "share_of_step": p["ms"] / step_ms, "peak_source": pk["source"], "timed": "one extra instrumented step (not inside the `value` region)",
                  "families_ms": {fam_names[f]: prof[f]["ms"] for f in range(3)}})
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         a, w, info = cpu_reference_sample(full=full)
         cpu = {"value": a / w, "unit": "audio-sec/s", "cores": host_threads(), "kind": "port",
                "sample": f"1 of the {batch} utterances (250 speech tokens, 10 s audio): LM {info['lm_s']:.1f}s flow {info['flow_s']:.1f}s HiFT {info['hift_s']:.1f}s"}
+    stats = strong["stats"]
+    per_gpu = [len(pl) for pl in plan]
     line = {"metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"CosyVoice2-0.5B zero-shot batch-{batch} per GPU, NFE=10, ragged Z10 requests (40-60 text tokens -> 200-300 speech tokens, "
-                                   "75 prompt tokens / 150 prompt mel frames)" + ("" if full else " [SMALL DEBUG MODEL]"),
-                       "batch_per_gpu": batch, "nfe": 10, "l2": "working set (1.3 GB weights + GBs of activations) exceeds the 126 MB L2",
-                       "parallelism": f"dp{n_gpus} (independent utterances, weights broadcast once over NCCL, waveforms gathered)",
-                       "stage_ms_last_step": {k: stats[k] for k in ("lm_ms", "flow_ms", "hift_ms")}, "rtf": 1.0 / value},
-            "e2e": {"value": e2e_v, "unit": "audio-sec/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_ms_per_step": wall_ms / args.steps}
+            "config": {"workload": f"CosyVoice2-0.5B zero-shot batch-{batch} (the same {batch} ragged Z10 requests sharded over the GPUs by LPT on expected tokens: "
+                                   f"{per_gpu} per GPU), NFE=10, 40-60 text tokens -> 200-300 speech tokens, 75 prompt tokens / 150 prompt mel frames"
+                                   + ("" if full else " [SMALL DEBUG MODEL]"),
+                       "global_batch": batch, "per_gpu": per_gpu, "nfe": 10,
+                       "l2": "working set (1.3 GB weights + GBs of activations) exceeds the 126 MB L2",
+                       "parallelism": f"dp{n_gpus} (independent utterances, weights broadcast once over NCCL, waveform buffers gathered device-to-device on rank 0)",
+                       "stage_ms_last_step_rank0": {k: stats[k] for k in ("lm_ms", "flow_ms", "hift_ms")}, "rtf": 1.0 / value},
+            "e2e": {"value": e2e_v, "unit": "audio-sec/s", "h2d_bytes_per_step": strong["h2d"], "d2h_bytes_per_step": strong["d2h"]},
+            "gpu_launches": strong["launches"], "clocks": strong["clocks"], "roofline": roof, "wall_ms_per_step": strong["wall_ms"] / args.steps}
     try:                                                # per-stage view the north star asks for; never allowed to break the line
-        line["stage_roofline"] = stage_roofline(stats, inputs, pk)
+        line["stage_roofline"] = stage_roofline(stats, strong["inputs"], pk)
+        lim = max(("lm", "flow", "hift"), key=lambda k: stats[k + "_ms"])
+        line["stage_roofline"]["limiting_stage_rank0"] = lim
     except Exception as e:                              # noqa: BLE001
         line["stage_roofline"] = {"error": repr(e)}
+    if weak is not None:
+        line["weak"] = {"value": weak["value"], "unit": "audio-sec/s", "ms_per_step": weak["dev_ms"] / args.steps, "e2e": weak["e2e"],
+                        "workload": f"{batch} requests PER GPU ({batch * world} in flight)",
+                        "stage_ms_last_step_rank0": {k: weak["stats"][k] for k in ("lm_ms", "flow_ms", "hift_ms")}}
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

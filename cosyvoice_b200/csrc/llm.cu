@@ -327,7 +327,7 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
   tl_stamp(tl, 0);
   pdl_wait();
   tl_stamp(tl, 1);
-  if (!standalone && done[b]) return;
+  if (!standalone && done[b]) { tl_stamp(tl, 2); return; }
   float* x = scores + (size_t)b * V;
   const int per = (V + SAMPLER_THREADS - 1) / SAMPLER_THREADS;
   const int lo = tid * per, hi = min(lo + per, V);
@@ -525,6 +525,7 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
       atomicSub(live, 1);
     }
   }
+  tl_stamp(tl, 2);
 }
 
 __global__ void logsoftmax_rows_kernel(float* __restrict__ x, int V) {

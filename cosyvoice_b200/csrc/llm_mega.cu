@@ -210,22 +210,34 @@ lm_mega_kernel(const MegaParams p) {
     int mma_it = 0, tl_i = 0;
     const bool stamp = p.tl != nullptr && cta == 0 && wt == 0;
     if (stamp) p.tl[tl_i++] = gtime();
+    // fine-grained debug stamps of layer 1: CTA 0 (row 0 of the reduce phases, qkv / down GEMM unit) -> tl[512..], CTA 100 (o GEMM unit,
+    // gate_up unit) -> tl[768..]
+    int fs_i = 0;
+    bool fs_on = false;
+    long long* fs = p.tl ? p.tl + (cta == 0 ? 512 : 768) : nullptr;
+    const bool fs_cta = p.tl != nullptr && (cta == 0 || cta == 100) && wt == 0;
+#define FS() do { if (fs_cta && fs_on && fs_i < 250) fs[fs_i++] = gtime(); } while (0)
 
     // grid-wide barrier: every worker's global writes happen-before (bar.sync) the release-add of thread 0; the acquire-load that
     // sees the last arrival happens-before (bar.sync) every worker's following reads (which use ld.global.cg: L2 is the
     // coherence point, stale L1 lines of the previous layer's activations are never consulted)
     auto grid_sync = [&]() {
       bar_target += (unsigned)G;
+      FS();
       worker_bar();
+      FS();
       if (wt == 0) {
         red_release_add(p.bar, 1u);
+        FS();
         const long long t0 = clock64();
         while ((int)(ld_acquire(p.bar) - bar_target) < 0) {
           if (clock64() - t0 > 4000000000ll) __trap();
         }
         if (stamp) p.tl[tl_i++] = gtime();
+        FS();
       }
       worker_bar();
+      FS();
     };
 
     // one GEMM phase: this CTA's unit = tile u.nt of the weight, K chunks [kc0, kc0 + nblk) of the activation matrix `actg`
@@ -260,6 +272,7 @@ lm_mega_kernel(const MegaParams p) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the MMA (async proxy)
         worker_bar();
+        FS();
       }
       if (warp == 1) {
         if (lane == 0) {
@@ -343,6 +356,7 @@ lm_mega_kernel(const MegaParams p) {
         }
         ss = warp_sum(ss);
         if (lane == 0) red[ww] = ss;
+        FS();
         worker_bar();
         float tot = 0.f;
 #pragma unroll
@@ -359,6 +373,7 @@ lm_mega_kernel(const MegaParams p) {
 
     for (int l = 0; l < p.num_layers; ++l) {
       const MegaLayerDev Lw = s_layers[l];
+      fs_on = l == 1;
       bf16* kc_l = p.kcache + (size_t)l * p.kv_layer_stride;
       bf16* vc_l = p.vcache + (size_t)l * p.kv_layer_stride;
       if (cta < B * NKV && warp >= 8) {

@@ -364,10 +364,10 @@ class B200CosyVoice2Model:
                 noise = torch.randn(sum(lens) * SAMPLES_PER_FRAME, 9, device=self.device, generator=self.generator)
             return self.ctx.hift_inference(mel_tm, lens, noise, cache_source, cache_lens)
 
-    def tts_batch(self, inputs, uniforms=None, noise=None, return_stats=False, to_host=True):
-        """inputs: list of dicts with the kwargs of tts() (text, prompt_text, llm_prompt_speech_token,
-        flow_prompt_speech_token, prompt_speech_feat, flow_embedding).  Returns a list of waveforms [1,N]
-        (CPU tensors, or views of one device buffer when to_host=False)."""
+    def tts_batch_device(self, inputs, uniforms=None, noise=None):
+        """The batched pipeline with the result left on the device: returns (wav_flat, lens, stats) - wav_flat is the vocoder's
+        output buffer (float32 [sum n_i], the utterances back to back in input order, empty ones skipped), lens[i] the sample
+        count of input i (0 when the LM produced no token).  Used by tts_batch and by the multi-GPU gather (parallel.gather_flat)."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         with torch.cuda.stream(self.stream):
             ev[0].record()
@@ -384,14 +384,30 @@ class B200CosyVoice2Model:
         wav, _ = self.hift_batch(mel, lens, noise=noise)
         with torch.cuda.stream(self.stream):
             ev[3].record()
+        n = [0] * len(inputs)
+        for b, L in zip(keep, lens):
+            n[b] = L * SAMPLES_PER_FRAME
+        stats = {"ev": ev, "tokens": [len(x) for x in ids], "mel_frames": lens}
+        return wav, n, stats
+
+    def _stage_ms(self, stats):
+        ev = stats.pop("ev")
+        stats.update({"lm_ms": ev[0].elapsed_time(ev[1]), "flow_ms": ev[1].elapsed_time(ev[2]), "hift_ms": ev[2].elapsed_time(ev[3])})
+        return stats
+
+    def tts_batch(self, inputs, uniforms=None, noise=None, return_stats=False, to_host=True):
+        """inputs: list of dicts with the kwargs of tts() (text, prompt_text, llm_prompt_speech_token,
+        flow_prompt_speech_token, prompt_speech_feat, flow_embedding).  Returns a list of waveforms [1,N]
+        (CPU tensors, or views of one device buffer when to_host=False)."""
+        wav, n, stats = self.tts_batch_device(inputs, uniforms, noise)
+        with torch.cuda.stream(self.stream):
             host = wav.cpu() if to_host else wav          # one D2H for the whole batch
         self.stream.synchronize()
-        out, o = [torch.zeros(1, 0) for _ in inputs], 0
-        for b, L in zip(keep, lens):
-            out[b] = host[o:o + L * SAMPLES_PER_FRAME].unsqueeze(0)
-            o += L * SAMPLES_PER_FRAME
-        self.timings = {"lm_ms": ev[0].elapsed_time(ev[1]), "flow_ms": ev[1].elapsed_time(ev[2]), "hift_ms": ev[2].elapsed_time(ev[3]),
-                        "tokens": [len(x) for x in ids], "mel_frames": lens}
+        out, o = [], 0
+        for k in n:
+            out.append(host[o:o + k].unsqueeze(0) if k else torch.zeros(1, 0))
+            o += k
+        self.timings = self._stage_ms(stats)
         return (out, dict(self.timings)) if return_stats else out
 
     # ---------------------------------------------------------------- reference-shaped single-request API

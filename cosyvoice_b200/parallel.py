@@ -2,7 +2,8 @@
 
 Only two collectives exist, both outside the compute kernels (no exchange step inside LM -> flow -> HiFT):
   * broadcast of the weights from rank 0 at load time,
-  * gather of the finished waveforms (lengths, then padded samples) to rank 0.
+  * gather of the finished waveforms to rank 0: lengths (one small all_gather), then every rank's flat DEVICE buffer straight
+    into its slice of one device buffer on rank 0 (grouped send / recv, exact sizes, no padding), then ONE pinned D2H copy.
 `torch.distributed` is the transport (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 """
 from collections import OrderedDict
@@ -73,6 +74,68 @@ def gather_waveforms(wavs, dist, device):
         for i in range(int(counts[r])):
             n = int(all_lens[r][i])
             lst.append(bufs[r][o:o + n].cpu().unsqueeze(0))
+            o += n
+        out.append(lst)
+    return out
+
+
+def gather_flat(flat, lens, dist, device, counts=None):
+    """Device-resident gather.  flat: 1-D float32 tensor on `device` = this rank's waveforms back to back (the vocoder's own
+    output buffer); lens: their lengths in samples.  counts: utterances per rank when every rank already knows them (the LPT
+    plan is deterministic), else exchanged.  Rank 0 returns (host_flat, per_rank_lens): ONE host tensor (pinned when CUDA) holding
+    rank 0's, rank 1's, ... samples back to back, and the list of length lists; other ranks return None.
+
+    Traffic: world x maxn int64 lengths (all_gather) + exactly the samples (point-to-point into rank 0's buffer at the right
+    offset) + one D2H copy.  Round 1 went D2H -> H2D -> zero-padded NCCL gather -> one .cpu() per utterance."""
+    if dist is None or dist.get_world_size() == 1:
+        host = torch.empty(flat.numel(), dtype=torch.float32, pin_memory=flat.is_cuda)
+        host.copy_(flat, non_blocking=True)
+        if flat.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        return host, [list(lens)]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if counts is None:
+        c = torch.zeros(world, dtype=torch.int64, device=device)
+        c[rank] = len(lens)
+        dist.all_reduce(c)
+        counts = [int(x) for x in c.tolist()]
+    maxn = max(max(counts), 1)
+    lens_p = torch.zeros(maxn, dtype=torch.int64, device=device)
+    if len(lens):
+        lens_p[:len(lens)] = torch.tensor(list(lens), dtype=torch.int64)
+    all_lens = torch.zeros(world * maxn, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_lens, lens_p)
+    if rank != 0:
+        if flat.numel():
+            dist.send(flat, dst=0)
+        return None
+    al = all_lens.view(world, maxn).tolist()
+    per_rank = [[int(x) for x in al[r][:counts[r]]] for r in range(world)]
+    totals = [sum(p) for p in per_rank]
+    big = torch.empty(sum(totals), dtype=torch.float32, device=device)
+    big[:totals[0]].copy_(flat)
+    ops, o = [], totals[0]
+    for r in range(1, world):
+        if totals[r]:
+            ops.append(dist.P2POp(dist.irecv, big[o:o + totals[r]], r))
+        o += totals[r]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    host = torch.empty(big.numel(), dtype=torch.float32, pin_memory=big.is_cuda)
+    host.copy_(big, non_blocking=True)
+    if big.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    return host, per_rank
+
+
+def split_flat(host, per_rank):
+    """views [1,n] of the gathered host buffer, one list per rank"""
+    out, o = [], 0
+    for lens in per_rank:
+        lst = []
+        for n in lens:
+            lst.append(host[o:o + n].unsqueeze(0))
             o += n
         out.append(lst)
     return out

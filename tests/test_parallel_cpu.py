@@ -42,6 +42,20 @@ def _worker(rank, world, port, q):
             ok &= len(res[r]) == 2 + r
             for i, w in enumerate(res[r]):
                 ok &= tuple(w.shape) == (1, 10 + 3 * r + i) and bool((w == r * 10 + i).all())
+    # device-resident variant: flat buffers, exact sizes, point-to-point into rank 0's buffer
+    from cosyvoice_b200.parallel import gather_flat, split_flat
+    flat = torch.cat([w.reshape(-1) for w in wavs])
+    for counts in (None, [2 + r for r in range(world)]):
+        got2 = gather_flat(flat, [w.shape[-1] for w in wavs], dist, dev, counts=counts)
+        if rank == 0:
+            host, per_rank = got2
+            res2 = split_flat(host, per_rank)
+            for r in range(world):
+                ok &= len(res2[r]) == 2 + r
+                for i, w in enumerate(res2[r]):
+                    ok &= tuple(w.shape) == (1, 10 + 3 * r + i) and bool((w == r * 10 + i).all())
+        else:
+            ok &= got2 is None
     q.put((rank, chk, ok))
     dist.destroy_process_group()
 

@@ -100,3 +100,9 @@ if a.timeline:
     print("chain stamps (head, head_finish, sampler) entry/waited/end us rel:", [round((x - ch[0]) / 1e3, 2) if x else 0 for x in ch[:12]])
     if mg[0] and ch[0]:
         print(f"sampler past pdl_wait -> mega first stamp: {(mg[0] - ch[9]) / 1e3:.2f} us; step (head waited -> mega end): {(mg[7 * a.layers] - ch[1]) / 1e3:.1f} us")
+
+    for name, off in (("CTA 0", 2048 + 512), ("CTA 100", 2048 + 768)):
+        f = [x for x in t[off:off + 250] if x]
+        if f:
+            print(f"fine stamps layer 1, {name} ({len(f)}): deltas us:", [round((f[i + 1] - f[i]) / 1e3, 2) for i in range(len(f) - 1)])
+    print("sampler end:", round((ch[10] - ch[0]) / 1e3, 2) if ch[10] else 0)
