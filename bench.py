@@ -358,6 +358,81 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ================================================================================================ config #4: CosyVoice3 bi-streaming
+def run_cv3_bistream(args):
+    """BASELINE.json configs[3]: Fun-CosyVoice3-0.5B bi-streaming (text arrives as a generator, audio leaves in chunks), batch 8 on
+    one GPU: 8 concurrent tts(text=<generator>, stream=True) requests on ONE B200CosyVoice3Model (the reference serves concurrent
+    requests from threads, runtime/python/grpc/server.py:69).  Every yielded chunk is a host tensor, so `value` and `e2e` are the
+    same measurement here (the public API has no device-resident variant of a streaming request)."""
+    import threading
+    import torch
+    from cosyvoice_b200 import synth
+    from cosyvoice_b200.model3 import B200CosyVoice3Model
+    dev = torch.device("cuda", 0)
+    full = not args.small
+    nl, depth = (24, 22) if full else (2, 2)
+    model = B200CosyVoice3Model(precision=args.precision, device=0, workspace_gb=args.workspace_gb)
+    model.load_state_dicts(*synth.cosyvoice3_state_dicts(dev, 1986, nl, depth))
+    torch.cuda.empty_cache()
+    model.silent_tokens = []                   # uniform synthetic ids: count every id
+    batch = args.batch if args.batch != BATCH else 8
+    reqs = [synth.cv3_bistream_request(i) for i in range(batch)]
+    model.bistream_max_tokens = int(reqs[0]["text"].shape[1] * TOKEN_RATIO)          # random weights never emit eos (see model.py)
+    pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else [c.pin_memory() for c in v]) for k, v in r.items()} for r in reqs]
+    h2d = sum(sum(v.numel() * v.element_size() for v in r.values() if torch.is_tensor(v)) for r in reqs)
+
+    def one(r, out, i):
+        n, first = 0, None
+        t0 = time.perf_counter()
+        for o in model.tts(text=iter(r["text_chunks"]), flow_embedding=r["flow_embedding"], llm_embedding=r["llm_embedding"],
+                           prompt_text=r["prompt_text"], llm_prompt_speech_token=r["llm_prompt_speech_token"],
+                           flow_prompt_speech_token=r["flow_prompt_speech_token"], prompt_speech_feat=r["prompt_speech_feat"], stream=True):
+            if first is None:
+                first = time.perf_counter() - t0
+            n += o["tts_speech"].shape[1]
+        out[i] = (n, first)
+
+    def step():
+        model.token_hop_len = 25
+        out = [None] * batch
+        ts = [threading.Thread(target=one, args=(pinned[i], out, i)) for i in range(batch)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return out
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = model.ctx.launch_count()
+    t0 = time.perf_counter()
+    audio, firsts, d2h = 0.0, [], 0
+    for _ in range(args.steps):
+        out = step()
+        audio += sum(n for n, _ in out) / 24000.0
+        firsts += [f for _, f in out]
+        d2h = sum(n for n, _ in out) * 4
+    torch.cuda.synchronize()
+    wall_ms = 1000 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    launches = model.ctx.launch_count() - l0
+    v = audio / (wall_ms / 1000.0)
+    firsts.sort()
+    line = {"metric": "audio-sec/s, Fun-CosyVoice3-0.5B bi-streaming batch-8, NFE=10", "value": v, "unit": "audio-sec/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"Fun-CosyVoice3-0.5B bi-streaming: {batch} concurrent tts(text generator of 4 chunks, stream=True) requests, 48 text ids -> "
+                                   f"{model.bistream_max_tokens} speech ids each (capped: random weights emit no eos), 75 prompt tokens / 150 prompt mel frames, DiT depth {depth}, "
+                                   "causal vocoder; chunk schedule hop 25 -> 50 -> 100 with 3 look-ahead tokens (cli/model.py:346-373)" + ("" if full else " [SMALL DEBUG MODEL]"),
+                       "batch": batch, "nfe": 10, "first_chunk_latency_s": {"median": firsts[len(firsts) // 2], "max": firsts[-1]},
+                       "timing": "wall clock around the concurrent requests (every chunk is a host tensor; no device-only variant of the streaming API)"},
+            "e2e": {"value": v, "unit": "audio-sec/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,9 +446,13 @@ def main():
     ap.add_argument("--workspace-gb", type=float, default=40.0)
     ap.add_argument("--lm-chains", type=int, default=1)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (cvk_set_option), repeatable")
+    ap.add_argument("--workload", default="batch32", choices=["batch32", "cv3-bistream"],
+                    help="batch32 = the headline metric (BASELINE.json configs[2]); cv3-bistream = configs[3] (1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cv3-bistream":
+        run_cv3_bistream(args)
     else:
         run_ours(args)
 

@@ -42,7 +42,7 @@ void llm_feed(cvk_ctx* ctx, cvk_lm_session* s, const int32_t* ids, const int32_t
 void llm_next_logp(cvk_ctx* ctx, cvk_lm_session* s, float* logp, cudaStream_t st);
 void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st);
-void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, cudaStream_t st);
+void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, int fmax_hz, float* mel, cudaStream_t st);
 void mel_init(cvk_ctx* ctx);
 
 #define CVK_API_BEGIN            \
@@ -131,6 +131,7 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   else if (k == "lm_fused") ctx->lm_fused = value;
   else if (k == "pdl") ctx->pdl = value;
   else if (k == "lm_mega") ctx->lm_mega = value;
+  else if (k == "hift_f16") ctx->hift_f16 = value;      // takes effect at the next cvk_finalize("hift" / "hift3")
   else if (k == "mega_coop") ctx->mega_coop = value;
   else if (k == "chain_timeline") {
     if (value && !ctx->tl) {
@@ -363,6 +364,20 @@ int cvk_cfm_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float
   flow_estimator(ctx, x, mu, t, spks, cond, lens, B, streaming, out, (cudaStream_t)stream);
   CVK_API_END
 }
+int cvk_cfm_estimator_inplace(cvk_ctx* ctx, float* x, const float* mu, const float* t, const float* spks, const float* cond, const int* lens,
+                              int B, int streaming, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(x && mu && t && spks && cond && lens && B > 0, "cvk_cfm_estimator_inplace: bad arguments");
+  flow_estimator(ctx, x, mu, t, spks, cond, lens, B, streaming, x, (cudaStream_t)stream);     // x is packed before the first write
+  CVK_API_END
+}
+int cvk_workspace_bytes(cvk_ctx* ctx, size_t* capacity, size_t* high_water) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(capacity && high_water, "cvk_workspace_bytes: bad arguments");
+  *capacity = ctx->arena.cap;
+  *high_water = ctx->arena.high;
+  CVK_API_END
+}
 int cvk_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float* cond, const int* lens, int B, const float* z,
                   int n_timesteps, float cfg_rate, int streaming, float* out, void* stream) {
   CVK_API_BEGIN
@@ -483,7 +498,13 @@ int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* histo
 int cvk_mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, void* stream) {
   CVK_API_BEGIN
   CVK_REQUIRE(wav && lens && mel && B > 0, "cvk_mel_spectrogram: bad arguments");
-  mel_spectrogram(ctx, wav, lens, B, mel, (cudaStream_t)stream);
+  mel_spectrogram(ctx, wav, lens, B, 8000, mel, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_mel_spectrogram_ex(cvk_ctx* ctx, const float* wav, const int* lens, int B, int fmax_hz, float* mel, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(wav && lens && mel && B > 0, "cvk_mel_spectrogram_ex: bad arguments");
+  mel_spectrogram(ctx, wav, lens, B, fmax_hz, mel, (cudaStream_t)stream);
   CVK_API_END
 }
 

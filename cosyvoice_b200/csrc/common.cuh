@@ -23,6 +23,7 @@ struct EpiDev {
   void* out2;
   int out2_dtype;
   int out2_ld;
+  int ab_f16;        // tcgen05 GEMM: operands are IEEE half (instruction-descriptor formats 0) instead of bf16
 };
 
 inline EpiDev to_dev(const Epilogue& e) {
@@ -47,21 +48,33 @@ inline EpiDev to_dev(const Epilogue& e) {
   d.out2 = e.out2.p;
   d.out2_dtype = e.out2.dtype;
   d.out2_ld = e.out2.ld;
+  d.ab_f16 = 0;
   return d;
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+// saturating: an activation beyond the half range becomes +-65504, not inf (fp32 accumulation downstream stays finite)
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// 16-bit storage of either kind as raw bits
+__device__ __forceinline__ unsigned short f32_to_16(float v, int dtype) {
+  if (dtype == DT_F16) return __half_as_ushort(from_f32<__half>(v));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float f16bits_to_f32(unsigned short b, int dtype) {
+  return dtype == DT_F16 ? __half2float(__ushort_as_half(b)) : __bfloat162float(__ushort_as_bfloat16(b));
+}
 
 __device__ __forceinline__ float ld_any(const void* p, int dtype, size_t i) {
-  return dtype == DT_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+  return dtype == DT_F32 ? ((const float*)p)[i] : f16bits_to_f32(((const unsigned short*)p)[i], dtype);
 }
 __device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
   if (dtype == DT_F32) ((float*)p)[i] = v;
-  else ((bf16*)p)[i] = __float2bfloat16_rn(v);
+  else ((unsigned short*)p)[i] = f32_to_16(v, dtype);
 }
 
 // torch semantics: F.gelu(approximate='none'), F.silu, F.mish (softplus threshold 20), F.elu(alpha=1),

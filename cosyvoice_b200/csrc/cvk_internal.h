@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -40,7 +41,9 @@ struct CvkError : std::runtime_error {
 #define CVK_LAUNCH_CHECK() CVK_CHECK_CUDA(cudaGetLastError())
 
 // ------------------------------------------------------------------------------------------------ tensors
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
+// DT_F16: IEEE half operands (10-bit mantissa) - used for the vocoder stage in the tensor-core mode: the reference keeps HiFT in
+// "fp32", i.e. on the GPU cuDNN's default TF32 convolutions (10-bit mantissa as well); bf16 (7 bits) would be narrower than that.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 
 // A 2-D row-major view [rows, cols] with row pitch ld (elements).  Activations are time-major: one row per
 // frame / token / sample-block, channels contiguous.
@@ -79,6 +82,7 @@ struct ConvW {
   int N = 0, K = 0, taps = 1, dil = 1, shift0 = 0;
   float* w32 = nullptr;   // always present
   bf16* w16 = nullptr;    // present in bf16 mode
+  __half* wf16 = nullptr; // IEEE-half copy instead of w16 (vocoder weights when the stage runs on fp16 operands)
   float* bias = nullptr;  // [N] or null
 };
 
@@ -190,7 +194,10 @@ struct cvk_ctx {
   std::vector<cudaEvent_t> event_pool;
   int pdl = 1;                              // LM decode chain: programmatic dependent launch (next kernel's prologue + weight prefetch overlap this kernel)
   int lm_fused = 1;                         // LM decode: fused finish+rmsnorm / rope+attention / SwiGLU-epilogue kernels
-  int lm_mega = 1;                          // LM decode: all layers of a step in one persistent cooperative kernel (llm_mega.cu)
+  int hift_f16 = 1;                         // tensor-core mode: vocoder operands in IEEE half (TF32-class mantissa) instead of bf16
+  int build_f16 = 0;                        // set while a stage whose weights need the half copy is being finalised
+  int lm_mega = 0;                          // LM decode: all layers of a step in one persistent cooperative kernel (llm_mega.cu); measured
+                                            // 973 us / step against 886 us for the PDL-chained per-op path at batch 32 (profiles/r02_lm_decode.md): off by default
   int mega_coop = 1;                        // ... launched with the cooperative attribute (co-residency guaranteed by the driver)
   int use_skinny = 1;                       // LM decode GEMMs on the weight-streaming split-K kernel
   int use_tc_attn = 1;                      // bf16 mode: tcgen05 attention kernel (0 = CUDA-core flash kernel)

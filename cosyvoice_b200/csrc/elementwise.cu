@@ -114,6 +114,10 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
 }
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = from_f32<__half>(x[i]);
+}
 // weight_norm (dim 0): w[i, ...] = g[i] * v[i, ...] / ||v[i, ...]||_2   (one block per leading index)
 __global__ void weight_norm_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ w, int inner) {
   __shared__ float red[32];
@@ -142,6 +146,13 @@ float* dev_copy_f32(cvk_ctx* ctx, const float* src_dev, size_t n) {
 }
 
 void finish_convw(cvk_ctx* ctx, ConvW& w) {
+  if (ctx->precision == CVK_PREC_BF16 && w.K % 8 == 0 && ctx->build_f16) {      // vocoder stage on IEEE-half operands
+    size_t n = (size_t)w.N * w.taps * w.K;
+    w.wf16 = (__half*)ctx->dmalloc(n * sizeof(__half));
+    f32_to_f16_kernel<<<256, 256>>>(w.w32, w.wf16, n);
+    CVK_LAUNCH_CHECK();
+    return;
+  }
   if (ctx->precision == CVK_PREC_BF16 && w.K % 8 == 0) {
     size_t n = (size_t)w.N * w.taps * w.K;
     w.w16 = (bf16*)ctx->dmalloc(n * sizeof(bf16));
@@ -445,7 +456,11 @@ void act_copy_scaled(cvk_ctx* ctx, cudaStream_t st, const Mat& x, float pre_scal
   int g = grid_for(total);
 #define LAUNCH(TI, TO, xi, oo) \
   act_copy_kernel<TI, TO><<<g, 256, 0, st>>>(xi, x.ld, x.rows, x.cols, act, param, alpha, pre_scale, row2seq, oo, out.ld)
-  if (x.dtype == DT_F32 && out.dtype == DT_F32) LAUNCH(float, float, x.f32(), out.f32());
+  if (x.dtype == DT_F32 && out.dtype == DT_F16) LAUNCH(float, __half, x.f32(), (__half*)out.p);
+  else if (x.dtype == DT_F16 && out.dtype == DT_F32) LAUNCH(__half, float, (const __half*)x.p, out.f32());
+  else if (x.dtype == DT_F16 && out.dtype == DT_F16) LAUNCH(__half, __half, (const __half*)x.p, (__half*)out.p);
+  else if (x.dtype == DT_F16 || out.dtype == DT_F16) throw CvkError(CVK_ERR_INVALID, "act_copy: half <-> bf16 conversion is not provided");
+  else if (x.dtype == DT_F32 && out.dtype == DT_F32) LAUNCH(float, float, x.f32(), out.f32());
   else if (x.dtype == DT_F32) LAUNCH(float, bf16, x.f32(), out.b16());
   else if (out.dtype == DT_F32) LAUNCH(bf16, float, x.b16(), out.f32());
   else LAUNCH(bf16, bf16, x.b16(), out.b16());

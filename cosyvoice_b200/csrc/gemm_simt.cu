@@ -105,6 +105,6 @@ void conv_gemm_simt(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W,
 }
 
 void conv_gemm(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep) {
-  if (A.dtype == DT_BF16 && ctx->use_tc) conv_gemm_tc(ctx, st, A, W, ep);
+  if (A.dtype != DT_F32 && ctx->use_tc) conv_gemm_tc(ctx, st, A, W, ep);
   else conv_gemm_simt(ctx, st, A, W, ep);
 }

@@ -15,7 +15,12 @@ namespace {
 constexpr int SK_BM = 128;      // output features per CTA (UMMA M)
 constexpr int SK_BK = 64;
 constexpr int SK_STAGES = 8;
-constexpr int SK_THREADS = 192;
+constexpr int SK_THREADS = 288;   // warp 0: TMA producer; warps 1, 6, 7, 8: MMA issuers; warps 2..5: epilogue
+// With N <= 64 an MMA is 16-32 cycles of tensor-core work, but ONE issuing thread spends ~0.35 us per 64-K chunk on the
+// instruction stream itself (mbarrier wait ~0.16 us + 4 MMAs and a commit ~0.19 us; in-kernel stamps, profiles/r02_lm_mega.md)
+// - 4.9 us of the 8.8 us gate|up GEMM of a decode step.  The chunks are therefore dealt round-robin to SK_NACC issuer warps,
+// each accumulating into its own TMEM tile; the epilogue adds the tiles.
+constexpr int SK_NACC = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -26,6 +31,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;                       // fast path: no clock reads on the MMA issuer's instruction stream
   const long long t0 = clock64();
   for (;;) {
     asm volatile(
@@ -132,11 +145,11 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_acc), 1);
+    mbar_init(smem_u32(&bar_acc), SK_NACC);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)(BPAD < 32 ? 32 : BPAD))
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)(SK_NACC * BPAD))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -184,23 +197,28 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     } else {
       pdl_wait();
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp >= 6) {
+    // MMA issuers: issuer ii takes chunks ii, ii + SK_NACC, ... into accumulator tile ii
+    const int ii = warp == 1 ? 0 : warp - 5;
     pdl_wait();
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
+      const uint32_t tacc = tmem + (uint32_t)ii * BPAD;
+      for (int it = ii; it < iters; it += SK_NACC) {
         const int s = it % SK_STAGES;
         const uint32_t round = (uint32_t)(it / SK_STAGES);
         mbar_wait(smem_u32(&bar_full[s]), round & 1u);
         if (trace && it < 32) dbg[40 + it] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+        const uint64_t da = desc_sw128(sa), db = desc_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < SK_BK / 16; ++k) umma(tmem, desc_sw128(sa + k * 32), desc_sw128(sb + k * 32), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < SK_BK / 16; ++k) umma(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (it >= SK_NACC || k > 0) ? 1u : 0u);
         umma_commit(smem_u32(&bar_empty[s]));
       }
-      umma_commit(smem_u32(&bar_acc));
+      if (ii < iters) umma_commit(smem_u32(&bar_acc));
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_acc)) : "memory");    // no chunk for this issuer
     }
-  } else {
+  } else {      // warps 2..5: epilogue (TMEM lane quarter = warp & 3)
     const int q = warp & 3;
     const int n_pre = n0 + q * 32 + lane;
     const float bias_n = (!partial && !swiglu && ep.bias && n_pre < N) ? ep.bias[n_pre] : 0.f;   // fetched while the weights stream
@@ -219,6 +237,15 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
     for (int c = 0; c < BPAD; c += 16) {
       float acc[16];
       tmem_ld16(trow + (uint32_t)c, acc);
+#pragma unroll
+      for (int a = 1; a < SK_NACC; ++a) {
+        if (a < iters) {                    // tiles of issuers without a chunk were never written
+          float t2[16];
+          tmem_ld16(trow + (uint32_t)(a * BPAD + c), t2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] += t2[e];
+        }
+      }
       if (trace && threadIdx.x == 64) dbg[3 + (c >> 4)] = clock64();
       if (swiglu) {
         // rows of W are interleaved (2i = gate_i, 2i+1 = up_i): lanes pair up, the even lane emits silu(g) * u
@@ -258,7 +285,7 @@ skinny_gemm_kernel(const bf16* __restrict__ w_tiled, const __grid_constant__ CUt
   }
   tl_stamp(tl, 2);
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(BPAD < 32 ? 32 : BPAD)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(SK_NACC * BPAD)) : "memory");
   }
 }
 

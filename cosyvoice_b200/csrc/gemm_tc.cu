@@ -30,6 +30,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // bounded spin: a broken pipeline traps (-> CUDA error in the host API) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;            // fast path without clock reads: the wait sits on the single MMA-issuing thread's instruction stream
   const long long t0 = clock64();
   for (;;) {
     asm volatile(
@@ -150,14 +158,14 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   } else {
-    bf16* op = (bf16*)e.out + o;
+    unsigned short* op = (unsigned short*)e.out + o;
     if (e.accumulate) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(op[i]);
+      for (int i = 0; i < 16; ++i) v[i] += f16bits_to_f32(op[i], e.out_dtype);
     }
-    __align__(16) bf16 t[16];
+    __align__(16) unsigned short t[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = __float2bfloat16_rn(v[i]);
+    for (int i = 0; i < 16; ++i) t[i] = f32_to_16(v[i], e.out_dtype);
     *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(t);
     *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(t + 8);
   }
@@ -176,10 +184,10 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int r, int n0, int 
 #pragma unroll
       for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
     } else {
-      bf16* op = (bf16*)e.out2 + o2;
-      __align__(16) bf16 t[16];
+      unsigned short* op = (unsigned short*)e.out2 + o2;
+      __align__(16) unsigned short t[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) t[i] = __float2bfloat16_rn(w[i]);
+      for (int i = 0; i < 16; ++i) t[i] = f32_to_16(w[i], e.out2_dtype);
       *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(t);
       *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(t + 8);
     }
@@ -256,14 +264,19 @@ __device__ __forceinline__ void epi_math16(const EpiDev& e, int r, bool rin, int
 
 // 16 consecutive columns of one tile row into a SWIZZLE_128B staging tile (128-byte wide sub-tiles of 128 rows, 16 KB each)
 __device__ __forceinline__ void stage_store16(uint32_t stg, int dtype, int row, int c, const float* v) {
-  if (dtype == DT_BF16) {
+  if (dtype != DT_F32) {
     const uint32_t sub = stg + (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
     const uint32_t ch = (uint32_t)((c & 63) >> 3);
     uint32_t pk[8];
+    if (dtype == DT_BF16) {
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i], v[i + 1]);
-      pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int i = 0; i < 16; i += 2) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i], v[i + 1]);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) pk[i >> 1] = (uint32_t)f32_to_16(v[i], DT_F16) | ((uint32_t)f32_to_16(v[i + 1], DT_F16) << 16);
     }
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sub + ((ch ^ (uint32_t)(row & 7)) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sub + (((ch + 1) ^ (uint32_t)(row & 7)) << 4)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
@@ -309,7 +322,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   // UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=bf16, K-major both,
   // N>>3 at bit 17, M>>4 at bit 24
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint32_t IDESC = ep.ab_f16 ? (IDESC_BF & ~((1u << 7) | (1u << 10))) : IDESC_BF;   // a/b format 0 = IEEE half, 1 = bf16
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B aligned tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -509,14 +523,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
         for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
-        bf16* op = (bf16*)ep.out + o;
+        unsigned short* op = (unsigned short*)ep.out + o;
         if (ep.accumulate) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(op[i]);
+          for (int i = 0; i < 16; ++i) v[i] += f16bits_to_f32(op[i], ep.out_dtype);
         }
-        __align__(16) bf16 tt[16];
+        __align__(16) unsigned short tt[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tt[i] = __float2bfloat16_rn(v[i]);
+        for (int i = 0; i < 16; ++i) tt[i] = f32_to_16(v[i], ep.out_dtype);
         *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(tt);
         *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(tt + 8);
       }
@@ -530,10 +544,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(w2[i], w2[i + 1], w2[i + 2], w2[i + 3]);
         } else {
-          bf16* op = (bf16*)ep.out2 + o2;
-          __align__(16) bf16 tt[16];
+          unsigned short* op = (unsigned short*)ep.out2 + o2;
+          __align__(16) unsigned short tt[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) tt[i] = __float2bfloat16_rn(w2[i]);
+          for (int i = 0; i < 16; ++i) tt[i] = f32_to_16(w2[i], ep.out2_dtype);
           *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(tt);
           *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(tt + 8);
         }
@@ -573,7 +587,8 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint32_t IDESC = ep.ab_f16 ? (IDESC_BF & ~((1u << 7) | (1u << 10))) : IDESC_BF;   // a/b format 0 = IEEE half, 1 = bf16
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + NSTG * STAGE_BYTES;          // 64 KB staging region (one 64 KB or two 32 KB tiles)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -752,7 +767,8 @@ void launch_tc_persist(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, con
 }  // namespace
 
 void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, const Epilogue& ep) {
-  CVK_REQUIRE(A.dtype == DT_BF16 && W.w16 != nullptr, "conv_gemm_tc: bf16 operands required");
+  CVK_REQUIRE((A.dtype == DT_BF16 && W.w16 != nullptr) || (A.dtype == DT_F16 && W.wf16 != nullptr), "conv_gemm_tc: 16-bit operands (A and W of the same kind) required");
+  const void* w16p = A.dtype == DT_F16 ? (const void*)W.wf16 : (const void*)W.w16;
   CVK_REQUIRE(A.cols >= W.K, "conv_gemm_tc: A has fewer columns than K");
   CVK_REQUIRE(W.K % 8 == 0 && A.ld % 8 == 0 && ((uintptr_t)A.p & 15) == 0, "conv_gemm_tc: operands must be 16-byte aligned");
   CVK_REQUIRE(ep.out.p != nullptr && ep.out.cols >= W.N, "conv_gemm_tc: bad output");
@@ -773,11 +789,12 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
     cuuint64_t strides[2] = {(cuuint64_t)W.K * 2, (cuuint64_t)W.K * W.taps * 2};
     cuuint32_t box[3] = {TC_BK, 1, (cuuint32_t)BN};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, W.w16, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w16p), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CVK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W) failed: " + std::to_string((int)r));
   }
   EpiDev e = to_dev(ep);
+  e.ab_f16 = A.dtype == DT_F16;
   if (!e.bias) e.bias = W.bias;
   int rowsOut = ep.out.rows;
   CVK_REQUIRE((ep.out.ld * ep.out.esize()) % 16 == 0 && ((uintptr_t)ep.out.p & 15) == 0, "conv_gemm_tc: output rows must be 16-byte aligned");

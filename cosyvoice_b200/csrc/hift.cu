@@ -28,6 +28,7 @@ struct ResBlockW {
 }  // namespace
 
 struct HiftModel {
+  bool half_weights = false;   // conv weights were finalised as IEEE half (wf16): the body runs on DT_F16 operands
   ConvW f0_conv[5];
   ConvW f0_cls;
   float* src_w = nullptr;   // [9]
@@ -290,13 +291,17 @@ ResBlockW build_resblock(cvk_ctx* ctx, const std::string& p, int k) {
 void hift_build(cvk_ctx* ctx) {
   init_consts();
   HiftModel* m = new HiftModel();
+  m->half_weights = ctx->precision == CVK_PREC_BF16 && ctx->hift_f16;
+  struct F16Scope { cvk_ctx* c; F16Scope(cvk_ctx* c_, bool on) : c(c_) { c->build_f16 = on; } ~F16Scope() { c->build_f16 = 0; } } f16scope(ctx, m->half_weights);
   const std::string P = "hift.";
   for (int i = 0; i < 5; ++i) {
     m->f0_conv[i] = wn_conv(ctx, P + "f0_predictor.condnet." + std::to_string(2 * i), 1, -1);
     m->f0_conv[i].w16 = nullptr;   // the f0 predictor always runs fp32 (phase accumulates f0 over the utterance)
+    m->f0_conv[i].wf16 = nullptr;
   }
   m->f0_cls = make_linear(ctx, P + "f0_predictor.classifier.weight", P + "f0_predictor.classifier.bias");
   m->f0_cls.w16 = nullptr;
+  m->f0_cls.wf16 = nullptr;
   m->src_w = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.weight").p, 9);
   m->src_b = dev_copy_f32(ctx, ctx->get_raw(P + "m_source.l_linear.bias").p, 1);
   m->conv_pre = wn_conv(ctx, P + "conv_pre", 1, -3);
@@ -447,7 +452,9 @@ static void run_resblock(cvk_ctx* ctx, cudaStream_t st, const ResBlockW& rb, con
 static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat& mel32, const float* src_packed,
                      const HiftModel* m = nullptr, const int* d_len_sig = nullptr) {
   if (!m) m = ctx->hift;
-  const int adt = ctx->act_dtype;
+  // tensor-core mode: IEEE-half operands (10-bit mantissa, the class of the TF32 convolutions the reference's "fp32" vocoder runs
+  // on under cuDNN's defaults) unless the option hift_f16 is off (then bf16, 7 bits: narrower than the reference)
+  const int adt = (ctx->act_dtype == DT_BF16 && m->half_weights) ? DT_F16 : ctx->act_dtype;
   const Seqs& s0 = g.s0;
   // STFT of the source at the x120 rate
   const Seqs& s3 = g.lv[2];
@@ -458,6 +465,7 @@ static Mat hift_body(cvk_ctx* ctx, cudaStream_t st, const HiftGeom& g, const Mat
     int bx = ceil_div(F, 128);
     if (bx > 1024) bx = 1024;
     if (adt == DT_F32) stft16_kernel<float><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.f32(), stft.ld, d_len_sig);
+    else if (adt == DT_F16) stft16_kernel<__half><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, (__half*)stft.p, stft.ld, d_len_sig);
     else stft16_kernel<bf16><<<dim3(bx, s0.B), 128, 0, st>>>(src_packed, s0.d_start, s0.d_len, s3.d_start, stft.b16(), stft.ld, d_len_sig);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
@@ -790,6 +798,8 @@ ResBlockW build_resblock_causal(cvk_ctx* ctx, const std::string& p, int k) {
 void hift3_build(cvk_ctx* ctx) {
   init_consts();
   HiftModel* m = new HiftModel();
+  m->half_weights = ctx->precision == CVK_PREC_BF16 && ctx->hift_f16;
+  struct F16Scope { cvk_ctx* c; F16Scope(cvk_ctx* c_, bool on) : c(c_) { c->build_f16 = on; } ~F16Scope() { c->build_f16 = 0; } } f16scope(ctx, m->half_weights);
   Hift3Extra* x = ctx->hift3_extra ? (Hift3Extra*)ctx->hift3_extra : new Hift3Extra();
   const std::string P = "hift3.";
   // float64 f0 predictor: conv0 k4 looking RIGHT (f0_predictor.py:71), then four causal k3 convolutions

@@ -271,6 +271,8 @@ __global__ void gather_last_kernel(const float* __restrict__ x, const int* __res
   for (int c = threadIdx.x; c < D; c += blockDim.x) out[(size_t)b * D + c] = src[c];
 }
 
+static inline size_t sampler_smem(int V) { return (size_t)2 * ((V + 3) & ~3) * sizeof(float); }   // probabilities + scores
+
 // ---- block-wide helpers for the sampler (256 threads, contiguous segments of `per` entries per thread) ----
 __device__ __forceinline__ float block_max(float v, float* red) {
   v = warp_max(v);
@@ -301,6 +303,11 @@ __device__ __forceinline__ float block_hsum(float seg, float* part, float* total
 // the full distribution with the repeated id removed -> stop / length logic -> append id, gather next embedding.
 // Bit-for-bit restatement: oracle/sampling.py (ras_sample, nucleus_select, draw_index, softmax_f32).
 // standalone mode (cvk_ras_sample): `scores` already holds log-probs, history given explicitly, no state update.
+//
+// The row lives in SHARED memory for the whole kernel (one coalesced read, one coalesced write-back of the log-probs with the
+// reference's in-place -inf marks): round 1 walked the global row with a 104-byte stride per lane in ~8 dependent passes and took
+// 91 us per decode step (in-kernel stamps, profiles/r02_lm_mega.md) - 9 % of the step.  The arithmetic (segment order of every
+// float32 sum, stable tie-break of the nucleus) is unchanged.
 __global__ void __launch_bounds__(SAMPLER_THREADS)
 ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const float* __restrict__ uniforms /*[..][B][2]*/, int B,
                    const int32_t* __restrict__ min_len, const int32_t* __restrict__ max_len, int32_t* __restrict__ out_ids, int out_ld,
@@ -309,17 +316,15 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
                    const float* __restrict__ speech_emb, float* __restrict__ next_x,
                    const int32_t* __restrict__ history, int hist_ld, const int32_t* __restrict__ hist_count,
                    const int32_t* __restrict__ ignore_eos_in, int32_t* __restrict__ ids_out, const float* __restrict__ ln_gamma,
-                   bf16* __restrict__ xn_out, long long* __restrict__ tl) {
-  extern __shared__ float sp[];            // V probabilities
+                   bf16* __restrict__ xn_out, long long* __restrict__ tl, long long* __restrict__ dbg_fine) {
+  extern __shared__ __align__(16) float sp_all[];   // [V4] probabilities | [V4] scores (log-probs), V4 = V rounded up to 4
   __shared__ float red[SAMPLER_THREADS / 32];
   __shared__ float part[SAMPLER_THREADS];
   __shared__ float tot;
-  __shared__ float bv[SAMPLER_THREADS / 32];
-  __shared__ int bi[SAMPLER_THREADS / 32];
+  __shared__ int bi[2][SAMPLER_THREADS / 32];
   __shared__ float kept_p[TOPK];
   __shared__ int kept_i[TOPK];
-  __shared__ int s_n, s_top, s_seg;
-  __shared__ float s_thr, s_cum;
+  __shared__ int s_n, s_top;
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool standalone = ids_out != nullptr;
@@ -327,88 +332,140 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
   tl_stamp(tl, 0);
   pdl_wait();
   tl_stamp(tl, 1);
+  long long* sf = (dbg_fine && b == 0 && tid == 0) ? dbg_fine : nullptr;      // stage stamps of CTA 0 (debug option chain_timeline)
+  int sf_i = 0;
+#define SF() do { if (sf) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); sf[sf_i++] = t_; } } while (0)
+  SF();
   if (!standalone && done[b]) { tl_stamp(tl, 2); return; }
-  float* x = scores + (size_t)b * V;
+  const int V4 = (V + 3) & ~3;
+  float* sp = sp_all;
+  float* x = sp_all + V4;
+  float* xg = scores + (size_t)b * V;
+  if ((V & 3) == 0) {
+    for (int i = tid; i < V / 4; i += SAMPLER_THREADS) reinterpret_cast<float4*>(x)[i] = __ldcg(reinterpret_cast<const float4*>(xg) + i);
+  } else {
+    for (int i = tid; i < V; i += SAMPLER_THREADS) x[i] = __ldcg(xg + i);
+  }
   const int per = (V + SAMPLER_THREADS - 1) / SAMPLER_THREADS;
   const int lo = tid * per, hi = min(lo + per, V);
   const int cnt = standalone ? hist_count[b] : out_count[b];
   const bool ignore_eos = standalone ? (ignore_eos_in[b] != 0) : (cnt < min_len[b]);
   const float u1 = standalone ? uniforms[b * 2] : uniforms[((size_t)cnt * B + b) * 2];
   const float u2 = standalone ? uniforms[b * 2 + 1] : uniforms[((size_t)cnt * B + b) * 2 + 1];
+  __syncthreads();
+  // The thread's contiguous segment (<= SAMPLER_PER entries) lives in REGISTERS from here on: every pass below is an unrolled
+  // register loop (the shared-memory version was a chain of ~30-cycle dependent LDS per element: 48 us per step).  Entries past
+  // the segment hold -inf (scores) / -3 (probabilities) and are skipped by the ordered sums.
+  float xr[SAMPLER_PER], pr[SAMPLER_PER];
+#pragma unroll
+  for (int i = 0; i < SAMPLER_PER; ++i) xr[i] = (i < per && lo + i < hi) ? x[lo + i] : -INFINITY;
+  SF();
 
   // (1) log-softmax of the head output (llm.py:542): (x - max) - log(hsum(exp(x - max)))
   if (from_logits) {
     float mx = -INFINITY;
-    for (int i = lo; i < hi; ++i) mx = fmaxf(mx, x[i]);
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) mx = fmaxf(mx, xr[i]);
     mx = block_max(mx, red);
     float seg = 0.f;
-    for (int i = lo; i < hi; ++i) seg += expf(x[i] - mx);
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i)
+      if (i < per && lo + i < hi) seg += expf(xr[i] - mx);
     float s = block_hsum(seg, part, &tot);
     float ls = logf(s);
-    for (int i = lo; i < hi; ++i) x[i] = (x[i] - mx) - ls;
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i)
+      if (i < per && lo + i < hi) xr[i] = (xr[i] - mx) - ls;
   }
+  SF();
   // (2) eos mask before min_len (llm.py:157-158: only index speech_token_size is masked)
-  if (ignore_eos && tid == 0) x[EOS] = -INFINITY;
-  __syncthreads();
+  if (ignore_eos) {
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i)
+      if (i < per && lo + i == EOS && lo + i < hi) xr[i] = -INFINITY;
+  }
   // (3) softmax of the scores
   float mx = -INFINITY;
-  for (int i = lo; i < hi; ++i) mx = fmaxf(mx, x[i]);
+#pragma unroll
+  for (int i = 0; i < SAMPLER_PER; ++i) mx = fmaxf(mx, xr[i]);
   mx = block_max(mx, red);
   {
     float seg = 0.f;
-    for (int i = lo; i < hi; ++i) {
-      float e = x[i] == -INFINITY ? 0.f : expf(x[i] - mx);
-      sp[i] = e;
-      seg += e;
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) {
+      const bool ok = i < per && lo + i < hi;
+      float e = (!ok || xr[i] == -INFINITY) ? 0.f : expf(xr[i] - mx);
+      pr[i] = e;
+      if (ok) seg += e;
     }
     float s = block_hsum(seg, part, &tot);
-    for (int i = lo; i < hi; ++i) sp[i] = sp[i] / s;
-  }
-  if (tid == 0) { s_n = 0; s_cum = 0.f; }
-  __syncthreads();
-  // (4) nucleus: repeatedly take the largest remaining probability (ties -> lowest index == stable sort)
-  float lbest = -1.f;
-  int lidx = -1;
-  for (int i = lo; i < hi; ++i)
-    if (sp[i] > lbest) { lbest = sp[i]; lidx = i; }
-  for (int round = 0; round < TOPK; ++round) {
-    if (!(s_cum < 0.8f)) break;           // block-uniform (shared)
-    float v = lbest;
-    int ix = lidx;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, v, o);
-      int oi = __shfl_xor_sync(0xffffffffu, ix, o);
-      if (ov > v || (ov == v && oi >= 0 && (ix < 0 || oi < ix))) { v = ov; ix = oi; }
-    }
-    if ((tid & 31) == 0) { bv[tid >> 5] = v; bi[tid >> 5] = ix; }
-    __syncthreads();
-    if (tid == 0) {
-      float gv = bv[0];
-      int gi = bi[0];
-      for (int w = 1; w < SAMPLER_THREADS / 32; ++w)
-        if (bv[w] > gv || (bv[w] == gv && bi[w] >= 0 && (gi < 0 || bi[w] < gi))) { gv = bv[w]; gi = bi[w]; }
-      kept_p[s_n] = gv;
-      kept_i[s_n] = gi;
-      s_n = s_n + 1;
-      s_cum = s_cum + gv;
-      s_top = gi;
-    }
-    __syncthreads();
-    int taken = s_top;
-    if (taken >= lo && taken < hi) {      // owner removes it and rescans its segment
-      sp[taken] = -2.f;
-      lbest = -1.f;
-      lidx = -1;
-      for (int i = lo; i < hi; ++i)
-        if (sp[i] > lbest) { lbest = sp[i]; lidx = i; }
-    }
-    __syncthreads();
+    for (int i = 0; i < SAMPLER_PER; ++i) pr[i] = (i < per && lo + i < hi) ? pr[i] / s : -3.f;
   }
+  SF();
+  // (4) nucleus: repeatedly take the largest remaining probability (ties -> lowest index == stable sort).  The 25 rounds are a
+  // serial chain, so a round is kept short (it was ~1 us: two 5-level shuffle trees + a 27-entry rescan by the owner): every
+  // thread caches the three largest remaining entries of its segment (popped in O(1), rebuilt only when exhausted), the warp
+  // winner comes from two redux.sync (probabilities are >= 0, so their bit patterns order like unsigned integers; +1 keeps 0.0
+  // above "nothing left"), the 8 warp winners are double-buffered so that one barrier per round suffices, and every thread
+  // reduces them itself (running count / cumulative probability are thread-uniform registers).
+  float c_v[3];
+  int c_i[3], c_n;
+  auto rebuild = [&]() {
+    c_v[0] = c_v[1] = c_v[2] = -1.f;
+    c_i[0] = c_i[1] = c_i[2] = -1;
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) {
+      const float v = pr[i];               // removed entries hold -2, entries past the segment -3
+      const int ix = lo + i;
+      if (v > c_v[0]) { c_v[2] = c_v[1]; c_i[2] = c_i[1]; c_v[1] = c_v[0]; c_i[1] = c_i[0]; c_v[0] = v; c_i[0] = ix; }
+      else if (v > c_v[1]) { c_v[2] = c_v[1]; c_i[2] = c_i[1]; c_v[1] = v; c_i[1] = ix; }
+      else if (v > c_v[2]) { c_v[2] = v; c_i[2] = ix; }
+    }
+    c_n = (c_v[0] >= 0.f) + (c_v[1] >= 0.f) + (c_v[2] >= 0.f);
+  };
+  rebuild();
+  __shared__ unsigned bk[2][SAMPLER_THREADS / 32];
+  int n_kept = 0;
+  float cum = 0.f;
+  for (int round = 0; round < TOPK; ++round) {
+    if (!(cum < 0.8f)) break;             // thread-uniform
+    const unsigned key = c_n > 0 ? __float_as_uint(c_v[0]) + 1u : 0u;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+    const int widx = __reduce_min_sync(0xffffffffu, (key == wmax && wmax != 0u) ? c_i[0] : 0x7fffffff);
+    const int pb = round & 1;
+    if ((tid & 31) == 0) { bk[pb][tid >> 5] = wmax; bi[pb][tid >> 5] = widx; }
+    __syncthreads();
+    unsigned gk = bk[pb][0];
+    int gi = bi[pb][0];
+#pragma unroll
+    for (int w = 1; w < SAMPLER_THREADS / 32; ++w) {
+      const unsigned k2 = bk[pb][w];
+      const int i2 = bi[pb][w];
+      if (k2 > gk || (k2 == gk && i2 < gi)) { gk = k2; gi = i2; }
+    }
+    if (gk == 0u) break;                  // nothing left (cannot happen: V > TOPK)
+    const float gv = __uint_as_float(gk - 1u);
+    if (tid == 0) {
+      kept_p[n_kept] = gv;
+      kept_i[n_kept] = gi;
+    }
+    n_kept += 1;
+    cum = cum + gv;
+    if (gi >= lo && gi < hi) {            // owner removes it: mark the entry, pop the cache
+#pragma unroll
+      for (int i = 0; i < SAMPLER_PER; ++i)
+        if (lo + i == gi) pr[i] = -2.f;
+      c_v[0] = c_v[1]; c_i[0] = c_i[1];
+      c_v[1] = c_v[2]; c_i[1] = c_i[2];
+      c_v[2] = -1.f; c_i[2] = -1;
+      if (--c_n == 0) rebuild();
+    }
+  }
+  SF();
   // (5) inverse-CDF draw over the kept (unnormalised) probabilities
   if (tid == 0) {
-    int n = s_n;
+    int n = n_kept;
     float total = 0.f;
     for (int i = 0; i < n; ++i) total += kept_p[i];
     float thr = u1 * total, acc = 0.f;
@@ -428,24 +485,33 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
     s_n = rep >= 1 ? 1 : 0;
   }
   __syncthreads();
+  SF();
   if (s_n) {
     int top = s_top;
-    if (tid == 0) x[top] = -INFINITY;
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i)
+      if (lo + i == top) xr[i] = -INFINITY;
     float m3 = -INFINITY;
-    for (int i = lo; i < hi; ++i) m3 = fmaxf(m3, x[i]);
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) m3 = fmaxf(m3, xr[i]);
     m3 = block_max(m3, red);
     float seg = 0.f;
-    for (int i = lo; i < hi; ++i) {
-      float e = x[i] == -INFINITY ? 0.f : expf(x[i] - m3);
-      sp[i] = e;
-      seg += e;
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) {
+      const bool ok = i < per && lo + i < hi;
+      float e = (!ok || xr[i] == -INFINITY) ? 0.f : expf(xr[i] - m3);
+      pr[i] = e;
+      if (ok) seg += e;
     }
     float s = block_hsum(seg, part, &tot);
     seg = 0.f;
-    for (int i = lo; i < hi; ++i) {
-      sp[i] = sp[i] / s;
-      seg += sp[i];
+#pragma unroll
+    for (int i = 0; i < SAMPLER_PER; ++i) {
+      if (i < per && lo + i < hi) {
+        pr[i] = pr[i] / s;
+        seg += pr[i];
+        sp[lo + i] = pr[i];                 // the walk below reads other threads' segments
+      }
     }
     // hierarchical inverse CDF (oracle draw_index): segment sums -> sequential prefix -> walk inside the segment
     __syncthreads();
@@ -486,7 +552,21 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
     }
     __syncthreads();
   }
+  SF();
+  // the scores with the reference's in-place marks go back to shared memory for the coalesced write-back
+#pragma unroll
+  for (int i = 0; i < SAMPLER_PER; ++i)
+    if (i < per && lo + i < hi) x[lo + i] = xr[i];
+  __syncthreads();
   const int top = s_top;
+  // the log-probs with the reference's in-place marks (eos / repeated id = -inf) go back to the caller's buffer
+  // (cvk_ras_sample modifies logp like common.py does; cvk_lm_last_logits reads them)
+  if ((V & 3) == 0) {
+    for (int i = tid; i < V / 4; i += SAMPLER_THREADS) reinterpret_cast<float4*>(xg)[i] = reinterpret_cast<const float4*>(x)[i];
+  } else {
+    for (int i = tid; i < V; i += SAMPLER_THREADS) xg[i] = x[i];
+  }
+  SF();
   if (standalone) {
     if (tid == 0) ids_out[b] = top;
     return;
@@ -495,10 +575,19 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
   const bool stop = top >= EOS;      // Qwen2LM: 6561..6563 (llm.py:297); CosyVoice3LM: 6561..6760 (llm.py:704); nothing else exists above 6560
   if (!stop) {
     float ss = 0.f;
-    for (int c = tid; c < D; c += SAMPLER_THREADS) {
-      const float v = speech_emb[(size_t)top * D + c];
-      next_x[(size_t)b * D + c] = v;
-      ss += v * v;
+    float ev[(D + SAMPLER_THREADS - 1) / SAMPLER_THREADS];
+#pragma unroll
+    for (int k = 0; k < (D + SAMPLER_THREADS - 1) / SAMPLER_THREADS; ++k) {
+      const int c = tid + k * SAMPLER_THREADS;
+      ev[k] = c < D ? speech_emb[(size_t)top * D + c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < (D + SAMPLER_THREADS - 1) / SAMPLER_THREADS; ++k) {
+      const int c = tid + k * SAMPLER_THREADS;
+      if (c < D) {
+        next_x[(size_t)b * D + c] = ev[k];
+        ss += ev[k] * ev[k];
+      }
     }
     if (xn_out) {   // fused decode path: RMSNorm of the next layer-0 input (input_layernorm of layer 0)
       ss = warp_sum(ss);
@@ -508,8 +597,11 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
       float t2 = 0.f;
       for (int i = 0; i < SAMPLER_THREADS / 32; ++i) t2 += red[i];
       const float r = rsqrtf(t2 / D + RMS_EPS);
-      for (int c = tid; c < D; c += SAMPLER_THREADS)
-        xn_out[(size_t)b * D + c] = __float2bfloat16_rn(ln_gamma[c] * (speech_emb[(size_t)top * D + c] * r));
+#pragma unroll
+      for (int k = 0; k < (D + SAMPLER_THREADS - 1) / SAMPLER_THREADS; ++k) {
+        const int c = tid + k * SAMPLER_THREADS;
+        if (c < D) xn_out[(size_t)b * D + c] = __float2bfloat16_rn(ln_gamma[c] * (ev[k] * r));
+      }
     }
   }
   if (tid == 0) {
@@ -525,7 +617,9 @@ ras_sampler_kernel(float* __restrict__ scores, int V, int from_logits, const flo
       atomicSub(live, 1);
     }
   }
+  SF();
   tl_stamp(tl, 2);
+#undef SF
 }
 
 __global__ void logsoftmax_rows_kernel(float* __restrict__ x, int V) {
@@ -743,7 +837,7 @@ cvk_lm_session* llm_session_create(cvk_ctx* ctx, int max_batch, int max_context)
   s->vcache = alloc(cache);
   s->ctx_len = (int*)alloc(sizeof(int) * max_batch);
   s->base_len = (int*)alloc(sizeof(int) * max_batch);
-  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOUT3_PAD * (int)sizeof(float)));
+  CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sampler_smem(VOUT3_PAD)));
   CVK_REQUIRE((NH / NKV) * max_context * sizeof(float) <= 200 * 1024, "session context too long for the decode attention kernel");
   {
     // the limit is per function, not per session: never lower it for a smaller session created later
@@ -862,10 +956,11 @@ static void decode_step_fused(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) 
     conv_gemm_skinny_ex(ctx, st, xn, m->head, e, s->scratch, s->scratch_floats, 0);
   }
   const bool pdl = ctx->pdl != 0;
-  launch_ex(ras_sampler_kernel, dim3(B), dim3(SAMPLER_THREADS), m->vout * sizeof(float), st, pdl, s->logits, m->vout, 1, s->g_uniforms, B, s->g_min,
+  launch_ex(ras_sampler_kernel, dim3(B), dim3(SAMPLER_THREADS), sampler_smem(m->vout), st, pdl, s->logits, m->vout, 1, s->g_uniforms, B, s->g_min,
             s->g_max, s->g_out_ids, s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, (const int*)s->base_len, s->live,
             (const float*)m->speech_emb, s->x, (const int32_t*)nullptr, 0, (const int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr,
-            (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next());
+            (const float*)(fused ? m->layers[0].ln1 : nullptr), fused ? (bf16*)s->xn : (bf16*)nullptr, ctx->tl_next(),
+            ctx->tl ? (long long*)ctx->tl + 1024 : (long long*)nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   if (lm_mega_usable(ctx, s, B)) {     // all layers in one persistent cooperative kernel (llm_mega.cu)
@@ -912,10 +1007,10 @@ static void decode_step(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s) {
   Mat hid(s->hidden, DT_F32, B, D, D), x(s->x, DT_F32, B, D, D), xn(s->xn, adt, B, D, D), qkv(s->qkv, adt, B, QKV_N, QKV_N),
       att(s->att, adt, B, D, D), gu(s->gu, adt, B, 2 * DFF, 2 * DFF), ffa(s->ffa, adt, B, DFF, DFF), logits(s->logits, DT_F32, B, m->vout, m->vout);
   head_logits(ctx, st, m, hid, xn, logits, s);
-  ras_sampler_kernel<<<B, SAMPLER_THREADS, m->vout * sizeof(float), st>>>(s->logits, m->vout, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, sampler_smem(m->vout), st>>>(s->logits, m->vout, 1, s->g_uniforms, B, s->g_min, s->g_max, s->g_out_ids,
                                                                        s->g_out_ld, s->g_out_count, s->g_done, s->ctx_len, s->base_len, s->live,
                                                                        m->speech_emb, s->x, nullptr, 0, nullptr, nullptr, nullptr, fused ? m->layers[0].ln1 : nullptr,
-                                                                       fused ? (bf16*)s->xn : nullptr, nullptr);
+                                                                       fused ? (bf16*)s->xn : nullptr, nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   for (int li = 0; li < m->num_layers; ++li) layer_forward(ctx, st, m, li, x, xn, qkv, att, gu, ffa, nullptr, s, true);
@@ -1090,12 +1185,12 @@ void llm_forward_logp(cvk_ctx* ctx, const float* embeds, const int* lens, int B,
 
 void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* history, int hist_ld, const int32_t* hist_count,
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st) {
-  CVK_REQUIRE(V > EOS + 2 && V * sizeof(float) <= 200 * 1024, "vocabulary size out of range");
+  CVK_REQUIRE(V > EOS + 2 && V <= SAMPLER_PER * SAMPLER_THREADS, "vocabulary size out of range (6564 .. 6912 supported)");
   CVK_CHECK_CUDA(cudaFuncSetAttribute(ras_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (V > VOUT3_PAD ? V : VOUT3_PAD) * (int)sizeof(float)));   // per function, never lowered
-  ras_sampler_kernel<<<B, SAMPLER_THREADS, V * sizeof(float), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                      (int)sampler_smem(V > VOUT3_PAD ? V : VOUT3_PAD)));   // per function, never lowered
+  ras_sampler_kernel<<<B, SAMPLER_THREADS, sampler_smem(V), st>>>(logp, V, 0, uniforms, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                                                                     nullptr, nullptr, nullptr, nullptr, history, hist_ld, hist_count, ignore_eos,
-                                                                    out_ids, nullptr, nullptr, nullptr);
+                                                                    out_ids, nullptr, nullptr, nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

@@ -9,6 +9,7 @@ constexpr int VOUT3 = 6761, VOUT3_PAD = 6764;   // CosyVoice3LM head (llm.py:689
 constexpr int QKV_N = NH * HD + 2 * NKV * HD;   // 1152
 constexpr float ROPE_THETA = 1.0e6f, RMS_EPS = 1e-6f;
 constexpr int SAMPLER_THREADS = 256, TOPK = 25, WIN = 10;
+constexpr int SAMPLER_PER = (VOUT3_PAD + SAMPLER_THREADS - 1) / SAMPLER_THREADS;   // 27: largest per-thread segment of the sampler
 
 struct LayerW {
   float *ln1, *ln2;

@@ -5,14 +5,18 @@
 // Why: the step is HBM-bound in principle (727.6 MB of bf16 weights per step shared by all rows) but the
 // per-op chain was latency-bound: 171 kernels per step, each a launch + a few dependent memory round trips over <= 148 CTAs
 // (977 us per step against a 0.126 ms floor, profiles/r01_ncu_summary.md §C).  Here
-//   * one CTA per SM stays resident for the whole step; phases are separated by grid-wide barriers (one atomic + one polled
-//     word in L2) instead of kernel boundaries;
-//   * the weights are re-laid out once into PER-CTA STREAMS: the 16 KB SWIZZLE_128B operand blocks a CTA will consume, in
-//     the order it consumes them, across phases and layers.  A dedicated producer warp walks that stream with plain bulk
-//     copies into a 10-stage (160 KB) shared-memory ring and never waits for a phase boundary, so HBM keeps streaming
-//     through the barriers and through the latency-bound phases (attention, split-K reductions);
-//   * GEMMs are swap-AB tcgen05 (weights = the 128-row M side, the <= 64 batch rows = UMMA N) with the fp32 accumulator in
-//     TMEM; activations (the B operand) arrive by TMA after the barrier;
+//   * one CTA per SM stays resident for the whole step; phases are separated by grid-wide barriers (one release-add + one
+//     acquire-polled word in L2) instead of kernel boundaries;
+//   * the weights are re-laid out once into PER-CTA STREAMS: the SWIZZLE_128B operand blocks ([64 or 72 output rows] x [64 K],
+//     8 / 9 KB) a CTA will consume, in the order it consumes them, across phases and layers.  Every projection is cut by OUTPUT
+//     ROWS (and K ranges) so that all 148 CTAs carry about the same bytes per layer (~200 KB) and no unit exceeds the ring;
+//     a dedicated producer warp walks the stream with plain bulk copies into an 18-slot (162 KB) shared-memory ring and never
+//     waits for a phase boundary, so HBM keeps streaming through the barriers and the latency-bound phases.  At most
+//     MG_INFLIGHT blocks of a CTA are in flight at once: a deeper burst only queues in front of the latency-critical loads
+//     and stores of the same SM (measured: activation loads 1.3-2.9 us, release fences up to 2.8 us behind 160 KB bursts);
+//   * GEMMs are swap-AB tcgen05 (weights = the M side: the MMA reads 128 rows from the slot, rows past the block belong to the
+//     next slot and produce accumulator lanes nobody reads; the <= 64 batch rows = UMMA N) with the fp32 accumulator in TMEM;
+//     activations (the B operand) are gathered with ld.global.cg into the swizzled layout after the barrier;
 //   * split-K partial sums go to a small fp32 scratch and are reduced in a fixed order (deterministic, no atomics) by the
 //     attention unit (qkv) or by a per-row reduce + residual + RMSNorm phase (o_proj, down_proj).
 // Phases per layer: qkv GEMM | bias + RoPE + cache append + attention | o GEMM | +res, RMSNorm | gate/up GEMM + SwiGLU |
@@ -25,28 +29,36 @@ using namespace lm;
 
 namespace {
 
-constexpr int MG_THREADS = 512;          // warp 0: weight producer; warps 1..15: workers (1: MMA issue, 2: activation TMA, 4..7: epilogue)
+constexpr int MG_THREADS = 512;          // warp 0: weight producer; warps 1..15: workers (1, 2, 3, 8: MMA issue, 4..7: epilogue)
 constexpr int MG_WORKERS = MG_THREADS - 32;
 constexpr int MG_NW = MG_WORKERS / 32;   // 15
-constexpr int MG_BM = 128, MG_BK = 64;
-constexpr uint32_t MG_BLK = MG_BM * MG_BK * 2;   // 16 KB weight block
-constexpr int MG_MAX_STAGES = 10;
+constexpr int MG_BK = 64;
+constexpr int MG_MAXROWS = 72;           // output rows of a weight block (multiple of 8)
+constexpr uint32_t MG_SLOT = MG_MAXROWS * 128;   // 9 KB ring slot (a 64-row block uses 8 KB of it)
+constexpr int MG_MAX_STAGES = 18;
+constexpr int MG_INFLIGHT = 3;           // bulk copies of one CTA in flight
 constexpr int MG_KCH = D / MG_BK;        // 14 K chunks of the 896-wide activations
 constexpr int MG_PH = 4;                 // GEMM phases per layer: qkv, o, gate_up, down
+constexpr int MG_MAX_LAYERS = 32;
+// static schedule constants shared by the host-side table builder and the kernel (compile-time split counts let every
+// partial-sum load of a reduction be issued before the first add)
+constexpr int MG_TILE = 64;                                          // output rows per unit of qkv / o / down
+constexpr int MG_CPU_QKV = 2, MG_CPU_O = 2;                          // K chunks per unit
+constexpr int MG_SPL_QKV = MG_KCH / MG_CPU_QKV;                      // 7
+constexpr int MG_SPL_O = MG_KCH / MG_CPU_O;                          // 7
+constexpr int MG_SPL_DOWN = 10;                                      // 76 K chunks -> 6 units of 8 + 4 of 7 per row tile
 
-struct MegaUnit { int nt, kc0, nblk, split; };
+struct MegaUnit { int row0, nrows, kc0, nblk, split; };
 struct MegaLayerDev { const float* qkv_bias; const float* ln2; const float* next_gamma; };
 
 struct MegaParams {
   const uint8_t* wstream;
   const unsigned long long* cta_off;   // [G] byte offset of the CTA's stream
-  const int* cta_bpl;                  // [G] blocks per layer of the CTA
   const MegaUnit* units;               // [4][G]
   const MegaLayerDev* layers;          // [L]
   int num_layers, B, max_ctx;
   float* x; bf16* xn; bf16* att; bf16* ffa;
   float *part_qkv, *part_o, *part_down;
-  int splits_qkv, splits_o, splits_down;
   bf16 *kcache, *vcache;
   unsigned long long kv_layer_stride;  // elements
   const int* ctx_len;
@@ -64,6 +76,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;                       // fast path: no clock reads on the MMA issuers' instruction stream
   const long long t0 = clock64();
   for (;;) {
     asm volatile(
@@ -77,12 +97,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) break;     // ~2 s: a protocol bug traps instead of hanging the GPU
   }
   __trap();
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -113,41 +127,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// generic-proxy writes to global memory that a TMA (async proxy) of another CTA will read after the grid barrier, and the
-// mirror fence on the reading side
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MG_WORKERS) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// static schedule constants shared by the host-side table builder and the kernel (compile-time split counts let every
-// partial-sum load of a reduction be issued before the first add)
-constexpr int MG_CPU_QKV = 2, MG_CPU_O = 2, MG_CPU_DOWN = 8;        // K chunks per unit
-constexpr int MG_SPL_QKV = MG_KCH / MG_CPU_QKV;                      // 7
-constexpr int MG_SPL_O = MG_KCH / MG_CPU_O;                          // 7
-constexpr int MG_SPL_DOWN = (DFF / MG_BK + MG_CPU_DOWN - 1) / MG_CPU_DOWN;   // 10
-constexpr int MG_MAX_LAYERS = 32;
-
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int BPAD>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 lm_mega_kernel(const MegaParams p) {
-  constexpr int NST = BPAD == 32 ? 10 : 7;
+  constexpr int NST = BPAD == 32 ? 18 : 12;
   constexpr uint32_t ACT_CHUNK = BPAD * 128;     // one 64-wide K chunk of the activations: [BPAD rows][128 B], SWIZZLE_128B
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BPAD >> 3) << 17) | ((uint32_t)(MG_BM >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int STG_LD = 40;                     // SwiGLU staging pitch (bf16): 36 channels + pad, rows 8-byte aligned
+  // ONE issuing thread spends ~0.35 us per 64-K block on the instruction stream (mbarrier wait ~0.16 us, 4 MMAs + commit ~0.19 us:
+  // in-kernel stamps) - 5 us for the 14 blocks of the gate|up unit.  The blocks of a unit are dealt round-robin to NACC issuer
+  // warps (1, 2, 3, 8), each with its own TMEM accumulator tile; the epilogue adds the tiles.
+  constexpr int NACC = 4;
+  constexpr uint32_t TMEM_COLS = NACC * BPAD;
   static_assert(decode_attn_smem_floats<MG_NW>() * 4 <= MG_KCH * ACT_CHUNK, "attention scratch must fit the activation buffer");
+  static_assert(BPAD * STG_LD * 2 <= MG_KCH * ACT_CHUNK, "SwiGLU staging must fit the activation buffer");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MG_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MG_MAX_STAGES];
@@ -159,8 +169,8 @@ lm_mega_kernel(const MegaParams p) {
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t ring = sbase, act = sbase + NST * MG_BLK;
-  uint8_t* act_ptr = sptr + NST * MG_BLK;
+  const uint32_t ring = sbase, act = sbase + NST * MG_SLOT;
+  uint8_t* act_ptr = sptr + NST * MG_SLOT;
   float* attn_sm = reinterpret_cast<float*>(act_ptr);       // aliases the activation buffer (disjoint phases)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -171,13 +181,13 @@ lm_mega_kernel(const MegaParams p) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_acc), 1);
+    mbar_init(smem_u32(&bar_acc), NACC);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + MG_PH) s_units[threadIdx.x - 64] = p.units[(threadIdx.x - 64) * G + cta];
   if (threadIdx.x >= 128 && threadIdx.x < 128 + p.num_layers) s_layers[threadIdx.x - 128] = p.layers[threadIdx.x - 128];
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)BPAD) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -189,15 +199,24 @@ lm_mega_kernel(const MegaParams p) {
     // ---------------------------------------------------------------------------------------- weight producer
     if (lane == 0) {
       const uint8_t* src = p.wstream + p.cta_off[cta];
-      const int total = p.cta_bpl[cta] * p.num_layers;
-      for (int it = 0; it < total; ++it) {
-        const int s = it % NST;
-        const uint32_t round = (uint32_t)(it / NST);
-        if (it >= NST) mbar_wait(smem_u32(&bar_empty[s]), (round & 1u) ^ 1u);
-        const uint32_t fb = smem_u32(&bar_full[s]);
-        mbar_expect_tx(fb, MG_BLK);
-        bulk_load(ring + s * MG_BLK, src + (size_t)it * MG_BLK, MG_BLK, fb);
-      }
+      int it = 0;
+      for (int l = 0; l < p.num_layers; ++l)
+        for (int ph = 0; ph < MG_PH; ++ph) {
+          const int nblk = s_units[ph].nblk;
+          const uint32_t bytes = (uint32_t)s_units[ph].nrows * 128u;
+          for (int j = 0; j < nblk; ++j, ++it) {
+            const int s = it % NST;
+            if (it >= NST) mbar_wait(smem_u32(&bar_empty[s]), ((uint32_t)(it / NST) & 1u) ^ 1u);
+            if (it >= MG_INFLIGHT) {     // block it - MG_INFLIGHT has landed: bounded burst in front of this SM's latency-critical traffic
+              const int itp = it - MG_INFLIGHT;
+              mbar_wait(smem_u32(&bar_full[itp % NST]), (uint32_t)(itp / NST) & 1u);
+            }
+            const uint32_t fb = smem_u32(&bar_full[s]);
+            mbar_expect_tx(fb, bytes);
+            bulk_load(ring + s * MG_SLOT, src, bytes, fb);
+            src += bytes;
+          }
+        }
     }
     __syncwarp();
   } else {
@@ -210,8 +229,7 @@ lm_mega_kernel(const MegaParams p) {
     int mma_it = 0, tl_i = 0;
     const bool stamp = p.tl != nullptr && cta == 0 && wt == 0;
     if (stamp) p.tl[tl_i++] = gtime();
-    // fine-grained debug stamps of layer 1: CTA 0 (row 0 of the reduce phases, qkv / down GEMM unit) -> tl[512..], CTA 100 (o GEMM unit,
-    // gate_up unit) -> tl[768..]
+    // fine-grained debug stamps of layer 1: CTA 0 -> tl[512..], CTA 100 -> tl[768..]
     int fs_i = 0;
     bool fs_on = false;
     long long* fs = p.tl ? p.tl + (cta == 0 ? 512 : 768) : nullptr;
@@ -225,7 +243,6 @@ lm_mega_kernel(const MegaParams p) {
       bar_target += (unsigned)G;
       FS();
       worker_bar();
-      FS();
       if (wt == 0) {
         red_release_add(p.bar, 1u);
         FS();
@@ -237,11 +254,11 @@ lm_mega_kernel(const MegaParams p) {
         FS();
       }
       worker_bar();
-      FS();
     };
 
-    // one GEMM phase: this CTA's unit = tile u.nt of the weight, K chunks [kc0, kc0 + nblk) of the activation matrix `actg`
-    // [B][K] bf16.  mode 0: fp32 partial sums -> out_f32[(split * B + b) * N + n]; mode 1: SwiGLU on interleaved gate/up rows -> ffa
+    // one GEMM phase: this CTA's unit = output rows [row0, row0 + nrows) of the weight, K chunks [kc0, kc0 + nblk) of the
+    // activation matrix `actg` [B][K] bf16.  mode 0: fp32 partial sums -> out_f32[(split * B + b) * N + n]; mode 1: SwiGLU on
+    // interleaved gate/up rows -> ffa
     auto gemm_phase = [&](int ph, const bf16* actg, int K, float* out_f32, int N, int mode) {
       const MegaUnit u = s_units[ph];
       if (u.nblk <= 0) return;
@@ -274,54 +291,94 @@ lm_mega_kernel(const MegaParams p) {
         worker_bar();
         FS();
       }
-      if (warp == 1) {
+      if (warp <= 3 || warp == 8) {
+        // MMA issuers: issuer ii takes blocks ii, ii + NACC, ... of the unit into accumulator tile ii
+        const int ii = warp <= 3 ? warp - 1 : 3;
         if (lane == 0) {
+          long long* ms = (p.tl && cta == 0 && fs_on && ph == 2 && ii == 0) ? p.tl + 1280 : nullptr;     // issuer-0 stamps, gate_up of layer 1
+          int ms_i = 0;
+          if (ms) ms[ms_i++] = gtime();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int j = 0; j < u.nblk; ++j) {
+          const uint32_t tacc = tmem + (uint32_t)ii * BPAD;
+          for (int j = ii; j < u.nblk; j += NACC) {
             const int it = mma_it + j;
             const int s = it % NST;
             mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(it / NST) & 1u);
+            if (ms) ms[ms_i++] = gtime();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = ring + s * MG_BLK, sb = act + j * ACT_CHUNK;
+            const uint64_t da = desc_sw128(ring + s * MG_SLOT), db = desc_sw128(act + j * ACT_CHUNK);
 #pragma unroll
-            for (int k = 0; k < MG_BK / 16; ++k) umma(tmem, desc_sw128(sa + k * 32), desc_sw128(sb + k * 32), IDESC, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < MG_BK / 16; ++k) umma(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (j >= NACC || k > 0) ? 1u : 0u);
             umma_commit(smem_u32(&bar_empty[s]));
+            if (ms) ms[ms_i++] = gtime();
           }
-          umma_commit(smem_u32(&bar_acc));
+          if (ii < u.nblk) umma_commit(smem_u32(&bar_acc));
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_acc)) : "memory");   // no block for this issuer
+          if (ms) ms[ms_i++] = gtime();
         }
         __syncwarp();
       }
       if (warp >= 4 && warp < 8) {
         const int q = warp & 3;
-        const int n = u.nt * MG_BM + q * 32 + lane;
-        mbar_wait(smem_u32(&bar_acc), acc_par);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const int r = q * 32 + lane;               // accumulator lane = row of the unit
+        const int n = u.row0 + r;
+        const bool warp_has_rows = q * 32 < u.nrows;
+        bf16* stage = reinterpret_cast<bf16*>(act_ptr);
+        long long* es = (p.tl && cta == 0 && fs_on && ph == 2 && threadIdx.x == 128) ? p.tl + 1400 : nullptr;
+        int es_i = 0;
+        if (es) es[es_i++] = gtime();
+        if (warp_has_rows) {
+          mbar_wait(smem_u32(&bar_acc), acc_par);
+          if (es) es[es_i++] = gtime();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BPAD; c += 16) {
-          float acc[16];
-          tmem_ld16(trow + (uint32_t)c, acc);
-          if (mode == 1) {
-            // rows of W are interleaved (2i = gate_i, 2i+1 = up_i): lanes pair up, the even lane emits silu(g) * u
-            // (Qwen2 MLP act_fn(gate_proj(x)) * up_proj(x)) into column n/2
+          for (int c = 0; c < BPAD; c += 16) {
+            float acc[16];
+            tmem_ld16(trow + (uint32_t)c, acc);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float other = __shfl_xor_sync(0xffffffffu, acc[e], 1);
-              const int b = c + e;
-              if (!(lane & 1) && b < B) {
-                const float g = acc[e];
-                p.ffa[(size_t)b * DFF + (n >> 1)] = __float2bfloat16_rn(__fdividef(g, 1.f + fast_exp(-g)) * other);
+            for (int a = 1; a < NACC; ++a) {
+              if (a < u.nblk) {                   // tiles of issuers without a block were never written
+                float t2[16];
+                tmem_ld16(trow + (uint32_t)(a * BPAD + c), t2);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] += t2[e];
               }
             }
-          } else {
+            if (mode == 1) {
+              // rows of W are interleaved (2i = gate_i, 2i+1 = up_i): lanes pair up, the even lane forms silu(g) * u (Qwen2 MLP
+              // act_fn(gate_proj(x)) * up_proj(x)) for channel (row0 + r) / 2 and parks it in the staging tile [b][channel]
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int b = c + e;
-              if (b < B) out_f32[((size_t)u.split * B + b) * N + n] = acc[e];
+              for (int e = 0; e < 16; ++e) {
+                const float other = __shfl_xor_sync(0xffffffffu, acc[e], 1);
+                const int b = c + e;
+                if (!(lane & 1) && r < u.nrows && b < B) {
+                  const float g = acc[e];
+                  stage[b * STG_LD + (r >> 1)] = __float2bfloat16_rn(__fdividef(g, 1.f + fast_exp(-g)) * other);
+                }
+              }
+            } else if (r < u.nrows) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int b = c + e;
+                if (b < B) out_f32[((size_t)u.split * B + b) * N + n] = acc[e];
+              }
             }
           }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (es) es[es_i++] = gtime();
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (mode == 1) {
+          // staging tile -> ffa[b][row0/2 .. + nrows/2) with 8-byte stores (each row's run is 64 or 72 bytes, 8-byte aligned)
+          epi_bar();
+          const int nq = u.nrows >> 3;               // 8-byte chunks per row (4 channels each)
+          const int ch0 = u.row0 >> 1;
+          for (int i = threadIdx.x - 128; i < B * nq; i += 128) {
+            const int b = i / nq, c4 = i % nq;
+            *reinterpret_cast<uint2*>(p.ffa + (size_t)b * DFF + ch0 + c4 * 4) = *reinterpret_cast<const uint2*>(stage + b * STG_LD + c4 * 4);
+          }
+          if (es) es[es_i++] = gtime();
+        }
       }
       acc_par ^= 1u;
       mma_it += u.nblk;
@@ -418,20 +475,25 @@ lm_mega_kernel(const MegaParams p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)BPAD) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 }
 
-// dst[i] <- src[i], 16 KB blocks
-__global__ void copy_blocks_kernel(const uint8_t* const* __restrict__ src, uint8_t* const* __restrict__ dst, int n) {
+// one weight block: rows [row0, row0 + nrows) x K chunk kc of W [N][K] bf16 row-major -> the shared-memory image of a K-major
+// SWIZZLE_128B operand tile (row r, 16-byte chunk c at r*128 + ((c ^ (r & 7)) << 4)); nrows*128 contiguous bytes in the stream
+struct PackDesc { const bf16* w; int K, row0, nrows, kc; unsigned long long dst; };
+__global__ void pack_blocks_kernel(const PackDesc* __restrict__ descs, int n, uint8_t* __restrict__ out) {
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint4* s = reinterpret_cast<const uint4*>(src[i]);
-    uint4* d = reinterpret_cast<uint4*>(dst[i]);
-    for (int e = threadIdx.x; e < (int)(MG_BLK / 16); e += blockDim.x) d[e] = s[e];
+    const PackDesc d = descs[i];
+    for (int e = threadIdx.x; e < d.nrows * 8; e += blockDim.x) {
+      const int r = e >> 3, c = e & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(d.w + (size_t)(d.row0 + r) * d.K + (size_t)d.kc * MG_BK + c * 8);
+      *reinterpret_cast<uint4*>(out + d.dst + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
   }
 }
 
-template <int BPAD> constexpr size_t mega_smem() { return (size_t)(BPAD == 32 ? 10 : 7) * MG_BLK + (size_t)MG_KCH * BPAD * 128 + 1024; }
+template <int BPAD> constexpr size_t mega_smem() { return (size_t)(BPAD == 32 ? 18 : 12) * MG_SLOT + (size_t)MG_KCH * BPAD * 128 + 1024; }
 
 }  // namespace
 
@@ -440,7 +502,6 @@ struct LmMega {
   int splits[MG_PH] = {0, 0, 0, 0};
   uint8_t* wstream = nullptr;
   unsigned long long* cta_off = nullptr;
-  int* cta_bpl = nullptr;
   MegaUnit* units = nullptr;
   MegaLayerDev* layers = nullptr;
   size_t stream_bytes = 0;
@@ -453,79 +514,80 @@ struct MegaSession {
 
 void lm_mega_build(cvk_ctx* ctx, LlmModel* m) {
   const int G = ctx->num_sms, L = m->num_layers;
+  if (L > MG_MAX_LAYERS) return;
+  // static schedule (identical for every layer): which output rows x K range of each projection a CTA owns.  Row-granular cuts
+  // spread every projection over (nearly) all CTAs with about equal bytes, so no unit exceeds the ring and the aggregate HBM
+  // stream is balanced; K splits (partial sums) only where the output is narrow (qkv 1152, o / down 896 rows).
+  std::vector<MegaUnit> units((size_t)MG_PH * G, MegaUnit{0, 0, 0, 0, 0});
+  auto put = [&](int ph, int c, MegaUnit u) {
+    c = ((c % G) + G) % G;
+    CVK_REQUIRE(units[(size_t)ph * G + c].nblk == 0, "lm mega: two units on one CTA in a phase");
+    units[(size_t)ph * G + c] = u;
+  };
+  const int qkv_tiles = QKV_N / MG_TILE, o_tiles = D / MG_TILE, down_chunks = DFF / MG_BK;
+  if (qkv_tiles * MG_SPL_QKV > G || o_tiles * MG_SPL_O > G || o_tiles * MG_SPL_DOWN > G) return;      // fewer SMs than the schedule assumes
+  for (int t = 0; t < qkv_tiles; ++t)
+    for (int s = 0; s < MG_SPL_QKV; ++s) put(0, t * MG_SPL_QKV + s, MegaUnit{t * MG_TILE, MG_TILE, s * MG_CPU_QKV, MG_CPU_QKV, s});
+  for (int t = 0; t < o_tiles; ++t)
+    for (int s = 0; s < MG_SPL_O; ++s) put(1, G - o_tiles * MG_SPL_O + t * MG_SPL_O + s, MegaUnit{t * MG_TILE, MG_TILE, s * MG_CPU_O, MG_CPU_O, s});
+  {
+    // gate|up (interleaved rows, whole K, SwiGLU in the epilogue): 9728 rows in groups of 8 dealt over all CTAs
+    const int groups = 2 * DFF / 8, base = groups / G, extra = groups % G;
+    if ((base + (extra ? 1 : 0)) * 8 > MG_MAXROWS || base < 1) return;
+    int row = 0;
+    for (int c = 0; c < G; ++c) {
+      const int nr = (base + (c < extra ? 1 : 0)) * 8;
+      put(2, c, MegaUnit{row, nr, 0, MG_KCH, 0});
+      row += nr;
+    }
+  }
+  {
+    const int base = down_chunks / MG_SPL_DOWN, extra = down_chunks % MG_SPL_DOWN;       // 7, 6
+    for (int t = 0; t < o_tiles; ++t) {
+      int kc = 0;
+      for (int s = 0; s < MG_SPL_DOWN; ++s) {
+        const int nb = base + (s < extra ? 1 : 0);
+        put(3, t * MG_SPL_DOWN + s, MegaUnit{t * MG_TILE, MG_TILE, kc, nb, s});
+        kc += nb;
+      }
+    }
+  }
   LmMega* mg = new LmMega();
   mg->G = G;
-  // static schedule (identical for every layer): which (tile, K range) of each projection a CTA owns.  The HBM stream is
-  // decoupled from the phases by the per-CTA prefetch ring, so the assignment optimises the critical path of a phase
-  // (blocks per unit = serial MMAs; splits = partial sums the consumer must add) and only roughly balances bytes per CTA.
-  struct Cfg { int tiles, kchunks, cpu /*chunks per unit*/, first; };
-  const Cfg cfg[MG_PH] = {
-      {QKV_N / MG_BM, D / MG_BK, MG_CPU_QKV, 0},        // qkv: 9 tiles x 7 splits = 63 units
-      {D / MG_BM, D / MG_BK, MG_CPU_O, 63},             // o: 7 x 7 = 49 units
-      {2 * DFF / MG_BM, D / MG_BK, D / MG_BK, G - 76},  // gate|up (interleaved rows): 76 tiles, whole K (SwiGLU in the epilogue)
-      {D / MG_BM, DFF / MG_BK, MG_CPU_DOWN, 0},         // down: 7 tiles x 10 splits = 70 units
-  };
-  std::vector<MegaUnit> units((size_t)MG_PH * G, MegaUnit{0, 0, 0, 0});
-  for (int ph = 0; ph < MG_PH; ++ph) {
-    const int splits = ceil_div(cfg[ph].kchunks, cfg[ph].cpu);
-    mg->splits[ph] = splits;
-    CVK_REQUIRE(ph == 2 || splits == (ph == 0 ? MG_SPL_QKV : ph == 1 ? MG_SPL_O : MG_SPL_DOWN), "lm mega: split constants out of sync");
-    CVK_REQUIRE(cfg[ph].tiles * splits <= G, "lm mega: more units than CTAs in a phase");
-    for (int t = 0; t < cfg[ph].tiles; ++t)
-      for (int s = 0; s < splits; ++s) {
-        const int c = ((cfg[ph].first + t * splits + s) % G + G) % G;
-        MegaUnit& u = units[(size_t)ph * G + c];
-        CVK_REQUIRE(u.nblk == 0, "lm mega: two units on one CTA in a phase");
-        u.nt = t;
-        u.kc0 = s * cfg[ph].cpu;
-        u.nblk = std::min(cfg[ph].cpu, cfg[ph].kchunks - u.kc0);
-        u.split = s;
-      }
-  }
-  std::vector<int> bpl(G, 0);
+  mg->splits[0] = MG_SPL_QKV; mg->splits[1] = MG_SPL_O; mg->splits[2] = 1; mg->splits[3] = MG_SPL_DOWN;
+  std::vector<unsigned> lbytes(G, 0);
   std::vector<unsigned long long> off(G, 0);
-  size_t total_blocks = 0;
+  size_t total = 0;
   for (int c = 0; c < G; ++c) {
-    for (int ph = 0; ph < MG_PH; ++ph) bpl[c] += units[(size_t)ph * G + c].nblk;
-    off[c] = (unsigned long long)total_blocks * L * MG_BLK;
-    total_blocks += bpl[c];
+    for (int ph = 0; ph < MG_PH; ++ph) lbytes[c] += (unsigned)(units[(size_t)ph * G + c].nblk * units[(size_t)ph * G + c].nrows * 128);
+    off[c] = total;
+    total += (size_t)lbytes[c] * L;
   }
-  mg->stream_bytes = total_blocks * (size_t)L * MG_BLK;
-  mg->wstream = (uint8_t*)ctx->dmalloc(mg->stream_bytes);
-  // gather list: stream block <- block (tile, chunk) of the pre-tiled weight (gemm_skinny.cu tile_weights_kernel: the exact
-  // SWIZZLE_128B shared-memory image of a 128 x 64 K-major operand tile)
-  std::vector<const uint8_t*> src;
-  std::vector<uint8_t*> dst;
-  src.reserve(total_blocks * L);
-  dst.reserve(total_blocks * L);
+  mg->stream_bytes = total;
+  mg->wstream = (uint8_t*)ctx->dmalloc(total);
+  std::vector<PackDesc> descs;
   for (int c = 0; c < G; ++c)
     for (int l = 0; l < L; ++l) {
       const LayerW& w = m->layers[l];
       const ConvW* Ws[MG_PH] = {&w.qkv, &w.o, &w.gate_up_il, &w.down};
-      int j0 = 0;
+      unsigned long long dst = off[c] + (unsigned long long)l * lbytes[c];
       for (int ph = 0; ph < MG_PH; ++ph) {
         const MegaUnit& u = units[(size_t)ph * G + c];
-        if (u.nblk == 0) continue;
-        const uint8_t* tw = (const uint8_t*)skinny_tiled_weights(ctx, *Ws[ph]);
+        CVK_REQUIRE(u.nblk == 0 || (Ws[ph]->w16 && u.row0 + u.nrows <= Ws[ph]->N && (u.kc0 + u.nblk) * MG_BK <= Ws[ph]->K), "lm mega: unit outside its weight");
         for (int j = 0; j < u.nblk; ++j) {
-          src.push_back(tw + ((size_t)u.nt * cfg[ph].kchunks + u.kc0 + j) * MG_BLK);
-          dst.push_back(mg->wstream + off[c] + ((size_t)l * bpl[c] + j0 + j) * MG_BLK);
+          descs.push_back(PackDesc{Ws[ph]->w16, Ws[ph]->K, u.row0, u.nrows, u.kc0 + j, dst});
+          dst += (unsigned long long)u.nrows * 128;
         }
-        j0 += u.nblk;
       }
     }
   {
-    const uint8_t** dsrc = nullptr;
-    uint8_t** ddst = nullptr;
-    CVK_CHECK_CUDA(cudaMalloc((void**)&dsrc, src.size() * sizeof(void*)));
-    CVK_CHECK_CUDA(cudaMalloc((void**)&ddst, dst.size() * sizeof(void*)));
-    CVK_CHECK_CUDA(cudaMemcpy(dsrc, src.data(), src.size() * sizeof(void*), cudaMemcpyHostToDevice));
-    CVK_CHECK_CUDA(cudaMemcpy(ddst, dst.data(), dst.size() * sizeof(void*), cudaMemcpyHostToDevice));
-    copy_blocks_kernel<<<148 * 8, 256>>>(dsrc, ddst, (int)src.size());
+    PackDesc* dd = nullptr;
+    CVK_CHECK_CUDA(cudaMalloc((void**)&dd, descs.size() * sizeof(PackDesc)));
+    CVK_CHECK_CUDA(cudaMemcpy(dd, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
+    pack_blocks_kernel<<<148 * 8, 256>>>(dd, (int)descs.size(), mg->wstream);
     CVK_LAUNCH_CHECK();
     CVK_CHECK_CUDA(cudaDeviceSynchronize());
-    cudaFree(dsrc);
-    cudaFree(ddst);
+    cudaFree(dd);
   }
   std::vector<MegaLayerDev> lay(L);
   for (int l = 0; l < L; ++l) {
@@ -539,7 +601,6 @@ void lm_mega_build(cvk_ctx* ctx, LlmModel* m) {
     return d;
   };
   mg->cta_off = (unsigned long long*)up(off.data(), off.size() * sizeof(unsigned long long));
-  mg->cta_bpl = (int*)up(bpl.data(), bpl.size() * sizeof(int));
   mg->units = (MegaUnit*)up(units.data(), units.size() * sizeof(MegaUnit));
   mg->layers = (MegaLayerDev*)up(lay.data(), lay.size() * sizeof(MegaLayerDev));
   CVK_CHECK_CUDA(cudaFuncSetAttribute(lm_mega_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem<32>()));
@@ -581,11 +642,10 @@ void lm_mega_layers(cvk_ctx* ctx, cudaStream_t st, cvk_lm_session* s, int B) {
   CVK_REQUIRE(mg && ms && B >= 1 && B <= 64 && m->num_layers <= MG_MAX_LAYERS, "lm mega: not initialised");
   const int bpad = B <= 32 ? 32 : 64;
   MegaParams p;
-  p.wstream = mg->wstream; p.cta_off = mg->cta_off; p.cta_bpl = mg->cta_bpl; p.units = mg->units; p.layers = mg->layers;
+  p.wstream = mg->wstream; p.cta_off = mg->cta_off; p.units = mg->units; p.layers = mg->layers;
   p.num_layers = m->num_layers; p.B = B; p.max_ctx = s->max_ctx;
   p.x = s->x; p.xn = (bf16*)s->xn; p.att = (bf16*)s->att; p.ffa = (bf16*)s->ffa;
   p.part_qkv = ms->part_qkv; p.part_o = ms->part_o; p.part_down = ms->part_down;
-  p.splits_qkv = mg->splits[0]; p.splits_o = mg->splits[1]; p.splits_down = mg->splits[3];
   p.kcache = (bf16*)s->kcache; p.vcache = (bf16*)s->vcache;
   p.kv_layer_stride = (unsigned long long)s->max_batch * NKV * s->max_ctx * HD;
   p.ctx_len = s->ctx_len; p.inv_freq = m->d_inv_freq;

@@ -17,7 +17,8 @@ constexpr int BINS_LD = 968;
 
 struct MelModel {
   ConvW dft;    // [2*961][4][480]
-  ConvW mel;    // [80][961]
+  ConvW mel;    // [80][961], fmax 8000 (cosyvoice2.yaml:150-158)
+  ConvW mel_nyq;  // [80][961], fmax = sr/2 (CosyVoice3: `fmax: null`, cosyvoice3.yaml:140-147)
 };
 
 __global__ void dft_weight_kernel(float* __restrict__ w) {
@@ -35,12 +36,14 @@ __global__ void dft_weight_kernel(float* __restrict__ w) {
   }
 }
 
-// reflect-pad each utterance by 720 and lay it out as rows of 480 samples
+// reflect-pad each utterance by 720 (about sample 0 and about its TRUE last sample, torch.nn.functional.pad(mode="reflect") on
+// the whole signal, audio.py:70-72) and lay the first (N/480 + 3) * 480 padded samples out as rows of 480: the center=False
+// framing of audio.py:74-86 uses exactly those (frame f = padded samples [480 f, 480 f + 1920))
 __global__ void frame_rows_kernel(const float* __restrict__ wav, const int* __restrict__ off, const int* __restrict__ nsamp,
                                   const int* __restrict__ start, float* __restrict__ out) {
   int b = blockIdx.y;
   int N = nsamp[b];
-  int total = N + 2 * PAD;
+  int total = (N / HOP + 3) * HOP;
   const float* x = wav + off[b];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int m = i - PAD;
@@ -79,37 +82,46 @@ void mel_init(cvk_ctx* ctx) {
   m->dft.w32 = (float*)ctx->dmalloc((size_t)2 * N_BINS * N_FFT * sizeof(float));
   dft_weight_kernel<<<512, 256>>>(m->dft.w32);
   CVK_LAUNCH_CHECK();
-  // librosa.filters.mel(sr=24000, n_fft=1920, n_mels=80, fmin=0, fmax=8000): Slaney scale, Slaney (area) norm
-  std::vector<float> fb((size_t)N_MEL * N_BINS, 0.f);
-  std::vector<double> mel_f(N_MEL + 2);
-  double m0 = hz_to_mel(0.0), m1 = hz_to_mel(8000.0);
-  for (int i = 0; i < N_MEL + 2; ++i) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(N_MEL + 1));
-  for (int i = 0; i < N_MEL; ++i) {
-    double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
-    for (int k = 0; k < N_BINS; ++k) {
-      double f = (double)SR / 2 * (double)k / (double)(N_BINS - 1);
-      double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
-      double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
-      double w = lower < upper ? lower : upper;
-      if (w < 0) w = 0;
-      fb[(size_t)i * N_BINS + k] = (float)(w * enorm);
+  // librosa.filters.mel(sr=24000, n_fft=1920, n_mels=80, fmin=0, fmax): Slaney scale, Slaney (area) norm
+  auto filterbank = [&](double fmax_hz) {
+    std::vector<float> fb((size_t)N_MEL * N_BINS, 0.f);
+    std::vector<double> mel_f(N_MEL + 2);
+    double m0 = hz_to_mel(0.0), m1 = hz_to_mel(fmax_hz);
+    for (int i = 0; i < N_MEL + 2; ++i) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(N_MEL + 1));
+    for (int i = 0; i < N_MEL; ++i) {
+      double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+      for (int k = 0; k < N_BINS; ++k) {
+        double f = (double)SR / 2 * (double)k / (double)(N_BINS - 1);
+        double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+        double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+        double w = lower < upper ? lower : upper;
+        if (w < 0) w = 0;
+        fb[(size_t)i * N_BINS + k] = (float)(w * enorm);
+      }
     }
-  }
-  m->mel.N = N_MEL; m->mel.K = N_BINS;
-  m->mel.w32 = (float*)ctx->dmalloc(fb.size() * sizeof(float));
-  CVK_CHECK_CUDA(cudaMemcpy(m->mel.w32, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ConvW w;
+    w.N = N_MEL; w.K = N_BINS;
+    w.w32 = (float*)ctx->dmalloc(fb.size() * sizeof(float));
+    CVK_CHECK_CUDA(cudaMemcpy(w.w32, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return w;
+  };
+  m->mel = filterbank(8000.0);
+  m->mel_nyq = filterbank((double)SR / 2);
   CVK_CHECK_CUDA(cudaDeviceSynchronize());
   ctx->mel_model = m;
 }
 
-void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* mel, cudaStream_t st) {
+// fmax_hz: 8000 (CosyVoice2) or 0 / 12000 (= sr/2: the reference's `fmax: null`, CosyVoice3).  lens[b] >= 721 samples (reflect
+// padding by 720 needs more than 720 samples, as in torch); frames = lens[b] / 480 (integer division: the tail shorter than a hop
+// only contributes through the frames that overlap it).
+void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, int fmax_hz, float* mel, cudaStream_t st) {
   if (!ctx->mel_model) mel_init(ctx);
   MelModel* g_mel = (MelModel*)ctx->mel_model;
   ctx->arena.reset();
   std::vector<int> frames(B), rows(B), off(B), ns(lens, lens + B);
   int acc = 0;
   for (int b = 0; b < B; ++b) {
-    CVK_REQUIRE(lens[b] >= N_FFT && lens[b] % HOP == 0, "mel_spectrogram: length must be a multiple of 480 and >= 1920");
+    CVK_REQUIRE(lens[b] > PAD, "mel_spectrogram: reflect padding by 720 needs at least 721 samples (torch raises as well)");
     frames[b] = lens[b] / HOP;
     rows[b] = frames[b] + 3;
     off[b] = acc;
@@ -141,7 +153,8 @@ void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, flo
   {
     Epilogue e;
     e.out = out;
-    conv_gemm_simt(ctx, st, mag, g_mel->mel, e);
+    CVK_REQUIRE(fmax_hz == 8000 || fmax_hz == 0 || fmax_hz == SR / 2, "mel_spectrogram: fmax must be 8000 or sr/2 (0 = null)");
+    conv_gemm_simt(ctx, st, mag, fmax_hz == 8000 ? g_mel->mel : g_mel->mel_nyq, e);
   }
   log_clamp_kernel<<<148, 256, 0, st>>>(out.f32(), (size_t)sr.R * N_MEL);
   ctx->launches++;

@@ -47,6 +47,8 @@ SIGNATURES = {
     "cvk_hift_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp, _c_int_p, _vp, _vp, _vp]),
     "cvk_flow_encoder": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_cfm_estimator": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "cvk_cfm_estimator_inplace": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp]),
+    "cvk_workspace_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "cvk_cfm_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, _vp, _vp]),
     "cvk_flow_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_cfm_set_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
@@ -66,6 +68,7 @@ SIGNATURES = {
     "cvk_lm_next_logp": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "cvk_ras_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "cvk_mel_spectrogram": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
+    "cvk_mel_spectrogram_ex": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
 }
 
 
@@ -263,6 +266,19 @@ class Context:
                                                int(streaming), _ptr(out), _stream()))
         return out
 
+    def cfm_estimator_inplace(self, x, mu, t, spks, cond, lens, streaming=False):
+        """the TensorRT engine contract (flow_matching.py:140-148): x [sum T, 80] float32 on the device is overwritten"""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        mu, t, spks, cond = (_f32(a, self.device) for a in (mu, t, spks, cond))
+        self._check(self.lib.cvk_cfm_estimator_inplace(self.h, _ptr(x), _ptr(mu), _ptr(t), _ptr(spks), _ptr(cond), _ints(lens), len(lens),
+                                                       int(streaming), _stream()))
+        return x
+
+    def workspace_bytes(self):
+        cap, high = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self.lib.cvk_workspace_bytes(self.h, ctypes.byref(cap), ctypes.byref(high)))
+        return cap.value, high.value
+
     def hift3_set_noise(self, rand_ini, sine_noise):
         """CosyVoice3 vocoder: SineGen2.rand_ini [9] and SineGen2.sine_waves [n,9] (module attributes of the reference)"""
         rand_ini = _f32(rand_ini.reshape(-1), self.device)
@@ -387,8 +403,9 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ mel
-    def mel_spectrogram(self, wav, lens):
+    def mel_spectrogram(self, wav, lens, fmax=8000):
+        """wav [sum N_b] -> mel [sum N_b // 480, 80]; fmax 8000 (CosyVoice2) or None / 12000 (CosyVoice3)"""
         wav = _f32(wav, self.device)
         mel = torch.empty(sum(int(l) // 480 for l in lens), 80, device=self.device)
-        self._check(self.lib.cvk_mel_spectrogram(self.h, _ptr(wav), _ints(lens), len(lens), _ptr(mel), _stream()))
+        self._check(self.lib.cvk_mel_spectrogram_ex(self.h, _ptr(wav), _ints(lens), len(lens), int(fmax or 0), _ptr(mel), _stream()))
         return mel

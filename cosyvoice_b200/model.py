@@ -57,6 +57,9 @@ class B200CosyVoice2Model:
     bistream_fill_token = 6563
     bistream_eos_token = 6561
     bistream_eop_token = None
+    # benchmark aid only (None = the reference's behaviour: decode "until met eos", llm.py:642-661, without any cap): random-init
+    # weights cannot be made to emit eos at a chosen time, so bench.py ends the text-streaming decode after this many ids
+    bistream_max_tokens = None
 
     def __init__(self, llm=None, flow=None, hift=None, fp16=False, precision="bf16", device=0, workspace_gb=24.0):
         # attribute names follow cli/model.py:245-275
@@ -329,6 +332,8 @@ class B200CosyVoice2Model:
                         lm_input = [(SPEECH, top)]
             lm_input = lm_input + [(TEXT, t) for t in text_cache] + [(LLM, 1)]       # llm.py:643
             while True:
+                if self.bistream_max_tokens is not None and len(out_tokens) >= self.bistream_max_tokens:
+                    break
                 top = sample(forward(want_logp=True), ignore_eos=False)
                 out_tokens.append(top)
                 if top >= speech_vocab:

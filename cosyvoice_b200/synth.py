@@ -174,6 +174,111 @@ def hift_shapes():
     return s
 
 
+# ---------------------------------------------------------------------------------------------- CosyVoice3 shapes
+def llm3_shapes(num_layers=24):
+    """CosyVoice3LM (llm/llm.py:664-705): no llm_embedding, 6761-way head without bias, 6761-row speech embedding."""
+    s = llm_shapes(num_layers)
+    for k in ("llm_embedding.weight", "llm_decoder.bias"):
+        s.pop(k)
+    s["llm_decoder.weight"] = (6761, 896)
+    s["speech_embedding.weight"] = (6761, 896)
+    return s
+
+
+def dit_flow_shapes(depth=22):
+    """CausalMaskedDiffWithDiT (flow/flow.py:286-414, cosyvoice3.yaml: DiT dim 1024, depth 22, 16 heads x 64, ff_mult 2)."""
+    s = OrderedDict()
+    s["input_embedding.weight"] = (6561, 80)
+    s["spk_embed_affine_layer.weight"] = (80, 192)
+    s["spk_embed_affine_layer.bias"] = (80,)
+    s["pre_lookahead_layer.conv1.weight"] = (1024, 80, 4)
+    s["pre_lookahead_layer.conv1.bias"] = (1024,)
+    s["pre_lookahead_layer.conv2.weight"] = (80, 1024, 3)
+    s["pre_lookahead_layer.conv2.bias"] = (80,)
+    p = "decoder.estimator."
+    s[p + "time_embed.time_mlp.0.weight"] = (1024, 256)
+    s[p + "time_embed.time_mlp.0.bias"] = (1024,)
+    s[p + "time_embed.time_mlp.2.weight"] = (1024, 1024)
+    s[p + "time_embed.time_mlp.2.bias"] = (1024,)
+    s[p + "input_embed.proj.weight"] = (1024, 320)
+    s[p + "input_embed.proj.bias"] = (1024,)
+    for c in ("conv1", "conv2"):
+        s[p + f"input_embed.conv_pos_embed.{c}.0.weight"] = (1024, 64, 31)
+        s[p + f"input_embed.conv_pos_embed.{c}.0.bias"] = (1024,)
+    for i in range(depth):
+        b = p + f"transformer_blocks.{i}."
+        s[b + "attn_norm.linear.weight"] = (6144, 1024)
+        s[b + "attn_norm.linear.bias"] = (6144,)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            s[b + f"attn.{n}.weight"] = (1024, 1024)
+            s[b + f"attn.{n}.bias"] = (1024,)
+        s[b + "ff.ff.0.0.weight"] = (2048, 1024)
+        s[b + "ff.ff.0.0.bias"] = (2048,)
+        s[b + "ff.ff.2.weight"] = (1024, 2048)
+        s[b + "ff.ff.2.bias"] = (1024,)
+    s[p + "norm_out.linear.weight"] = (2048, 1024)
+    s[p + "norm_out.linear.bias"] = (2048,)
+    s[p + "proj_out.weight"] = (80, 1024)
+    s[p + "proj_out.bias"] = (80,)
+    return s
+
+
+def hift_causal_shapes():
+    """CausalHiFTGenerator (hifigan/generator.py:572-726): conv_pre k5 (look-right 4), CausalConv1dUpsample = plain Conv1d weights,
+    causal f0 predictor (first conv k4)."""
+    s = hift_shapes()
+    out = OrderedDict()
+    for k, v in s.items():
+        if k.startswith("conv_pre.parametrizations.weight.original1"):
+            v = (512, 80, 5)
+        if k.startswith("ups."):
+            i = int(k.split(".")[1])
+            cin, cout = 512 // 2 ** i, 512 // 2 ** (i + 1)
+            kk = (16, 11, 7)[i]
+            if k.endswith("bias"):
+                v = (cout,)
+            elif k.endswith("original0"):
+                v = (cout, 1, 1)
+            else:
+                v = (cout, cin, kk)
+        if k == "f0_predictor.condnet.0.parametrizations.weight.original1":
+            v = (512, 80, 4)
+        out[k] = v
+    return out
+
+
+DIT_GAINS = {"attn_norm.linear.weight": 0.1, "norm_out.linear.weight": 0.3, "conv_pos_embed": 0.5, "proj_out.weight": 0.012,
+             "input_embed.proj.weight": 0.25}
+
+
+def cosyvoice3_state_dicts(device, seed=1986, num_layers=24, depth=22):
+    """(llm_sd, flow_sd, hift_sd) of Fun-CosyVoice3-0.5B shape (cosyvoice3.yaml) for bench config #4.  The head rows of the special
+    ids are arranged like oracle.lm.bistream_state_dict3 (constant channel 0 + per-row weight = an emulated bias: CosyVoice3LM's head
+    has none): no special id is ever drawn (the text-streaming decode raises on them, llm.py:635, 653); the benchmark ends the decode by a cap."""
+    llm = random_state_dict(llm3_shapes(num_layers), device, seed, LLM_GAINS)
+    llm["llm.model.model.embed_tokens.weight"][:, 0] = 6.0
+    llm["speech_embedding.weight"][:, 0] = 6.0
+    for i in range(num_layers):            # channel 0 of the residual stream stays the planted constant through every layer
+        llm[f"llm.model.model.layers.{i}.self_attn.o_proj.weight"][0, :] = 0.0
+        llm[f"llm.model.model.layers.{i}.mlp.down_proj.weight"][0, :] = 0.0
+    w = llm["llm_decoder.weight"]
+    w[:, 0] = 0.0
+    w[6561:, 0] = -40.0                    # no special id is ever drawn; bench.py caps the decode (B200CosyVoice2Model.bistream_max_tokens)
+    flow = random_state_dict(dit_flow_shapes(depth), device, seed + 1, DIT_GAINS)
+    hift = random_state_dict(hift_causal_shapes(), device, seed + 2, HIFT_GAINS)
+    return llm, flow, hift
+
+
+def cv3_bistream_request(i, n_text=48, chunks=4):
+    """config #4 request: the tts text arrives as a generator of `chunks` pieces (example.py:62-67 pattern), the prompt text
+    contains <|endofprompt|> (151646, llm.py:585), 75 prompt speech tokens / 150 prompt mel frames."""
+    u = z10_utterance(1000 + i, n_text)
+    u["prompt_text"][0, 5] = 151646
+    step = (n_text + chunks - 1) // chunks
+    u["text_chunks"] = [u["text"][:, k:k + step] for k in range(0, n_text, step)]
+    return u
+
+
 # ---------------------------------------------------------------------------------------------- random init
 def random_state_dict(shapes, device, seed, gains=None):
     """Scale rules keep activations O(1) through the depth of each stage (same rules as the test generator)."""

@@ -58,6 +58,9 @@ double cvk_last_op_ms(cvk_ctx* ctx);
 /* debug: copy (and clear) the device timeline buffer filled by instrumented kernels when "debug_timeline" is on */
 int cvk_debug_read(cvk_ctx* ctx, long long* out, int n);
 /* debug switch: 1 (default) = bf16 GEMMs on the tcgen05 kernel, 0 = same operands through the SIMT kernel */
+/* workspace arena of the context (SURVEY.md §8b `cvk_workspace_bytes`): capacity given to cvk_create and the high-water mark of
+ * the calls made so far - what a caller needs to size cvk_create for its largest batch. */
+int cvk_workspace_bytes(cvk_ctx* ctx, size_t* capacity, size_t* high_water);
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value);
 
 /* Per-kernel-family device timing for the roofline report of bench.py: CUDA events are recorded around every launch
@@ -118,6 +121,10 @@ int cvk_flow_encoder(cvk_ctx* ctx, const int32_t* tokens, const int* lens_host, 
  * x, mu, cond [sum T,80]; t [B]; spks [B,80]; out [sum T,80]; mask = ones within each length. */
 int cvk_cfm_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t, const float* spks, const float* cond,
                       const int* lens_host, int B, int streaming, float* out, void* stream);
+/* the engine contract itself (flow/flow_matching.py:140-148: the last binding of the TensorRT context is x.data_ptr(), the
+ * result overwrites x).  `out` of cvk_cfm_estimator may alias `x` as well: x is consumed before the first write. */
+int cvk_cfm_estimator_inplace(cvk_ctx* ctx, float* x, const float* mu, const float* t, const float* spks, const float* cond,
+                              const int* lens_host, int B, int streaming, void* stream);
 /* flow/flow_matching.py:203-227 + 71-124: fixed seed-0 noise unless z given ([sum T,80]), cosine schedule, Euler,
  * CFG.  mu, cond [sum T,80]; spks [B,80]; out mel [sum T,80]. */
 int cvk_cfm_solve(cvk_ctx* ctx, const float* mu, const float* spks, const float* cond, const int* lens_host, int B,
@@ -199,9 +206,13 @@ int cvk_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* histo
                    const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- mel frontend
- * replaces third_party/Matcha-TTS/matcha/utils/audio.py:45-82 with cosyvoice2.yaml:150-158 parameters.
- * wav [sum N] (24 kHz, N multiple of 480) -> mel [sum N/480, 80] */
+ * replaces third_party/Matcha-TTS/matcha/utils/audio.py:45-82 with cosyvoice2.yaml:150-158 parameters (n_fft 1920, hop 480,
+ * 80 mels, fmin 0, fmax 8000, center False).  wav [sum N_b] (24 kHz, any N_b >= 721: the reflect padding is taken about the true
+ * last sample) -> mel [sum floor(N_b/480), 80] */
 int cvk_mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, float* mel, void* stream);
+/* same with the filterbank's upper edge as a parameter: fmax_hz = 8000 (CosyVoice2) or 0 / 12000 = sr/2 (`fmax: null` of
+ * examples/libritts/cosyvoice3/conf/cosyvoice3.yaml:140-147) */
+int cvk_mel_spectrogram_ex(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, int fmax_hz, float* mel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -354,6 +354,13 @@ def gen_mel():
     o = mel.mel_spectrogram(y)
     print(f"  max|oracle-ref| {(r - o).abs().max():.3g}")
     save("mel_b2", mel=r.numpy())
+    # CosyVoice3 feat_extractor (cosyvoice3.yaml:140-147: fmax null) on a length that is NOT a multiple of the hop: the reflect
+    # padding is about the true last sample and floor(N / 480) frames come out
+    y3 = cases.mel_case(B=2, n=24137, seed=6)
+    r3 = ref_mel(y3, 1920, 80, 24000, 480, 1920, 0, None, center=False)
+    o3 = mel.mel_spectrogram(y3, fmax=None)
+    print(f"  fmax=None, N=24137: {tuple(r3.shape)}, max|oracle-ref| {(r3 - o3).abs().max():.3g}")
+    save("mel_b2_cv3", mel=r3.numpy())
 
 
 def gen_masks():

@@ -127,3 +127,20 @@ def test_persistent_gemm_flow_bit_identical():
     assert lens == [2 * n for n in n_tok]
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]), maxdiff(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_engine_estimator_inplace_contract(precision, golden):
+    """INTEGRATION.md §2 executed: cosyvoice_b200.engine.CvkEstimator at the reference's TensorRT swap point
+    (flow_matching.py:126-153) - channel-major [2,80,T] tensors in, result written over x."""
+    from cosyvoice_b200.engine import CvkEstimator
+    g = golden("flow_small")
+    c, sd, cfg = model(precision, "small")
+    est = CvkEstimator(None, context=c)
+    x, mask, mu, t, spks, cond = cases.estimator_case()
+    xd = x.clone().cuda()
+    ret = est(xd, mask.cuda(), mu.cuda(), t.cuda(), spks.cuda(), cond.cuda(), streaming=False)
+    assert ret.data_ptr() == xd.data_ptr()
+    np.testing.assert_allclose(xd.cpu().numpy(), g["est_offline"], rtol=1e-2, atol=1e-4)
+    cap, high = c.workspace_bytes()
+    assert 0 < high <= cap

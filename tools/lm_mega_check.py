@@ -106,3 +106,8 @@ if a.timeline:
         if f:
             print(f"fine stamps layer 1, {name} ({len(f)}): deltas us:", [round((f[i + 1] - f[i]) / 1e3, 2) for i in range(len(f) - 1)])
     print("sampler end:", round((ch[10] - ch[0]) / 1e3, 2) if ch[10] else 0)
+
+    for name, off, n in (("sampler stages (CTA 0)", 1024, 16), ("MMA thread gate_up L1 (CTA 0)", 2048 + 1280, 40), ("epilogue thread gate_up L1 (CTA 0)", 2048 + 1400, 8)):
+        f = [x for x in t[off:off + n] if x]
+        if f:
+            print(f"{name} ({len(f)} stamps): deltas us:", [round((f[i + 1] - f[i]) / 1e3, 2) for i in range(len(f) - 1)])
