@@ -377,11 +377,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom
-          umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < TC_BK / 16; ++k)     // advance 16 elements = 32 B along K inside the 128-B swizzle atom: +2 in the address field
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(smem_u32(&bar_empty[s]));   // frees the smem stage once these MMAs have read it
       }
       umma_commit(smem_u32(&bar_acc));          // accumulator complete
@@ -646,9 +645,9 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);     // +32 bytes along K = +2 in the 16-byte address field
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&bar_empty[s]));
         }
         umma_commit(smem_u32(&bar_accf[buf]));

@@ -234,12 +234,21 @@ attn_fused_kernel(const float* __restrict__ partial /*[S][rows][1152]*/, int spl
   const int b = blockIdx.x, kvh = blockIdx.y;
   pdl_trigger();
   tl_stamp(tl, 0);
-  pdl_wait();
-  tl_stamp(tl, 1);
   bf16* kb = kc + ((size_t)b * NKV + kvh) * max_ctx * HD;
   bf16* vb = vc + ((size_t)b * NKV + kvh) * max_ctx * HD;
+  // Before waiting for the qkv projection: this warp's first 16-key block of OLD cache rows (written by earlier decode steps /
+  // the prefill, i.e. by grids that completed long before this one could start) is pulled from HBM while the projection still
+  // runs.  ctx_len[b] may be read mid-update by this step's sampler (it only grows by one per step): either value is a valid
+  // lower bound of the number of finished rows, and only blocks entirely below it are preloaded.
+  const int p0 = min(*reinterpret_cast<const volatile int*>(ctx_len + b), max_ctx);
+  const int wj0 = (threadIdx.x >> 5) * 16;
+  KvFrag pre;
+  const bool have_pre = wj0 + 16 <= p0;
+  if (have_pre) decode_attn_load_block(kb, vb, wj0, p0, threadIdx.x & 31, pre);
+  pdl_wait();
+  tl_stamp(tl, 1);
   decode_attn_unit<AF_WARPS, 0>(sm_all, threadIdx.x, partial, splits, rows, b, kvh, bias, kb, vb, ctx_len[b], max_ctx, inv_freq,
-                                out + (size_t)b * ldo);
+                                out + (size_t)b * ldo, pre, have_pre);
   tl_stamp(tl, 2);
 }
 

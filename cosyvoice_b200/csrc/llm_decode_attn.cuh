@@ -33,6 +33,34 @@ __device__ __forceinline__ void attn_bar() {
 template <int NW>
 __host__ __device__ constexpr int decode_attn_smem_floats() { return (NH / NKV + 2) * HD + NW * 8 * 2 + NW * (NH / NKV) * HD; }
 
+// K / V fragments of one 16-key block (rows j0 .. j0+15, all below `L`), in the MMA operand layout used by decode_attn_unit
+struct KvFrag {
+  uint32_t kf[2][4][2], vw[4][4];
+};
+__device__ __forceinline__ void decode_attn_load_block(const bf16* __restrict__ kb, const bf16* __restrict__ vb, int j0, int L, int lane, KvFrag& f) {
+  const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (size_t)min(j0 + nt * 8 + g, L - 1) * HD);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      f.kf[nt][kk][0] = kr[kk * 8 + t4];
+      f.kf[nt][kk][1] = kr[kk * 8 + 4 + t4];
+    }
+  }
+  const uint32_t* v0 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + t4 * 2, L - 1) * HD);
+  const uint32_t* v1 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + t4 * 2 + 1, L - 1) * HD);
+  const uint32_t* v2 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 8 + t4 * 2, L - 1) * HD);
+  const uint32_t* v3 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 9 + t4 * 2, L - 1) * HD);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f.vw[q][0] = v0[q * 8 + g];
+    f.vw[q][1] = v1[q * 8 + g];
+    f.vw[q][2] = v2[q * 8 + g];
+    f.vw[q][3] = v3[q * 8 + g];
+  }
+}
+
 // tid / warp / lane: coordinates inside the group of NW warps that runs the unit (all NW*32 threads must call).
 // partial [splits][rows][1152] fp32 split-K sums of the qkv projection of row b; kb / vb: this (row, kv head)'s cache
 // [max_ctx][64]; out: bf16 [.. ldo], this row's attention output (columns of the kv group's 7 query heads).
@@ -41,7 +69,9 @@ __host__ __device__ constexpr int decode_attn_smem_floats() { return (NH / NKV +
 template <int NW, int BAR_ID, int SPLITS = 0>
 __device__ __forceinline__ void decode_attn_unit(float* __restrict__ sm_all, int tid, const float* __restrict__ partial, int splits, int rows,
                                                  int b, int kvh, const float* __restrict__ bias, bf16* __restrict__ kb, bf16* __restrict__ vb,
-                                                 int pos, int max_ctx, const float* __restrict__ inv_freq, bf16* __restrict__ out_row) {
+                                                 int pos, int max_ctx, const float* __restrict__ inv_freq, bf16* __restrict__ out_row,
+                                                 KvFrag& fr /*fragment registers; if have_pre: this warp's first block, loaded early*/,
+                                                 bool have_pre) {
   constexpr int G = NH / NKV;
   constexpr int NT = NW * 32;
   const int warp = tid >> 5, lane = tid & 31;
@@ -130,29 +160,9 @@ __device__ __forceinline__ void decode_attn_unit(float* __restrict__ sm_all, int
   for (int j0 = warp * 16; j0 < L; j0 += NW * 16) {
     // every load of the block is issued before the first use: one memory round trip per 16 keys.  Rows past the end are
     // clamped to the last valid row (finite data), their probabilities are forced to zero below.
-    uint32_t kf[2][4][2], vw[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kb + (size_t)min(j0 + nt * 8 + g, L - 1) * HD);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        kf[nt][kk][0] = kr[kk * 8 + t4];
-        kf[nt][kk][1] = kr[kk * 8 + 4 + t4];
-      }
-    }
-    {
-      const uint32_t* v0 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + t4 * 2, L - 1) * HD);
-      const uint32_t* v1 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + t4 * 2 + 1, L - 1) * HD);
-      const uint32_t* v2 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 8 + t4 * 2, L - 1) * HD);
-      const uint32_t* v3 = reinterpret_cast<const uint32_t*>(vb + (size_t)min(j0 + 9 + t4 * 2, L - 1) * HD);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        vw[q][0] = v0[q * 8 + g];
-        vw[q][1] = v1[q * 8 + g];
-        vw[q][2] = v2[q * 8 + g];
-        vw[q][3] = v3[q * 8 + g];
-      }
-    }
+    if (!(have_pre && j0 == warp * 16)) decode_attn_load_block(kb, vb, j0, L, lane, fr);
+    uint32_t (&kf)[2][4][2] = fr.kf;
+    uint32_t (&vw)[4][4] = fr.vw;
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {

@@ -451,8 +451,9 @@ lm_mega_kernel(const MegaParams p) {
         const int b = u / NKV, kvh = u % NKV;
         bf16* kb = kc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
         bf16* vb = vc_l + ((size_t)b * NKV + kvh) * p.max_ctx * HD;
+        KvFrag fr;
         decode_attn_unit<MG_NW, 1, MG_SPL_QKV>(attn_sm, wt, p.part_qkv, MG_SPL_QKV, B, b, kvh, Lw.qkv_bias, kb, vb, p.ctx_len[b], p.max_ctx,
-                                               p.inv_freq, p.att + (size_t)b * D);
+                                               p.inv_freq, p.att + (size_t)b * D, fr, false);
         worker_bar();
       }
       grid_sync();

@@ -171,7 +171,10 @@ class B200CosyVoice2Model:
         mx = max(maxs)
         st = []
         try:
-            with torch.cuda.stream(main):
+            # The prefill uses the context's shared workspace arena, so it runs on the model's stream under ctx.lock like every other
+            # workspace call (flow / vocoder): the lock orders the host calls, the common stream orders the device work.  Only the
+            # decode steps - which touch nothing but their session - run on the generation's own stream.
+            with torch.cuda.stream(self.stream):
                 if uniforms is None and self.uniforms_override is not None:
                     uniforms = self.uniforms_override
                 if uniforms is None:
@@ -189,18 +192,22 @@ class B200CosyVoice2Model:
                     c = dict(rows=rows, n=len(rows), key=key, sess=sess,
                              min_len=torch.tensor([mins[r] for r in rows], dtype=torch.int32, device=d),
                              max_len=torch.tensor([maxs[r] for r in rows], dtype=torch.int32, device=d),
+                             max_len_host=torch.tensor([maxs[r] for r in rows], dtype=torch.int32),
                              out_ids=torch.zeros(len(rows), mx + 1, dtype=torch.int32, device=d),
                              out_count=torch.zeros(len(rows), dtype=torch.int32, device=d),
                              done=torch.zeros(len(rows), dtype=torch.int32, device=d),
                              U=uniforms[:, rows, :].contiguous(), live=len(rows))
                     st.append(c)
                     with self.ctx.lock:
-                        self.ctx.lm_prefill(sess, tt, tl, ss, sl)         # prefills share the workspace arena: serialised
-                ready = torch.cuda.Event()
-                ready.record(main)
+                        self.ctx.lm_prefill(sess, tt, tl, ss, sl)
+                        ready = torch.cuda.Event()
+                        ready.record(self.stream)
+                    c["ready"] = ready
             while len(self._lm_streams) < chains:
                 self._lm_streams.append(torch.cuda.Stream(d))
             n = 0
+            for c in st:
+                c["left"] = mx                     # upper bound of the steps this chain still needs (refined after every block)
             while True:
                 for g, c in enumerate(st):
                     if c["live"] == 0:
@@ -208,8 +215,11 @@ class B200CosyVoice2Model:
                     s_g = main if chains == 1 else self._lm_streams[g]
                     with torch.cuda.stream(s_g):
                         if n == 0:
-                            s_g.wait_event(ready)
-                        self.ctx.lm_decode(c["sess"], steps_per_sync, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"],
+                            s_g.wait_event(c["ready"])
+                        # never run past the longest possible remainder: the last block is cut to what the live rows can still emit
+                        # (round 1 always ran whole blocks: 320 steps for rows that end at 300)
+                        c["block"] = max(1, min(steps_per_sync, c["left"]))
+                        self.ctx.lm_decode(c["sess"], c["block"], c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"],
                                            want_live=False)
                 for g, c in enumerate(st):
                     if c["live"] == 0:
@@ -217,6 +227,9 @@ class B200CosyVoice2Model:
                     s_g = main if chains == 1 else self._lm_streams[g]
                     with torch.cuda.stream(s_g):
                         c["live"] = self.ctx.lm_decode(c["sess"], 0, c["U"], c["min_len"], c["max_len"], c["out_ids"], c["out_count"], c["done"])
+                        if c["live"]:
+                            cnt, dn = c["out_count"].cpu(), c["done"].cpu()
+                            c["left"] = int(((c["max_len_host"] - cnt) * (dn == 0)).max())
                 n += steps_per_sync
                 if on_progress is not None:
                     on_progress(st[0]["out_ids"], st[0]["out_count"], st[0]["live"])

@@ -48,7 +48,9 @@ def test_decode_golden(precision, sd, golden):
     mel_tm, lens = to_tm(melx)
     wav = c.hift_decode(mel_tm, lens, torch.from_numpy(g["source"]).reshape(-1)).view(2, -1)
     d = maxdiff(wav, torch.from_numpy(g["decode"]))
-    assert d < (1e-3 if precision == "fp32" else 8e-2), d
+    # tensor-core mode: IEEE-half operands (TF32-class mantissa, like the reference's default cuDNN convolutions)
+    print(f"[hift decode golden, {precision}] max |d| {d:.3g}")
+    assert d < (1e-3 if precision == "fp32" else 4e-3), d
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -68,7 +70,7 @@ def test_inference_ragged_batch_vs_oracle(precision, sd):
         assert maxdiff(src[o:o + T * 480], osrc.reshape(-1)) < 3e-3
         # the vocoder body is compared with the oracle's source injected (phase conditioning)
         w2 = c.hift_decode(m[0].t().contiguous(), [T], osrc.reshape(-1))
-        assert maxdiff(w2, ow.reshape(-1)) < (1e-3 if precision == "fp32" else 8e-2)
+        assert maxdiff(w2, ow.reshape(-1)) < (1e-3 if precision == "fp32" else 4e-3)
         o += T * 480
     assert wav.abs().max().item() <= 0.99 + 1e-6
 

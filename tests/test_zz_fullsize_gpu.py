@@ -43,8 +43,8 @@ def test_lm_teacher_forced_logp_fullsize(golden):
         overlap.append(len(a & b))
     am = int((got.argmax(-1) == ref.argmax(-1)).sum())
     print(f"[full-size LM, bf16] max |dlogp| {d:.4g} on |logp| <= {ref.abs().max().item():.3g}; top-25 overlap per row {overlap}; arg-max equal {am}/{ref.shape[0]}")
-    assert d < 0.35, d
-    assert min(overlap) >= 18, overlap
+    assert d < 0.35, d                    # measured 0.24 on |logp| <= 32.7
+    assert min(overlap) >= 22, overlap    # measured 24-25 of 25
 
 
 def test_lm_persistent_decode_vs_per_op_chain_batch32():
@@ -108,7 +108,8 @@ def test_flow_mel_fullsize(golden):
     dd = (mel.cpu() - ref).abs()
     print(f"[full-size flow, bf16] mel max |d| {dd.max().item():.4g}, mean |d| {dd.mean().item():.4g} on |mel| <= {ref.abs().max().item():.3g}; "
           f"yardstick (oracle under torch CPU bf16 autocast vs fp32): max {float(g['mel_autocast_bf16_max']):.4g}, mean {float(g['mel_autocast_bf16_mean']):.4g}")
-    assert dd.max().item() < 0.5 and dd.mean().item() < 0.05, (dd.max().item(), dd.mean().item())
+    # measured on B200: max 0.035, mean 0.0073 - the same as torch's own bf16 autocast shows against fp32 on this model (0.041 / 0.0077)
+    assert dd.max().item() < 0.08 and dd.mean().item() < 0.015, (dd.max().item(), dd.mean().item())
 
 
 def test_hift_wav_fullsize(golden):
@@ -124,4 +125,6 @@ def test_hift_wav_fullsize(golden):
     d = (wav - ref).abs()
     snr = 10 * torch.log10(ref.pow(2).sum() / (wav - ref).pow(2).sum()).item()
     print(f"[full-size vocoder, ctx precision bf16] wav max |d| {d.max().item():.4g}, rms {d.pow(2).mean().sqrt().item():.4g} on |wav| <= {ref.abs().max().item():.3g}; SNR {snr:.1f} dB")
-    assert d.max().item() < 8e-2, d.max().item()
+    # IEEE-half operands (10-bit mantissa, the class of the reference's default TF32 convolutions): measured 1.0e-3 / 54 dB SNR on B200;
+    # SURVEY.md §8(c)(ii) asks for <= 2e-3 with the source injected
+    assert d.max().item() < 2e-3 and snr > 48.0, (d.max().item(), snr)
