@@ -121,6 +121,7 @@ int cvk_set_option(cvk_ctx* ctx, const char* key, int value) {
   std::string k(key ? key : "");
   if (k == "use_tc") ctx->use_tc = value;
   else if (k == "tc_bn256") ctx->tc_bn256 = value;
+  else if (k == "tc_pbn256") ctx->tc_pbn256 = value;
   else if (k == "tc_epi") ctx->tc_epi = value;
   else if (k == "tc_persist") ctx->tc_persist = value;
   else if (k == "op_out_bf16") ctx->op_out_bf16 = value;

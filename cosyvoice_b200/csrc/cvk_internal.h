@@ -178,6 +178,7 @@ struct cvk_ctx {
   double op_ms = 0.0;
   int tc_epi = 2;                           // tcgen05 GEMM epilogue: 2 = smem-staged TMA stores, 0 = direct stores, 1 = direct + prefetch
   int tc_persist = 2;                       // tcgen05 GEMM, tiles > SMs: persistent CTAs + double-buffered TMEM accumulators (2 = 16 epilogue warps, 1 = 8, 0 = off)
+  int tc_pbn256 = 1;                        // persistent tcgen05 GEMM: 128x256 tiles for 16-bit outputs with N % 256 == 0 (halves the A re-reads out of L2)
   int tc_bn256 = 0;                         // experiment: 128x256 tiles (1 CTA/SM) instead of 128x128 (2 CTAs/SM)
   void* dbg = nullptr;                      // device int64[1024] timeline buffer (debug option)
   void* tl = nullptr;                       // device int64[4096] LM-chain timeline (debug option chain_timeline): 4 slots per launch

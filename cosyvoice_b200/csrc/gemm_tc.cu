@@ -571,13 +571,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NSTG, int EW>   // EW epilogue warps (8 or 16): EW/4 warps share a TMEM lane quarter and split the columns
+// BN = 128 or 256 output columns per tile.  The wide tile halves the re-reads of the A rows: ncu shows the 128 x 128 kernel moving
+// 6.5-6.9 TB/s from L2 to the SMs on the K = 256 / 512 GEMMs of the estimator (l1tex__m_xbar2l1tex_read_bytes: 494 MB for a
+// 32.8 GFLOP to_qkv) - operand traffic out of L2, not the tensor pipe, bounds them (profiles/r02_flow.md).
+template <int NSTG, int EW, int BN>   // EW epilogue warps (8 or 16): EW/4 warps share a TMEM lane quarter and split the columns
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                             const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, int N, int K, int taps,
                             int dil, int shift0, int rowsOut, EpiDev ep, int ntn, int ntiles, int stg_bufs) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int BN = 128;
   __shared__ __align__(8) uint64_t bar_full[NSTG];
   __shared__ __align__(8) uint64_t bar_empty[NSTG];
   __shared__ __align__(8) uint64_t bar_accf[2];
@@ -749,18 +751,18 @@ void launch_tc(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUten
   conv_gemm_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, epi_mode, (long long*)ctx->dbg);
 }
 
-template <int NSTG, int EW>
+template <int NSTG, int EW, int BN>
 void launch_tc_persist(cvk_ctx* ctx, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& to2,
                        const ConvW& W, int rowsOut, const EpiDev& e, int stg_bufs) {
-  constexpr size_t smem = (size_t)NSTG * (TC_BM * TC_BK * 2 + 128 * TC_BK * 2) + 65536 + 1024;
+  constexpr size_t smem = (size_t)NSTG * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 65536 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    CVK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<NSTG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<NSTG, EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int ntn = ceil_div(W.N, 128), ntiles = ntn * ceil_div(rowsOut, TC_BM);
+  const int ntn = ceil_div(W.N, BN), ntiles = ntn * ceil_div(rowsOut, TC_BM);
   const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
-  conv_gemm_tc_persist_kernel<NSTG, EW><<<grid, 64 + 32 * EW, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, ntn, ntiles, stg_bufs);
+  conv_gemm_tc_persist_kernel<NSTG, EW, BN><<<grid, 64 + 32 * EW, smem, st>>>(ta, tw, to, to2, W.N, W.K, W.taps, W.dil, W.shift0, rowsOut, e, ntn, ntiles, stg_bufs);
 }
 
 }  // namespace
@@ -772,7 +774,10 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
   CVK_REQUIRE(W.K % 8 == 0 && A.ld % 8 == 0 && ((uintptr_t)A.p & 15) == 0, "conv_gemm_tc: operands must be 16-byte aligned");
   CVK_REQUIRE(ep.out.p != nullptr && ep.out.cols >= W.N, "conv_gemm_tc: bad output");
   EncodeTiledFn enc = get_encode(ctx);
-  const int BN = ctx->tc_bn256 && W.N > 128 ? 256 : (W.N > 64 ? 128 : 64);
+  // persistent 128 x 256 tiles: 16-bit single output (64 KB staging tile), N a multiple of 256, more tiles than SMs
+  const bool persist256 = ctx->tc_persist && ctx->tc_pbn256 && ctx->tc_epi == 2 && W.N % 256 == 0 && ep.out.esize() == 2 && !ep.out2.p && !ep.accumulate &&
+                          (W.N / 256) * ceil_div(ep.out.rows, TC_BM) > ctx->num_sms;
+  const int BN = (persist256 || (ctx->tc_bn256 && W.N > 128)) ? 256 : (W.N > 64 ? 128 : 64);
   CUtensorMap ta, tw;
   {
     cuuint64_t dims[2] = {(cuuint64_t)W.K, (cuuint64_t)A.rows};
@@ -829,10 +834,17 @@ void conv_gemm_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& A, const ConvW& W, c
   }
   const size_t need_stage = (size_t)TC_BM * 128 * ep.out.esize() + (ep.out2.p ? (size_t)TC_BM * 128 * ep.out2.esize() : 0);
   const int ntiles_p = ceil_div(W.N, 128) * ceil_div(rowsOut, TC_BM);
+  if (persist256 && epi_mode == 2) {
+    if (ctx->tc_persist == 2) launch_tc_persist<3, 16, 256>(ctx, st, ta, tw, to, to2, W, rowsOut, e, 1);
+    else launch_tc_persist<3, 8, 256>(ctx, st, ta, tw, to, to2, W, rowsOut, e, 1);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    return;
+  }
   if (ctx->tc_persist && BN == 128 && epi_mode == 2 && need_stage <= 65536 && ntiles_p > ctx->num_sms) {
     // more tiles than SMs: persistent CTAs with double-buffered accumulators (epilogue overlaps the next main loop)
-    if (ctx->tc_persist == 2) launch_tc_persist<4, 16>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
-    else launch_tc_persist<4, 8>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
+    if (ctx->tc_persist == 2) launch_tc_persist<4, 16, 128>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
+    else launch_tc_persist<4, 8, 128>(ctx, st, ta, tw, to, to2, W, rowsOut, e, need_stage <= 32768 ? 2 : 1);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
     return;
