@@ -394,6 +394,30 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
                  (cudaStream_t)stream);
   CVK_API_END
 }
+int cvk_flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(out != nullptr, "cvk_flow_stream_create: bad arguments");
+  *out = flow_stream_create(ctx, max_frames, n_timesteps);
+  CVK_API_END
+}
+void cvk_flow_stream_destroy(cvk_ctx* ctx, cvk_flow_stream* fs) {
+  if (!ctx || !fs) return;
+  try { cudaSetDevice(ctx->device); flow_stream_destroy(fs); } catch (...) {}
+}
+long long cvk_flow_stream_bytes(const cvk_flow_stream* fs) { return fs ? (long long)flow_stream_bytes(fs) : 0; }
+int cvk_flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(fs && embedding && (prompt_feat || prompt_frames == 0), "cvk_flow_stream_begin: bad arguments");
+  flow_stream_begin(ctx, fs, prompt_feat, prompt_frames, embedding, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, int n_tokens, float* mel_out, int mel_capacity_frames,
+                          int* n_frames_out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(fs && tokens && mel_out && n_frames_out && n_tokens > 3, "cvk_flow_stream_chunk: bad arguments");
+  *n_frames_out = flow_stream_chunk(ctx, fs, tokens, n_tokens, mel_out, mel_capacity_frames, (cudaStream_t)stream);
+  CVK_API_END
+}
 int cvk_cfm_set_noise(cvk_ctx* ctx, const float* noise_tm, int T, int on_device) {
   CVK_API_BEGIN
   CVK_REQUIRE(noise_tm && T > 0, "cvk_cfm_set_noise: bad arguments");

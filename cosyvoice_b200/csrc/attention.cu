@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
                                                         const T* __restrict__ v, int ldv, const T* __restrict__ pos, int ldp, int pos_rows, int pos_center,
                                                         const float* __restrict__ bias_u, const float* __restrict__ bias_v,
                                                         const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale, int kv_div,
-                                                        T* __restrict__ out, int ldo) {
+                                                        T* __restrict__ out, int ldo, const int* __restrict__ kstart, const int* __restrict__ klen,
+                                                        const int* __restrict__ qoff) {
   __shared__ float Qs[BQ][HD + 1];
   __shared__ float Ks[BKEY][HD + 1];
   __shared__ float Vs[BKEY][HD + 1];
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
   __shared__ float dvu[HD];   // bias_v - bias_u: (q+v) = (q+u) + dvu
 
   const int b = blockIdx.z, h = blockIdx.y;
-  const int L = len[b], s0 = start[b];
+  const int L = len[b], s0 = start[b];               // query rows
+  const int Lk = klen ? klen[b] : L, ks0 = kstart ? kstart[b] : s0, q0 = qoff ? qoff[b] : 0;   // key rows; absolute position of query 0
   const int i0 = blockIdx.x * BQ;
   if (i0 >= L) return;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
@@ -44,8 +46,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
   }
   if (RELPOS && t < HD) dvu[t] = bias_v[h * HD + t] - bias_u[h * HD + t];
   // highest visible key over the queries of this tile
-  int i_last = min(i0 + BQ, L) - 1;
-  int kmax = chunk > 0 ? min(L, (i_last / chunk + 1) * chunk) : L;
+  int i_last = q0 + min(i0 + BQ, L) - 1;
+  int kmax = chunk > 0 ? min(Lk, (i_last / chunk + 1) * chunk) : Lk;
 
   float m_run[4], l_run[4], o[4][4];
 #pragma unroll
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     int i = i0 + ty * 4 + a;
-    klim[a] = chunk > 0 ? min(L, (i / chunk + 1) * chunk) : L;
+    klim[a] = chunk > 0 ? min(Lk, ((q0 + i) / chunk + 1) * chunk) : Lk;
     if (i >= L) klim[a] = 0;
   }
 
@@ -68,9 +70,9 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
     for (int e = t; e < BKEY * HD; e += 128) {
       int j = e >> 6, d = e & 63;
       float kv = 0.f, vv = 0.f;
-      if (j0 + j < L) {
-        kv = to_f32(k[(size_t)(s0 + j0 + j) * ldk + (h / kv_div) * HD + d]);
-        vv = to_f32(v[(size_t)(s0 + j0 + j) * ldv + (h / kv_div) * HD + d]);
+      if (j0 + j < Lk) {
+        kv = to_f32(k[(size_t)(ks0 + j0 + j) * ldk + (h / kv_div) * HD + d]);
+        vv = to_f32(v[(size_t)(ks0 + j0 + j) * ldv + (h / kv_div) * HD + d]);
       }
       Ks[j][d] = kv;
       Vs[j][d] = vv;
@@ -163,25 +165,29 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ q,
 }  // namespace
 
 void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                      float scale, const Mat& out, int kv_div);
+                      float scale, const Mat& out, int kv_div, const KvGeom* kg);
 
 void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                   float scale, const Mat& out, int kv_div) {
+                   float scale, const Mat& out, int kv_div, const KvGeom* kg) {
+  const int* ks = kg ? kg->d_kstart : nullptr;
+  const int* kl = kg ? kg->d_klen : nullptr;
+  const int* qo = kg ? kg->d_qoff : nullptr;
+  CVK_REQUIRE(!kg || (ks && kl && qo), "attention: incomplete key/value geometry");
   CVK_REQUIRE(q.dtype == k.dtype && q.dtype == v.dtype && q.dtype == out.dtype, "attention: mixed dtypes");
   dim3 grid(ceil_div(s.max_len, BQ), H, s.B);
   double fl = 0;
   for (int b = 0; b < s.B; ++b) fl += 4.0 * (double)s.len[b] * s.len[b] * 64 * H * (chunk > 0 ? 0.5 : 1.0);
   ProfScope ps(ctx, st, FAM_ATTN, fl, (double)s.sum_len * H * 64 * 4 * q.esize());
   if (q.dtype == DT_BF16 && ctx->use_tc_attn) {
-    attention_fwd_tc(ctx, st, q, k, v, s, H, chunk, scale, out, kv_div);
+    attention_fwd_tc(ctx, st, q, k, v, s, H, chunk, scale, out, kv_div, kg);
     return;
   }
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, false><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, nullptr, 0, 0, 0, nullptr, nullptr,
-                                                         s.d_start, s.d_len, chunk, scale, kv_div, out.f32(), out.ld);
+                                                         s.d_start, s.d_len, chunk, scale, kv_div, out.f32(), out.ld, ks, kl, qo);
   else
     attn_simt_kernel<bf16, false><<<grid, 128, 0, st>>>(q.b16(), q.ld, k.b16(), k.ld, v.b16(), v.ld, nullptr, 0, 0, 0, nullptr, nullptr,
-                                                        s.d_start, s.d_len, chunk, scale, kv_div, out.b16(), out.ld);
+                                                        s.d_start, s.d_len, chunk, scale, kv_div, out.b16(), out.ld, ks, kl, qo);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }
@@ -193,10 +199,10 @@ void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat
   dim3 grid(ceil_div(s.max_len, BQ), H, s.B);
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, true><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, pos.f32(), pos.ld, pos.rows, pos_center, bias_u,
-                                                        bias_v, s.d_start, s.d_len, chunk, scale, 1, out.f32(), out.ld);
+                                                        bias_v, s.d_start, s.d_len, chunk, scale, 1, out.f32(), out.ld, nullptr, nullptr, nullptr);
   else
     attn_simt_kernel<bf16, true><<<grid, 128, 0, st>>>(q.b16(), q.ld, k.b16(), k.ld, v.b16(), v.ld, pos.b16(), pos.ld, pos.rows, pos_center, bias_u,
-                                                       bias_v, s.d_start, s.d_len, chunk, scale, 1, out.b16(), out.ld);
+                                                       bias_v, s.d_start, s.d_len, chunk, scale, 1, out.b16(), out.ld, nullptr, nullptr, nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

@@ -112,7 +112,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const __grid_constant__ CUtensorMap tmv,
                const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale_log2e, int kv_div,
-               bf16* __restrict__ out, int ldo) {
+               bf16* __restrict__ out, int ldo, const int* __restrict__ kstart, const int* __restrict__ klen, const int* __restrict__ qoff) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_o, bar_p1done;
   __shared__ __align__(8) uint64_t bar_full[AT_KVST], bar_empty[AT_KVST];   // K/V stages
@@ -123,15 +123,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   __shared__ float xch[2][AT_BQ];   // row max / row sum exchange between the two threads of a row
 
   const int b = blockIdx.z, h = blockIdx.y;
-  const int L = len[b], s0 = start[b];
+  const int L = len[b], s0 = start[b];            // query rows
+  const int Lk = klen ? klen[b] : L, ks0 = kstart ? kstart[b] : s0, q0 = qoff ? qoff[b] : 0;   // key rows (cache geometry); position of query 0
   const int i0 = blockIdx.x * AT_BQ;
   if (i0 >= L) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sKV = base + Q_BYTES, sP = sKV + AT_KVST * KV_STAGE;
   // keys visible to this query tile: all of the sequence, or up to the end of the last query's chunk
-  const int i_last = min(i0 + AT_BQ, L) - 1;
-  const int kmax = chunk > 0 ? min(L, (i_last / chunk + 1) * chunk) : L;
+  const int i_last = q0 + min(i0 + AT_BQ, L) - 1;
+  const int kmax = chunk > 0 ? min(Lk, (i_last / chunk + 1) * chunk) : Lk;
   const int G = (kmax + AT_BK - 1) / AT_BK;      // half tiles per pass
 
   // instruction descriptors: D=f32, A=B=bf16, M=128;  S: N=64, both K-major;  O: N=64, B (=V) MN-major
@@ -181,8 +182,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         mbar_wait(smem_u32(&bar_empty[st]), (round & 1u) ^ 1u);
         const uint32_t fb = smem_u32(&bar_full[st]);
         mbar_expect_tx(fb, pass2 ? KV_STAGE : K_BYTES);
-        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, s0 + g * AT_BK);
-        if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, s0 + g * AT_BK);
+        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, ks0 + g * AT_BK);
+        if (pass2) tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, ks0 + g * AT_BK);
       }
     }
   } else if (warp == 9) {
@@ -235,7 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;
     const int i = i0 + row;
-    const int klim = i < L ? (chunk > 0 ? min(L, (i / chunk + 1) * chunk) : L) : 0;
+    const int klim = i < L ? (chunk > 0 ? min(Lk, ((q0 + i) / chunk + 1) * chunk) : Lk) : 0;
     const uint32_t trow = ((uint32_t)(q4 * 32) << 16);
     const int cb2 = half * 32;
     float m = -INFINITY;
@@ -362,7 +363,7 @@ void make_map(cvk_ctx* ctx, CUtensorMap* m, const Mat& x, int box_rows) {
 }  // namespace
 
 void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                      float scale, const Mat& out, int kv_div) {
+                      float scale, const Mat& out, int kv_div, const KvGeom* kg) {
   CVK_REQUIRE(q.dtype == DT_BF16 && out.dtype == DT_BF16, "attention_fwd_tc: bf16 only");
   CVK_REQUIRE(q.ld % 8 == 0 && k.ld % 8 == 0 && v.ld % 8 == 0 && out.ld % 8 == 0, "attention_fwd_tc: 16-byte row pitch required");
   CVK_REQUIRE((((uintptr_t)q.p | (uintptr_t)k.p | (uintptr_t)v.p | (uintptr_t)out.p) & 15) == 0, "attention_fwd_tc: 16-byte alignment required");
@@ -376,7 +377,8 @@ void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k,
     attr = true;
   }
   dim3 grid(ceil_div(s.max_len, AT_BQ), H, s.B);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
+                                                    kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

@@ -283,8 +283,22 @@ void convert_mat(cvk_ctx* ctx, cudaStream_t st, const Mat& in, const Mat& out);
 // attention (attention.cu)
 //  q,k,v: packed [R, H*64] views (same Seqs); mask: key j visible from query i iff j < klimit(i), with
 //  klimit(i) = len (chunk<=0) or min(len, (i/chunk+1)*chunk) (block-causal, utils/mask.py:155-157)
+// Keys / values living in a cache with their own row geometry (incremental streaming flow): sequence b's keys are rows
+// [kstart[b], kstart[b] + klen[b]) of the k / v matrices and its queries (rows of `s`) sit at absolute positions qoff[b] + i.
+struct KvGeom {
+  const int* d_kstart = nullptr;
+  const int* d_klen = nullptr;
+  const int* d_qoff = nullptr;
+};
+// incremental streaming flow (flow.cu)
+struct cvk_flow_stream;
+cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps);
+void flow_stream_destroy(cvk_flow_stream* fs);
+size_t flow_stream_bytes(const cvk_flow_stream* fs);
+void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding, cudaStream_t st);
+int flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, int n_tokens, float* mel_out, int mel_cap_frames, cudaStream_t st);
 void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Seqs& s, int H, int chunk,
-                   float scale, const Mat& out, int kv_div = 1);
+                   float scale, const Mat& out, int kv_div = 1, const KvGeom* kg = nullptr);
 void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Mat& pos /*[2*Tmax-1, H*64]*/,
                           int pos_center, const float* bias_u, const float* bias_v, const Seqs& s, int H, int chunk, float scale,
                           const Mat& out);

@@ -58,6 +58,23 @@ struct FlowModel {
   int noise_T = 0;
 };
 
+// One streaming synthesis session of the flow stage (cvk_flow_stream_*): the caches that let a chunk call compute ONLY its
+// new frames.  Per Euler step: K/V rows of every estimator transformer block for both CFG sequences, and the two-row tails of
+// every causal convolution's input.
+struct cvk_flow_stream {
+  int cap = 0, n_steps = 0, adt = DT_F32, n_tb = 0, n_conv = 0;
+  void* kv = nullptr;
+  void* conv = nullptr;
+  size_t kv_step_bytes = 0, conv_step_bytes = 0;
+  int frames_done = 0;          // mel frames (prompt included) already produced
+  int prompt_frames = 0;
+  float* prompt_feat = nullptr; // [prompt_frames][80]
+  float* spk = nullptr;         // [80] projected speaker embedding
+  int* d_geo = nullptr;         // kstart[2] | klen[2] | qoff[2]
+  KvGeom kg;
+  bool begun = false;
+};
+
 namespace {
 
 float* copy_param(cvk_ctx* ctx, const std::string& name) {
@@ -545,7 +562,60 @@ struct EstBuffers {
   Mat temb_all; // fp32 [B2, 14*256]
 };
 
-void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstBuffers& b, int chunk, const Mat* out2) {
+// ---- incremental (cached) estimator call: state of ONE Euler step of one streaming session ------------------------------
+// Block-causal attention (key j visible from query i iff j < (i/50+1)*50, utils/mask.py:127-158) and causal convolutions
+// (flow/decoder.py:25-62: left padding k-1) make every frame of a COMPLETE 50-frame chunk independent of later frames, so a
+// chunk boundary is a valid cut: per Euler step, per transformer block the K/V rows of all earlier frames, and per causal
+// convolution the last two input rows, are all a later call needs.  The reference recomputes the prefix instead
+// (cli/model.py:346-363).
+struct EstInc {
+  void* kv = nullptr;        // [n_tblocks][2 * cap + 64][1024] act dtype: K | V rows of CFG sequence 0 then 1
+  void* conv = nullptr;      // [n_convs][2 seqs][2 rows][512] act dtype
+  int cap = 0;               // cache rows per sequence
+  int t_prev = 0;            // frames already cached
+  int tb_idx = 0, conv_idx = 0;
+  KvGeom kg;
+};
+
+template <typename T>
+__global__ void conv_state_kernel(T* __restrict__ x, int ld, int C, const int* __restrict__ start, const int* __restrict__ len, T* __restrict__ state) {
+  // gap rows start-2, start-1 <- saved tail of the previous chunk; saved tail <- last two rows of this chunk
+  const int b = blockIdx.x, r = blockIdx.y;
+  T* srow = state + ((size_t)b * 2 + r) * 512;
+  T* gap = x + (size_t)(start[b] - 2 + r) * ld;
+  const T* tail = x + (size_t)(start[b] + len[b] - 2 + r) * ld;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    gap[c] = srow[c];
+    srow[c] = tail[c];
+  }
+}
+
+template <typename T>
+__global__ void kv_append_kernel(const T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len, T* __restrict__ cache,
+                                 int cap, int t_prev) {
+  const int b = blockIdx.y;
+  const int L = len[b];
+  for (int i = blockIdx.x; i < L; i += gridDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(start[b] + i) * ld + 512);
+    uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)b * cap + t_prev + i) * 1024);
+    for (int c = threadIdx.x; c < 1024 * (int)sizeof(T) / 16; c += blockDim.x) dst[c] = src[c];
+  }
+}
+
+// the two rows a causal k=3 convolution reads in front of the chunk (call right before the convolution that consumes `in`)
+void conv_state(cvk_ctx* ctx, cudaStream_t st, EstInc* inc, const Mat& in, const Seqs& s) {
+  if (!inc) return;
+  CVK_REQUIRE(in.cols <= 512 && s.B == 2, "conv_state: unexpected operand");
+  const size_t es = in.esize();
+  char* state = (char*)inc->conv + (size_t)inc->conv_idx * 2 * 2 * 512 * es;
+  ++inc->conv_idx;
+  if (in.dtype == DT_F32) conv_state_kernel<float><<<dim3(s.B, 2), 128, 0, st>>>(in.f32(), in.ld, in.cols, s.d_start, s.d_len, (float*)state);
+  else conv_state_kernel<bf16><<<dim3(s.B, 2), 128, 0, st>>>(in.b16(), in.ld, in.cols, s.d_start, s.d_len, (bf16*)state);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstBuffers& b, int chunk, const Mat* out2, EstInc* inc = nullptr) {
   layernorm(ctx, st, b.x, t.ln1_g, t.ln1_b, 1e-5f, ACT_NONE, 1.f, s.d_row2seq, b.xn);
   {
     Epilogue e;
@@ -553,6 +623,20 @@ void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstB
     e.out = b.qkv;
     conv_gemm(ctx, st, b.xn, t.qkv, e);
   }
+  if (inc) {
+    const size_t es = b.qkv.esize();
+    const int crow = 2 * inc->cap + 64;
+    Mat cache((char*)inc->kv + (size_t)inc->tb_idx * crow * 1024 * es, b.qkv.dtype, crow, 1024, 1024);
+    ++inc->tb_idx;
+    int bx = s.max_len < 256 ? s.max_len : 256;
+    if (b.qkv.dtype == DT_F32)
+      kv_append_kernel<float><<<dim3(bx, s.B), 128, 0, st>>>(b.qkv.f32(), b.qkv.ld, s.d_start, s.d_len, cache.f32(), inc->cap, inc->t_prev);
+    else
+      kv_append_kernel<bf16><<<dim3(bx, s.B), 128, 0, st>>>(b.qkv.b16(), b.qkv.ld, s.d_start, s.d_len, cache.b16(), inc->cap, inc->t_prev);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    attention_fwd(ctx, st, b.qkv.slice(0, 512), cache.slice(0, 512), cache.slice(512, 512), s, H_EST, chunk, 0.125f, b.att, 1, &inc->kg);
+  } else
   attention_fwd(ctx, st, b.qkv.slice(0, 512), b.qkv.slice(512, 512), b.qkv.slice(1024, 512), s, H_EST, chunk, 0.125f, b.att);
   {
     Epilogue e;
@@ -585,8 +669,9 @@ void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstB
 // resnet (matcha decoder.py:55-61 with CausalBlock1D) + n transformer blocks.  `in` = act operand [R, Cin];
 // the stage's output residual stream ends in b.x (fp32) and, as an activation operand, in *out_act.
 void stage_forward(cvk_ctx* ctx, cudaStream_t st, const StageW& w, int stage_idx, const Seqs& s, const Mat& in, EstBuffers& b, int chunk,
-                   const Mat& out_act) {
+                   const Mat& out_act, EstInc* inc = nullptr) {
   const float* tvec = b.temb_all.f32() + (size_t)stage_idx * C_EST;
+  conv_state(ctx, st, inc, in, s);
   {
     Epilogue e;
     e.row2seq = s.d_row2seq;
@@ -594,6 +679,7 @@ void stage_forward(cvk_ctx* ctx, cudaStream_t st, const StageW& w, int stage_idx
     conv_gemm(ctx, st, in, w.rn.c1, e);
   }
   layernorm(ctx, st, b.c, w.rn.ln1_g, w.rn.ln1_b, 1e-5f, ACT_MISH, 1.f, s.d_row2seq, b.h1, tvec, b.temb_all.ld);
+  conv_state(ctx, st, inc, b.h1, s);
   {
     Epilogue e;
     e.row2seq = s.d_row2seq;
@@ -608,11 +694,12 @@ void stage_forward(cvk_ctx* ctx, cudaStream_t st, const StageW& w, int stage_idx
     e.out = b.x;
     conv_gemm(ctx, st, in, w.rn.res, e);
   }
-  for (size_t j = 0; j < w.tb.size(); ++j) tblock(ctx, st, w.tb[j], s, b, chunk, j + 1 == w.tb.size() ? &out_act : nullptr);
+  for (size_t j = 0; j < w.tb.size(); ++j) tblock(ctx, st, w.tb[j], s, b, chunk, j + 1 == w.tb.size() ? &out_act : nullptr, inc);
 }
 
 // in0: act [R,320] packed input; t: [B2] device; out: fp32 [R,80] (ld 80)
-void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out) {
+void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out,
+                       EstInc* inc = nullptr) {
   FlowModel* m = ctx->flow;
   const int adt = ctx->act_dtype;
   const int chunk = streaming ? 2 * CHUNK_TOK : 0;
@@ -655,7 +742,8 @@ void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& 
     conv_gemm_simt(ctx, st, te3, m->tmlp_all, e);
   }
   // down stage: output -> skip half of `cat`
-  stage_forward(ctx, st, m->stages[0], 0, s, in0, b, chunk, b.cat.slice(C_EST, C_EST));
+  stage_forward(ctx, st, m->stages[0], 0, s, in0, b, chunk, b.cat.slice(C_EST, C_EST), inc);
+  conv_state(ctx, st, inc, b.cat.slice(C_EST, C_EST), s);
   {
     Epilogue e;      // down_blocks.0.2 causal conv on the skip tensor
     e.row2seq = s.d_row2seq;
@@ -664,16 +752,18 @@ void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& 
   }
   for (int i = 0; i < m->num_mid; ++i) {
     bool last = i + 1 == m->num_mid;
-    stage_forward(ctx, st, m->stages[1 + i], 1 + i, s, b.xa, b, chunk, last ? b.cat.slice(0, C_EST) : b.xa);
+    stage_forward(ctx, st, m->stages[1 + i], 1 + i, s, b.xa, b, chunk, last ? b.cat.slice(0, C_EST) : b.xa, inc);
   }
   if (m->num_mid == 0) convert_mat(ctx, st, b.xa, b.cat.slice(0, C_EST));
-  stage_forward(ctx, st, m->stages[nst - 1], nst - 1, s, b.cat, b, chunk, b.xa);
+  stage_forward(ctx, st, m->stages[nst - 1], nst - 1, s, b.cat, b, chunk, b.xa, inc);
+  conv_state(ctx, st, inc, b.xa, s);
   {
     Epilogue e;      // up_blocks.0.2
     e.row2seq = s.d_row2seq;
     e.out = b.h1;
     conv_gemm(ctx, st, b.xa, m->up_conv2, e);
   }
+  conv_state(ctx, st, inc, b.h1, s);
   {
     Epilogue e;      // final CausalBlock1D
     e.row2seq = s.d_row2seq;
@@ -695,7 +785,7 @@ void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const M
 
 // `dit`: 0 = CosyVoice2 causal U-Net estimator, 1 = CosyVoice3 DiT (32 gap rows: its causal position convolution looks 30 rows back)
 void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* lens, const Mat& mu, const Mat& cond, const float* spks,
-                      const Mat& x, int n_timesteps, float cfg_rate, int streaming, int dit = 0) {
+                      const Mat& x, int n_timesteps, float cfg_rate, int streaming, int dit = 0, cvk_flow_stream* fs = nullptr) {
   const int adt = ctx->act_dtype;
   const int B = s1.B;
   std::vector<int> lens2(2 * B);
@@ -732,7 +822,16 @@ void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* 
     ctx->launches++;
     CVK_LAUNCH_CHECK();
     if (dit) dit_estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
-    else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
+    else if (fs) {
+      EstInc inc;
+      inc.kv = (char*)fs->kv + (size_t)step * fs->kv_step_bytes;
+      inc.conv = (char*)fs->conv + (size_t)step * fs->conv_step_bytes;
+      inc.cap = fs->cap;
+      inc.t_prev = fs->frames_done;
+      inc.kg = fs->kg;
+      estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v, &inc);
+      CVK_REQUIRE(inc.tb_idx == fs->n_tb && inc.conv_idx == fs->n_conv, "flow stream: cache slots do not match the estimator");
+    } else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
     cfg_euler_kernel<<<dim3(bx, B), 96, 0, st>>>(x.f32(), v.f32(), v.ld, s1.d_start, s2.d_start, s1.d_len, B, dts[step], cfg_rate);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
@@ -1124,6 +1223,123 @@ void flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, 
   }
   cfm_solve_packed(ctx, st, s2, mel_lens.data(), mu, cond, spk.f32(), x, n_timesteps, 0.7f, streaming);
   unpack_rows_skip(ctx, st, x, s2, prompt_feat_lens, mel, N_MEL);
+}
+
+// ================================================================================================ incremental streaming flow
+cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps) {
+  FlowModel* m = ctx->flow;
+  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+  CVK_REQUIRE(max_frames >= 2 * CHUNK_TOK && n_timesteps >= 1, "flow stream: bad capacity / step count");
+  cvk_flow_stream* fs = new cvk_flow_stream();
+  fs->cap = round_up(max_frames, 64);
+  fs->n_steps = n_timesteps;
+  fs->adt = ctx->act_dtype;
+  const size_t es = fs->adt == DT_F32 ? 4 : 2;
+  const int nst = (int)m->stages.size();
+  fs->n_tb = nst * m->n_blocks;
+  fs->n_conv = 2 * nst + 3;
+  fs->kv_step_bytes = (size_t)fs->n_tb * (2 * fs->cap + 64) * 1024 * es;
+  fs->conv_step_bytes = (size_t)fs->n_conv * 2 * 2 * 512 * es;
+  CVK_CHECK_CUDA(cudaMalloc(&fs->kv, fs->kv_step_bytes * n_timesteps));
+  CVK_CHECK_CUDA(cudaMalloc(&fs->conv, fs->conv_step_bytes * n_timesteps));
+  CVK_CHECK_CUDA(cudaMalloc(&fs->prompt_feat, sizeof(float) * (size_t)fs->cap * N_MEL));
+  CVK_CHECK_CUDA(cudaMalloc(&fs->spk, sizeof(float) * N_MEL));
+  CVK_CHECK_CUDA(cudaMalloc(&fs->d_geo, sizeof(int) * 6));
+  CVK_CHECK_CUDA(cudaMemset(fs->kv, 0, fs->kv_step_bytes * n_timesteps));   // masked key rows of a partial tile must be finite
+  fs->kg.d_kstart = fs->d_geo;
+  fs->kg.d_klen = fs->d_geo + 2;
+  fs->kg.d_qoff = fs->d_geo + 4;
+  return fs;
+}
+
+void flow_stream_destroy(cvk_flow_stream* fs) {
+  if (!fs) return;
+  cudaFree(fs->kv); cudaFree(fs->conv); cudaFree(fs->prompt_feat); cudaFree(fs->spk); cudaFree(fs->d_geo);
+  delete fs;
+}
+
+size_t flow_stream_bytes(const cvk_flow_stream* fs) { return (fs->kv_step_bytes + fs->conv_step_bytes) * (size_t)fs->n_steps; }
+
+// new utterance: prompt mel [prompt_frames][80] and speaker embedding [192] (device pointers); clears the caches
+void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding, cudaStream_t st) {
+  FlowModel* m = ctx->flow;
+  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+  CVK_REQUIRE(fs->adt == ctx->act_dtype, "flow stream was created under another precision");
+  CVK_REQUIRE(prompt_frames >= 0 && prompt_frames < fs->cap, "flow stream: prompt longer than the cache");
+  ctx->arena.reset();
+  CVK_CHECK_CUDA(cudaMemsetAsync(fs->conv, 0, fs->conv_step_bytes * fs->n_steps, st));    // causal left padding of the first chunk
+  if (prompt_frames > 0)
+    CVK_CHECK_CUDA(cudaMemcpyAsync(fs->prompt_feat, prompt_feat, sizeof(float) * (size_t)prompt_frames * N_MEL, cudaMemcpyDeviceToDevice, st));
+  Mat en = arena_mat(ctx, DT_F32, 1, 192);
+  l2norm_kernel<<<1, 64, 0, st>>>(embedding, en.f32(), 192);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  {
+    Epilogue e;
+    e.out = Mat(fs->spk, DT_F32, 1, N_MEL, N_MEL);
+    conv_gemm_simt(ctx, st, en, m->spk_affine, e);
+  }
+  fs->prompt_frames = prompt_frames;
+  fs->frames_done = 0;
+  fs->begun = true;
+}
+
+// tokens: device [n_tokens] = prompt tokens + every speech token so far INCLUDING the 3 look-ahead tokens (the same argument
+// the reference passes to flow.inference(streaming=True, finalize=False), cli/model.py:346-363).  Produces the mel frames that
+// call would return beyond those already delivered: rows [max(frames_done, prompt_frames), 2 * (n_tokens - 3)), written to
+// mel_out [*, 80]; returns their count.  Both chunk ends must be multiples of the 50-frame static chunk (the reference's hop
+// schedule guarantees it: cli/model.py:346-352 pads the first hop to the 25-token grid).
+int flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, int n_tokens, float* mel_out, int mel_cap_frames, cudaStream_t st) {
+  FlowModel* m = ctx->flow;
+  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+  CVK_REQUIRE(fs->begun, "cvk_flow_stream_begin has not been called");
+  const int CH = 2 * CHUNK_TOK;
+  const int T_total = 2 * (n_tokens - 3);
+  const int T_prev = fs->frames_done;
+  CVK_REQUIRE(T_total > T_prev, "flow stream: no new frames in this call");
+  CVK_REQUIRE(T_total % CH == 0 && T_prev % CH == 0, "flow stream: chunk ends must be multiples of the 50-frame static chunk");
+  CVK_REQUIRE(T_total <= fs->cap, "flow stream: cache capacity exceeded");
+  CVK_REQUIRE(fs->prompt_frames < T_total, "flow stream: prompt_feat longer than the generated mel");
+  const int n_new = T_total - T_prev;
+  const int skip = fs->prompt_frames > T_prev ? fs->prompt_frames - T_prev : 0;   // prompt rows are computed but not returned
+  CVK_REQUIRE(n_new - skip <= mel_cap_frames, "flow stream: output buffer too small");
+  ctx->arena.reset();
+  // encoder over the whole prefix (1.5 % of the flow FLOPs; its chunk mask + look-ahead make the prefix rows final as well)
+  Seqs s2;
+  int lens_tok[1] = {n_tokens};
+  Mat h = encoder_forward(ctx, st, tokens, lens_tok, 1, 1, 3, &s2);
+  CVK_REQUIRE(s2.len[0] == T_total, "flow stream: encoder length mismatch");
+  Mat ha = h;
+  if (ctx->act_dtype != DT_F32) {
+    ha = arena_mat(ctx, ctx->act_dtype, s2.R, D_ENC);
+    convert_mat(ctx, st, h, ha);
+  }
+  Mat mu_full = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
+  {
+    Epilogue e;
+    e.row2seq = s2.d_row2seq;
+    e.out = mu_full;
+    conv_gemm(ctx, st, ha, m->enc_proj, e);
+  }
+  // geometry of the new rows
+  int lens_new[1] = {n_new};
+  Seqs s1 = make_seqs(ctx, lens_new, 1, 8, 1, 0, st);
+  Mat mu = arena_mat(ctx, DT_F32, s1.R, N_MEL, N_MEL), cond = arena_mat(ctx, DT_F32, s1.R, N_MEL, N_MEL), x = arena_mat(ctx, DT_F32, s1.R, N_MEL, N_MEL);
+  zero_mat(ctx, st, mu); zero_mat(ctx, st, cond); zero_mat(ctx, st, x);
+  const size_t rowb = sizeof(float) * N_MEL;
+  CVK_CHECK_CUDA(cudaMemcpyAsync(mu.f32() + (size_t)s1.start[0] * N_MEL, mu_full.f32() + (size_t)(s2.start[0] + T_prev) * N_MEL, rowb * n_new,
+                                 cudaMemcpyDeviceToDevice, st));
+  if (skip > 0)
+    CVK_CHECK_CUDA(cudaMemcpyAsync(cond.f32() + (size_t)s1.start[0] * N_MEL, fs->prompt_feat + (size_t)T_prev * N_MEL, rowb * skip, cudaMemcpyDeviceToDevice, st));
+  CVK_REQUIRE(m->noise && m->noise_T >= T_total, "cvk_cfm_set_noise has not been called (or the noise tensor is too short)");
+  CVK_CHECK_CUDA(cudaMemcpyAsync(x.f32() + (size_t)s1.start[0] * N_MEL, m->noise + (size_t)T_prev * N_MEL, rowb * n_new, cudaMemcpyDeviceToDevice, st));
+  int geo[6] = {0, fs->cap, T_total, T_total, T_prev, T_prev};
+  int* d_tmp = upload(ctx, std::vector<int>(geo, geo + 6), st);
+  CVK_CHECK_CUDA(cudaMemcpyAsync(fs->d_geo, d_tmp, sizeof(int) * 6, cudaMemcpyDeviceToDevice, st));
+  cfm_solve_packed(ctx, st, s1, lens_new, mu, cond, fs->spk, x, fs->n_steps, 0.7f, 1, 0, fs);
+  CVK_CHECK_CUDA(cudaMemcpyAsync(mel_out, x.f32() + (size_t)(s1.start[0] + skip) * N_MEL, rowb * (n_new - skip), cudaMemcpyDeviceToDevice, st));
+  fs->frames_done = T_total;
+  return n_new - skip;
 }
 
 // ================================================================================================ CosyVoice3 entry points

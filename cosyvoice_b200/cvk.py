@@ -51,6 +51,11 @@ SIGNATURES = {
     "cvk_workspace_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "cvk_cfm_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, _vp, _vp]),
     "cvk_flow_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "cvk_flow_stream_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "cvk_flow_stream_destroy": (None, [_vp, _vp]),
+    "cvk_flow_stream_bytes": (ctypes.c_longlong, [_vp]),
+    "cvk_flow_stream_begin": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "cvk_flow_stream_chunk": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _c_int_p, _vp]),
     "cvk_cfm_set_noise": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
     "cvk_hift3_set_noise": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_int]),
     "cvk_hift3_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
@@ -341,6 +346,33 @@ class Context:
                                                 _ptr(embedding), len(token_lens), n_timesteps, int(streaming), int(finalize),
                                                 _ptr(mel), _stream()))
         return mel, out_lens
+
+    # ------------------------------------------------------------------ incremental streaming flow (cvk.h: cvk_flow_stream_*)
+    def flow_stream(self, max_frames, n_timesteps=10):
+        s = ctypes.c_void_p()
+        self._check(self.lib.cvk_flow_stream_create(self.h, int(max_frames), int(n_timesteps), ctypes.byref(s)))
+        return s
+
+    def flow_stream_destroy(self, fs):
+        self.lib.cvk_flow_stream_destroy(self.h, fs)
+
+    def flow_stream_bytes(self, fs):
+        return int(self.lib.cvk_flow_stream_bytes(fs))
+
+    def flow_stream_begin(self, fs, prompt_feat, embedding):
+        """prompt_feat [Tp,80] (may be empty), embedding [192] or [1,192]"""
+        pf = _f32(prompt_feat, self.device) if prompt_feat is not None and prompt_feat.numel() else None
+        emb = _f32(embedding, self.device)
+        self._check(self.lib.cvk_flow_stream_begin(self.h, fs, _ptr(pf), 0 if pf is None else int(pf.shape[0]), _ptr(emb), _stream()))
+
+    def flow_stream_chunk(self, fs, tokens):
+        """tokens: 1-D int32 = prompt tokens + speech tokens so far + 3 look-ahead tokens.  Returns the new mel frames [n,80]."""
+        tokens = tokens.to(device=self.device, dtype=torch.int32).contiguous().reshape(-1)
+        cap = 2 * int(tokens.numel())
+        mel = torch.empty(cap, 80, device=self.device)
+        n = ctypes.c_int(0)
+        self._check(self.lib.cvk_flow_stream_chunk(self.h, fs, _ptr(tokens), int(tokens.numel()), _ptr(mel), cap, ctypes.byref(n), _stream()))
+        return mel[:n.value]
 
     # ------------------------------------------------------------------ LM
     def lm_session(self, max_batch, max_context):

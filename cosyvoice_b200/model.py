@@ -60,6 +60,11 @@ class B200CosyVoice2Model:
     # benchmark aid only (None = the reference's behaviour: decode "until met eos", llm.py:642-661, without any cap): random-init
     # weights cannot be made to emit eos at a chosen time, so bench.py ends the text-streaming decode after this many ids
     bistream_max_tokens = None
+    # streaming synthesis: intermediate chunks through the cached flow session (cvk_flow_stream_*: each chunk computes only its new
+    # frames) instead of the reference's prefix recompute (cli/model.py:346-363); same frames either way.  The U-Net estimator of
+    # CosyVoice2 only (B200CosyVoice3Model switches it off: the DiT has no session yet).
+    incremental_flow = True
+    stream_cache_frames = 2048           # mel frames (prompt included) one streaming request can cache (41 s); ~2.3 MB per frame in bf16
 
     def __init__(self, llm=None, flow=None, hift=None, fp16=False, precision="bf16", device=0, workspace_gb=24.0):
         # attribute names follow cli/model.py:245-275
@@ -86,6 +91,8 @@ class B200CosyVoice2Model:
         self.max_idle_sessions = 4
         self._pool_lock = threading.Lock()
         self._lm_streams = []
+        self.flow_stream_dict = {}           # uuid -> cvk_flow_stream handle, or False once a request has left the chunk grid
+        self._idle_flow_streams = []
         self.lm_chains = 1                   # independent decode chains run concurrently (see lm_generate)
         self._window = torch.from_numpy(self.speech_window).float().to(self.device)
         self.n_timesteps = 10
@@ -443,11 +450,57 @@ class B200CosyVoice2Model:
         self.stream.synchronize()
         return h
 
+    def _flow_stream_chunk(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid):
+        """The frames of this streaming chunk from the request's cached flow session, or None when the request cannot use one
+        (chunk ends off the 50-frame grid, prompt mel not 2 frames per prompt token, longer than the cache): the caller then
+        recomputes the prefix like the reference."""
+        if not self.incremental_flow or uuid not in self.tts_speech_token_dict:
+            return None
+        fs = self.flow_stream_dict.get(uuid)
+        if fs is False:
+            return None
+        P = int(prompt_token.shape[1])
+        total = TOKEN_MEL_RATIO * (P + int(token.shape[1]) - PRE_LOOKAHEAD)
+        done = TOKEN_MEL_RATIO * (P + token_offset) if token_offset else 0
+        chunk = 2 * 25                                   # cosyvoice2.yaml:16 static_chunk_size x token_mel_ratio
+        ok = (total % chunk == 0 and done % chunk == 0 and int(prompt_feat.shape[1]) == TOKEN_MEL_RATIO * P
+              and total <= self.stream_cache_frames and (fs is not None or token_offset == 0))
+        if not ok:
+            if fs:
+                self._release_flow_stream(uuid)
+            self.flow_stream_dict[uuid] = False
+            return None
+        d = self.device
+        with torch.cuda.stream(self.stream), self.ctx.lock:
+            if fs is None:
+                with self._pool_lock:
+                    fs = self._idle_flow_streams.pop() if self._idle_flow_streams else None
+                if fs is None:
+                    fs = self.ctx.flow_stream(self.stream_cache_frames, self.n_timesteps)
+                self.flow_stream_dict[uuid] = fs
+                self.ctx.flow_stream_begin(fs, prompt_feat[0].to(d, non_blocking=True), embedding.reshape(-1).to(d, non_blocking=True))
+            toks = torch.cat([prompt_token.reshape(-1).to(d, non_blocking=True), token.reshape(-1).to(d, non_blocking=True)]).to(torch.int32)
+            return self.ctx.flow_stream_chunk(fs, toks)
+
+    def _release_flow_stream(self, uuid):
+        fs = self.flow_stream_dict.pop(uuid, None)
+        if fs:
+            with self._pool_lock:
+                if len(self._idle_flow_streams) < 2:
+                    self._idle_flow_streams.append(fs)
+                    fs = None
+            if fs:
+                self.stream.synchronize()
+                self.ctx.flow_stream_destroy(fs)
+
     def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0):
         """cli/model.py:292-326"""
-        mel, lens = self.flow_batch([token.to(torch.int32)], [prompt_token], [prompt_feat], [embedding], streaming=stream, finalize=finalize)
+        new_mel = self._flow_stream_chunk(token.to(torch.int32), prompt_token, prompt_feat, embedding, token_offset, uuid) \
+            if (stream and not finalize) else None
+        if new_mel is None:
+            mel, lens = self.flow_batch([token.to(torch.int32)], [prompt_token], [prompt_feat], [embedding], streaming=stream, finalize=finalize)
         with torch.cuda.stream(self.stream):
-            tts_mel = mel[token_offset * TOKEN_MEL_RATIO:]
+            tts_mel = new_mel if new_mel is not None else mel[token_offset * TOKEN_MEL_RATIO:]
             cache = self.hift_cache_dict[uuid]
             cache_source, cache_lens = None, None
             if cache is not None:
@@ -556,4 +609,5 @@ class B200CosyVoice2Model:
             self.tts_speech_token_dict.pop(this_uuid)
             self.llm_end_dict.pop(this_uuid)
             self.hift_cache_dict.pop(this_uuid)
+        self._release_flow_stream(this_uuid)
         self.stream.synchronize()

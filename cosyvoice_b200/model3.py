@@ -18,6 +18,7 @@ class B200CosyVoice3Model(B200CosyVoice2Model):
     bistream_fill_token = 6564
     bistream_eos_token = 6562
     bistream_eop_token = 151646
+    incremental_flow = False          # cvk_flow_stream_* caches the CosyVoice2 U-Net estimator only
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)

@@ -135,6 +135,29 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
                        const int* prompt_feat_lens_host, const float* embedding, int B, int n_timesteps, int streaming,
                        int finalize, float* mel, void* stream);
 
+/* ---- incremental streaming flow -------------------------------------------------------------------------
+ * The reference's streaming loop calls flow.inference(streaming=True, finalize=False) on the GROWING token prefix for every
+ * chunk (cli/model.py:346-363) and keeps only the frames past token_offset.  Block-causal attention (utils/mask.py:127-158,
+ * static chunk 50 frames) and causal convolutions (flow/decoder.py:25-62) make every complete chunk independent of later
+ * frames, so a session object caches, per Euler step, the K/V rows of every estimator transformer block and the two-row
+ * input tails of every causal convolution; a chunk call then computes its NEW frames only and returns exactly the rows the
+ * reference call would (same noise rows of cvk_cfm_set_noise, same prompt conditioning).  Chunk ends must be multiples of
+ * 50 frames (the reference's hop schedule guarantees it); the final, non-streaming call (finalize=True runs with
+ * streaming=False in the reference, cli/model.py:372-378: full attention) stays cvk_flow_inference.
+ * create: caches for up to max_frames mel frames (prompt included) and n_timesteps Euler steps; cvk_flow_stream_bytes reports
+ * their size.  begin: new utterance - prompt_feat [prompt_frames,80], embedding [192] (device).  chunk: tokens = device
+ * [n_tokens] prompt tokens + all speech tokens so far + the 3 look-ahead tokens; writes the frames
+ * [max(done, prompt_frames), 2*(n_tokens-3)) to mel_out [mel_capacity_frames,80] and their count to *n_frames_out (host).
+ * Calls on one session are serialised by the caller, like every workspace call of the context. */
+typedef struct cvk_flow_stream cvk_flow_stream;
+int cvk_flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out);
+void cvk_flow_stream_destroy(cvk_ctx* ctx, cvk_flow_stream* fs);
+long long cvk_flow_stream_bytes(const cvk_flow_stream* fs);
+int cvk_flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding,
+                          void* stream);
+int cvk_flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, int n_tokens, float* mel_out,
+                          int mel_capacity_frames, int* n_frames_out, void* stream);
+
 /* ---- CosyVoice3 vocoder (stage "hift3") ------------------------------------------------------------------------------------
  * cosyvoice/hifigan/generator.py:572-726 CausalHiFTGenerator (+ f0_predictor.py:60-103 in float64, generator.py:716-717).
  * cvk_hift3_set_noise hands over the module's constructor-time random tensors, which are not state_dict entries

@@ -129,6 +129,51 @@ def test_persistent_gemm_flow_bit_identical():
     assert torch.equal(outs[0], outs[1]), maxdiff(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_incremental_stream_equals_prefix_recompute(precision, tag):
+    """cvk_flow_stream_* (cached K/V + causal-conv tails per Euler step) against the reference's schedule, which re-runs
+    flow.inference(streaming=True, finalize=False) on the growing prefix for every chunk (cli/model.py:346-363): same frames, chunk by
+    chunk.  Prompt of 30 tokens -> first hop padded to the 25-token grid (45), then hops of 25 and 50; the first chunk's prompt
+    rows are computed (they are attended to) but not returned.  Every row's arithmetic is the same sequence of operations in both
+    schedules (row-independent GEMMs, keys visited in the same order), so the bound is round-off, not a model tolerance."""
+    c, sd, cfg = model(precision, tag)
+    g = torch.Generator().manual_seed(77)
+    P, hops = 30, (45, 25, 50)
+    toks = torch.randint(0, 6561, (P + sum(hops) + 3,), generator=g, dtype=torch.int32)
+    pfeat = torch.rand(2 * P, 80, generator=g) * 13.5 - 11.5
+    emb = torch.randn(1, 192, generator=g)
+    fs = c.flow_stream(max_frames=512, n_timesteps=10)
+    try:
+        assert c.flow_stream_bytes(fs) > 0
+        c.flow_stream_begin(fs, pfeat, emb)
+        n, done = P, 0
+        for hop in hops:
+            n += hop
+            ref, lens = c.flow_inference(toks[:n + 3], [n + 3], pfeat, [2 * P], emb, streaming=True, finalize=False)
+            assert lens == [2 * n - 2 * P]
+            new = c.flow_stream_chunk(fs, toks[:n + 3])
+            want = ref[max(done - 2 * P, 0):]
+            assert new.shape == want.shape, (new.shape, want.shape)
+            assert torch.isfinite(new).all()
+            d = maxdiff(new, want)
+            assert d < (1e-5 if precision == "fp32" else 1e-3), (hop, d)
+            done = 2 * n
+        # a second utterance on the same session object: begin() resets the caches
+        c.flow_stream_begin(fs, pfeat, emb)
+        ref, _ = c.flow_inference(toks[:P + 45 + 3], [P + 45 + 3], pfeat, [2 * P], emb, streaming=True, finalize=False)
+        new = c.flow_stream_chunk(fs, toks[:P + 45 + 3])
+        assert maxdiff(new, ref) < (1e-5 if precision == "fp32" else 1e-3)
+        # a chunk end off the 50-frame grid is refused (the caches would not be exact), and so is a call without new frames
+        from cosyvoice_b200.cvk import CvkError
+        with pytest.raises(CvkError):
+            c.flow_stream_chunk(fs, toks[:P + 45 + 10 + 3])
+        with pytest.raises(CvkError):
+            c.flow_stream_chunk(fs, toks[:P + 45 + 3])
+    finally:
+        c.flow_stream_destroy(fs)
+
+
 @pytest.mark.parametrize("precision", ["fp32"])
 def test_engine_estimator_inplace_contract(precision, golden):
     """INTEGRATION.md §2 executed: cosyvoice_b200.engine.CvkEstimator at the reference's TensorRT swap point

@@ -15,6 +15,7 @@ from oracle import cases, lm, sampling
 def _pool(m):
     """session-pool attributes B200CosyVoice2Model.__init__ creates"""
     m._free_sessions, m._session_lru, m.max_idle_sessions, m._pool_lock = {}, [], 4, threading.Lock()
+    m.flow_stream_dict, m._idle_flow_streams = {}, []
     if not hasattr(m, "lock"):
         m.lock = threading.Lock()
     return m
@@ -264,7 +265,29 @@ class FakeCtx2(FakeCtx3):
     def __init__(self, lsd, fsd, hsd, fcfg):
         self.lsd, self.fsd, self.hsd, self.fcfg = lsd, fsd, hsd, fcfg
         self.lock = threading.Lock()
-        self.flow_calls, self.hift_calls = [], []
+        self.flow_calls, self.hift_calls, self.stream_calls = [], [], []
+
+    # cvk_flow_stream_*: a session returns, per chunk, the frames of flow.inference(streaming=True, finalize=False) on the prefix
+    # that it has not returned yet (tests/test_flow_gpu.py::test_incremental_stream_equals_prefix_recompute holds the library to it)
+    def flow_stream(self, max_frames, n_timesteps=10):
+        return {"done": 0, "cap": max_frames}
+
+    def flow_stream_begin(self, fs, prompt_feat, embedding):
+        fs.update(done=0, pf=prompt_feat, emb=embedding.reshape(1, -1))
+
+    def flow_stream_chunk(self, fs, toks):
+        from oracle import flow
+        P = self._P
+        self.stream_calls.append(int(toks.numel()))
+        mel = flow.inference(self.fsd, toks[None, P:], toks[None, :P], fs["pf"][None], fs["emb"], self.fcfg, 10, True, False)[0].t()
+        Tp = fs["pf"].shape[0]
+        out = mel[max(fs["done"] - Tp, 0):]
+        fs["done"] = Tp + mel.shape[0]
+        assert fs["done"] % 50 == 0 and fs["done"] <= fs["cap"]
+        return out.contiguous()
+
+    def flow_stream_destroy(self, fs):
+        pass
 
     def _run(self, sess, U, min_len, max_len):
         sd = self.lsd
@@ -331,16 +354,30 @@ def test_cosyvoice2_model_host_glue_matches_reference(golden, monkeypatch):
         m.mel_cache_len, m.source_cache_len = 8, 8 * 480
         m._window = torch.from_numpy(np.hamming(2 * 8 * 480)).float()
         m.min_token_text_ratio, m.max_token_text_ratio, m.n_timesteps = 2.0, 20.0, 10
-        ctx.flow_calls.clear()
-        ctx.hift_calls.clear()
-        chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
-                                                 llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
-                                                 stream=stream)]
-        assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
-        d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
-        assert d[:, :24000].max() < 5e-3 and d.max() < 2e-2, (d[:, :24000].max(), d.max())
+        for incremental in ((True, False) if stream else (True,)):
+            m.incremental_flow = incremental
+            m.token_hop_len = 25
+            k["k"] = 0
+            ctx.flow_calls.clear()
+            ctx.hift_calls.clear()
+            ctx.stream_calls.clear()
+            chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                     llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                     stream=stream)]
+            assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
+            d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
+            assert d[:, :24000].max() < 5e-3 and d.max() < 2e-2, (d[:, :24000].max(), d.max())
+            assert not m.flow_stream_dict                    # the session went back to the pool
+            if stream and incremental:
+                # the two streaming chunks (hop 25 padded to 41, then 50; 3 look-ahead tokens each) through the cached session, the
+                # final non-streaming call on all 140 tokens through flow_inference like the reference (cli/model.py:372-378)
+                assert ctx.stream_calls == [9 + 41 + 3, 9 + 41 + 50 + 3]
+                assert ctx.flow_calls == [(9 + 140, False, True)]
         if stream:
+            # last pass = the reference's schedule: prefix recompute for every chunk
             assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
+            assert ctx.stream_calls == []
+            assert len(m._idle_flow_streams) == 1
             # every vocoder call after the first re-uses 8 cached mel frames and 3840 cached source samples (cli/model.py:305-318)
             assert [c[1] for c in ctx.hift_calls] == [0, 3840, 3840]
 

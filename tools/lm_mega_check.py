@@ -11,7 +11,16 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--coop", type=int, default=1)
 ap.add_argument("--timeline", type=int, default=1)
+ap.add_argument("--a", default="lm_mega=1", help="options of variant A (comma-separated key=value)")
+ap.add_argument("--b", default="lm_mega=0", help="options of variant B (the reference of the comparison)")
 a = ap.parse_args()
+
+
+def parse_opts(txt):
+    return {k: int(v) for k, v in (kv.split("=") for kv in txt.split(",") if kv)}
+
+
+OPT_A, OPT_B = parse_opts(a.a), parse_opts(a.b)
 dev = torch.device("cuda", 0)
 sds = synth.cosyvoice2_state_dicts(dev, 1986, a.layers, (2, 1, 2, 2))
 m = B200CosyVoice2Model(precision="bf16", device=0, workspace_gb=8.0)
@@ -34,8 +43,9 @@ Ud = U.to(dev)
 big = torch.full((B,), 100000, dtype=torch.int32, device=dev)
 
 
-def run(mega, nsteps, timeline=False):
-    c.set_option("lm_mega", mega)
+def run(opts, nsteps, timeline=False):
+    for k, v in opts.items():
+        c.set_option(k, v)
     sess = c.lm_session(B, max(tl) + max(sl) + a.steps + 32)
     ids = torch.zeros(B, a.steps + 8, dtype=torch.int32, device=dev)
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -64,10 +74,10 @@ def run(mega, nsteps, timeline=False):
     return out
 
 
-l2a, la, ia, usa = run(1, a.steps)
-l2b, lb, ib, usb = run(0, a.steps)
+l2a, la, ia, usa = run(OPT_A, a.steps)
+l2b, lb, ib, usb = run(OPT_B, a.steps)
 fin = torch.isfinite(l2a) & torch.isfinite(l2b)
-print(f"B={B} layers={a.layers}: step time mega {usa:.1f} us, per-op chain {usb:.1f} us")
+print(f"B={B} layers={a.layers}: step time A {OPT_A} {usa:.1f} us, B {OPT_B} {usb:.1f} us")
 print(f"logits after 2 steps: max |mega - chain| = {(l2a - l2b)[fin].abs().max().item():.4g} (|logit| up to {l2b[fin].abs().max().item():.3g}), finite {fin.float().mean().item():.4f}")
 same = (ia == ib)
 first_div = [int((~same[b]).nonzero()[0]) if (~same[b]).any() else -1 for b in range(B)]
@@ -76,7 +86,8 @@ fin = torch.isfinite(la) & torch.isfinite(lb)
 print(f"logits after {a.steps + 2} steps: max |mega - chain| = {(la - lb)[fin].abs().max().item():.4g}")
 if a.timeline:
     # timeline: needs the option set BEFORE the graph is captured
-    c.set_option("lm_mega", 1)
+    for k, v in OPT_A.items():
+        c.set_option(k, v)
     c.set_option("chain_timeline", 1)
     sess = c.lm_session(B, max(tl) + max(sl) + 64)
     ids = torch.zeros(B, 64, dtype=torch.int32, device=dev)
@@ -96,6 +107,20 @@ if a.timeline:
         for k, n in enumerate(names):
             v = d[k::7]
             print(f"  {n:8s} mean {sum(v) / len(v):6.2f} us  (layer 0: {v[0]:.2f}, layer 1: {v[1] if len(v) > 1 else 0:.2f}, last: {v[-1]:.2f})")
+    if not OPT_A.get("lm_mega", 0):
+        # per-op chain: a block of 4 slots per kernel, 3 stamps (entry, past griddepcontrol.wait, end) per kernel in launch order
+        st3 = [t[i * 4:i * 4 + 3] for i in range(255) if t[i * 4]]
+        per_layer = (len(st3) - 3) // a.layers if a.layers else 0
+        print(f"chain: {len(st3)} stamped kernels, {per_layer} per layer")
+        if per_layer:
+            for k in range(per_layer):
+                rows = [st3[3 + l * per_layer + k] for l in range(1, a.layers)]
+                nxt = [st3[3 + l * per_layer + k + 1] if 3 + l * per_layer + k + 1 < len(st3) else None for l in range(1, a.layers)]
+                span = [(r[2] - r[1]) / 1e3 for r in rows]
+                period = [(n[1] - r[1]) / 1e3 for r, n in zip(rows, nxt) if n]
+                print(f"  kernel {k}: waited->end {sum(span) / len(span):5.2f} us, waited->next waited {sum(period) / max(len(period), 1):5.2f} us")
+            l0, l1 = st3[3 + per_layer][1], st3[3 + (a.layers - 1) * per_layer][1]
+            print(f"  layer period {(l1 - l0) / 1e3 / (a.layers - 2):.2f} us")
     ch = t[:16]
     print("chain stamps (head, head_finish, sampler) entry/waited/end us rel:", [round((x - ch[0]) / 1e3, 2) if x else 0 for x in ch[:12]])
     if mg[0] and ch[0]:
