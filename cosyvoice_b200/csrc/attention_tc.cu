@@ -339,6 +339,245 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   }
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
+// ---- single-pass variant ---------------------------------------------------------------------------------------------------
+// Same tiling, roles and hand-offs as attn_tc_kernel, but every score tile is computed and read ONCE.  The two softmax threads of
+// a query row (keys [0,32) / [32,64) of every half tile) each keep their OWN running maximum, row sum and output accumulator:
+// P V for the first two K16 steps of a half tile accumulates into O_A (TMEM columns [128,192)), for the last two into O_B
+// ([192,256)), so neither thread ever needs the other's maximum inside the loop (they sit in different warps; an exchange per
+// tile would be a 256-thread barrier).  The maximum is lazy: a thread keeps its stale m while the tile maximum exceeds it by at
+// most 8 (P <= 2^8: harmless in fp32 sums and in bf16, which has fp32's exponent range) and otherwise rescales its accumulator
+// row in TMEM (after the previous P V has completed, before releasing this tile's P) - a handful of times per row.  The two
+// partial results are merged flash-decoding style at the end: O = (w_A O_A + w_B O_B) / (w_A l_A + w_B l_B), w = 2^(m - max m).
+// TMEM: S half tiles in two 64-column buffers [0,64) [64,128); 256 columns per CTA, two CTAs per SM as before.
+constexpr float AT_LAZY = 8.f;
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const __grid_constant__ CUtensorMap tmv,
+                const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale_log2e, int kv_div,
+                bf16* __restrict__ out, int ldo, const int* __restrict__ kstart, const int* __restrict__ klen, const int* __restrict__ qoff) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_o;
+  __shared__ __align__(8) uint64_t bar_full[AT_KVST], bar_empty[AT_KVST];   // K/V stages
+  __shared__ __align__(8) uint64_t s_full[2], s_free[2];            // S half-tile buffers
+  __shared__ __align__(8) uint64_t p_full[2], p_free[2];            // P half-tile buffers
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xm[2][AT_BQ], xl[2][AT_BQ];   // (max, sum) exchange between the two threads of a row
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int L = len[b], s0 = start[b];
+  const int Lk = klen ? klen[b] : L, ks0 = kstart ? kstart[b] : s0, q0 = qoff ? qoff[b] : 0;
+  const int i0 = blockIdx.x * AT_BQ;
+  if (i0 >= L) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sKV = base + Q_BYTES, sP = sKV + AT_KVST * KV_STAGE;
+  const int i_last = q0 + min(i0 + AT_BQ, L) - 1;
+  const int kmax = chunk > 0 ? min(Lk, (i_last / chunk + 1) * chunk) : Lk;
+  const int G = (kmax + AT_BK - 1) / AT_BK;
+
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+  constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar_q), 1);
+    mbar_init(smem_u32(&bar_o), 1);
+    for (int s = 0; s < AT_KVST; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_free[s]), 256);
+      mbar_init(smem_u32(&p_full[s]), 256);
+      mbar_init(smem_u32(&p_free[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_slot, tOA = tmem_slot + 128, tOB = tmem_slot + 192;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
+      tma_load_2d(sQ, &tmq, smem_u32(&bar_q), h * AT_HD, s0 + i0);
+      for (int g = 0; g < G; ++g) {
+        const int st = g % AT_KVST;
+        mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)(((g / AT_KVST) & 1) ^ 1));
+        const uint32_t fb = smem_u32(&bar_full[st]);
+        mbar_expect_tx(fb, KV_STAGE);
+        tma_load_2d(sKV + st * KV_STAGE, &tmk, fb, (h / kv_div) * AT_HD, ks0 + g * AT_BK);
+        tma_load_2d(sKV + st * KV_STAGE + K_BYTES, &tmv, fb, (h / kv_div) * AT_HD, ks0 + g * AT_BK);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bar_q), 0);
+      auto issue_s = [&](int g) {
+        const int st = g % AT_KVST, sb = g & 1;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((g / AT_KVST) & 1));
+        mbar_wait(smem_u32(&s_free[sb]), (uint32_t)(((g >> 1) & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sK = sKV + st * KV_STAGE;
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) umma(tbase + (uint32_t)sb * 64u, desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[sb]));
+      };
+      issue_s(0);
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) issue_s(g + 1);
+        const int st = g % AT_KVST, pb = g & 1;
+        mbar_wait(smem_u32(&p_full[pb]), (uint32_t)((g >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sV = sKV + st * KV_STAGE + K_BYTES;
+        const uint32_t pa = sP + pb * 16384;
+#pragma unroll
+        for (int k = 0; k < AT_BK / 16; ++k)      // keys [0,32) -> O_A, keys [32,64) -> O_B
+          umma(k < 2 ? tOA : tOB, desc_sw128(pa + k * 32), desc_sw128(sV + k * 2048), IDESC_O, (g > 0 || (k & 1)) ? 1u : 0u);
+        umma_commit(smem_u32(&p_free[pb]));
+        umma_commit(smem_u32(&bar_empty[st]));
+      }
+      umma_commit(smem_u32(&bar_o));
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const int i = i0 + row;
+    const int klim = i < L ? (chunk > 0 ? min(Lk, ((q0 + i) / chunk + 1) * chunk) : Lk) : 0;
+    const uint32_t trow = ((uint32_t)(q4 * 32) << 16);
+    const int cb2 = half * 32;
+    const uint32_t tMine = (half ? tOB : tOA) + trow;
+    float m_run = -INFINITY;       // in log2 units (score * scale * log2 e)
+    float lsum = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const int pb = g & 1;
+      mbar_wait(smem_u32(&s_full[pb]), (uint32_t)((g >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int j0 = g * AT_BK + cb2;
+      const bool full = j0 + 32 <= klim;
+      uint32_t rr[2][16];
+      const uint32_t tS = tbase + (uint32_t)pb * 64u + trow + (uint32_t)cb2;
+      tmem_ld16_nowait(tS, rr[0]);
+      tmem_ld16_nowait(tS + 16u, rr[1]);
+      tmem_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&s_free[pb]));
+      float tm = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) tm = fmaxf(tm, fmaxf(__uint_as_float(rr[0][e]), __uint_as_float(rr[1][e])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          if (j0 + e < klim) tm = fmaxf(tm, __uint_as_float(rr[0][e]));
+          if (j0 + 16 + e < klim) tm = fmaxf(tm, __uint_as_float(rr[1][e]));
+        }
+      }
+      tm *= scale_log2e;             // scale > 0: max commutes with the scaling
+      const bool need = tm > m_run + AT_LAZY;          // also the first tile with a visible key (m_run = -inf)
+      const bool resc = need && m_run != -INFINITY;    // something has been accumulated under the old maximum
+      // tcgen05.ld / .st are warp-collective (.sync.aligned): the whole warp takes the rescale path when any row needs it, rows
+      // that do not scale by 1
+      if (__any_sync(0xffffffffu, resc)) {
+        // every P V issued so far has to be complete before the accumulator rows are rewritten: P V(g-1) is the last one
+        mbar_wait(smem_u32(&p_free[pb ^ 1]), (uint32_t)(((g - 1) >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float f = resc ? fast_ex2(m_run - tm) : 1.f;
+        lsum *= f;
+#pragma unroll 1
+        for (int c = 0; c < AT_HD; c += 16) {
+          float v[16];
+          tmem_ld16(tMine + (uint32_t)c, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] *= f;
+          tmem_st16(tMine + (uint32_t)c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      if (need) m_run = tm;
+      const float mneg = (m_run == -INFINITY) ? 0.f : -m_run;
+      mbar_wait(smem_u32(&p_free[pb]), (uint32_t)(((g >> 1) & 1) ^ 1));    // P(g-2) has been consumed by its MMA
+      const uint32_t prow = sP + (uint32_t)pb * 16384u + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+#pragma unroll
+      for (int c4 = 0; c4 < 2; ++c4) {
+        const int c = c4 * 16;
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float p0 = fast_ex2(fmaf(__uint_as_float(rr[c4][e]), scale_log2e, mneg));
+          float p1 = fast_ex2(fmaf(__uint_as_float(rr[c4][e + 1]), scale_log2e, mneg));
+          if (!full) {
+            if (j0 + c + e >= klim) p0 = 0.f;
+            if (j0 + c + e + 1 >= klim) p1 = 0.f;
+          }
+          lsum += p0 + p1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        const uint32_t ch = (uint32_t)((cb2 + c) >> 3);
+        const uint32_t a0 = prow + (((ch) ^ (uint32_t)(row & 7)) << 4);
+        const uint32_t a1 = prow + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&p_full[pb]));
+    }
+    xm[half][row] = m_run;
+    xl[half][row] = lsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float mA = xm[0][row], mB = xm[1][row];
+    const float mm = fmaxf(mA, mB);
+    const float wA = (mA == -INFINITY) ? 0.f : fast_ex2(mA - mm), wB = (mB == -INFINITY) ? 0.f : fast_ex2(mB - mm);
+    const float den = wA * xl[0][row] + wB * xl[1][row];
+    mbar_wait(smem_u32(&bar_o), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    const float fA = wA * inv, fB = wB * inv;
+#pragma unroll 1
+    for (int c = half * 32; c < half * 32 + 32; c += 16) {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_nowait(tOA + trow + (uint32_t)c, ra);
+      tmem_ld16_nowait(tOB + trow + (uint32_t)c, rb);
+      tmem_wait();
+      if (i < L) {
+        __align__(16) bf16 t[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          // an accumulator that never saw a visible key holds P = 0 products only, but guard against 0 * garbage all the same
+          const float a = wA > 0.f ? __uint_as_float(ra[e]) * fA : 0.f;
+          const float bb = wB > 0.f ? __uint_as_float(rb[e]) * fB : 0.f;
+          t[e] = __float2bfloat16_rn(a + bb);
+        }
+        bf16* op = out + (size_t)(s0 + i) * ldo + h * AT_HD + c;
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<uint4*>(t);
+        *reinterpret_cast<uint4*>(op + 8) = *reinterpret_cast<uint4*>(t + 8);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+  }
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -374,9 +613,14 @@ void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k,
   static bool attr = false;
   if (!attr) {
     CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
     attr = true;
   }
   dim3 grid(ceil_div(s.max_len, AT_BQ), H, s.B);
+  if (ctx->attn_single_pass)
+    attn_tc1_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
+                                                       kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr);
+  else
   attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
                                                     kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr);
   ctx->launches++;
