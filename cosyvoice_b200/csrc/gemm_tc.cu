@@ -262,6 +262,55 @@ __device__ __forceinline__ void epi_math16(const EpiDev& e, int r, bool rin, int
   }
 }
 
+// epi_math16 for a full group of 16 columns of the persistent kernel: the row's sequence index has been resolved by the caller
+// (loaded one tile ahead) and the bias of the tile's columns sits in shared memory.  In epi_math16 the dependent row2seq load
+// (an L2 round trip) and the bias loads are issued after tcgen05.wait::ld in every group, four times per tile and thread:
+// removing the math of a to_q/k/v tile took the kernel from 78.9 to 48.2 us (ablation in profiles/r02_flow.md).
+__device__ __forceinline__ void epi_math16p(const EpiDev& e, int r, bool rin, int seq, bool valid, const float* s_bias, int cl, int n0,
+                                            const float* acc, float* v, float* w2) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = acc[i];
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias + cl + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (e.rowvec && valid) {
+    const float* rv = e.rowvec + (size_t)seq * e.rowvec_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(rv + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  act16_fast(e.act1, v, e.act1_param, e.alpha1 ? e.alpha1 + n0 : nullptr);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] *= e.scale;
+  if (e.resid && rin) {
+    const float* rp = e.resid + (size_t)r * e.resid_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(rp + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  }
+  if (e.out2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w2[i] = v[i];
+    act16_fast(e.act2, w2, e.act2_param, e.alpha2 ? e.alpha2 + n0 : nullptr);
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w2[i] = 0.f;
+    }
+  }
+}
+
 // 16 consecutive columns of one tile row into a SWIZZLE_128B staging tile (128-byte wide sub-tiles of 128 rows, 16 KB each)
 __device__ __forceinline__ void stage_store16(uint32_t stg, int dtype, int row, int c, const float* v) {
   if (dtype != DT_F32) {
@@ -315,7 +364,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[BN], s_a1[BN], s_a2[BN];
+  __shared__ __align__(16) float s_bias[BN];
+  __shared__ float s_a1[BN], s_a2[BN];
 
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
@@ -398,6 +448,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // coalesced output: the tile is staged in shared memory (the operand stages are free once the accumulator is
       // complete) in SWIZZLE_128B sub-tiles and written by TMA stores - full 128-byte lines instead of one 32/64-byte
       // piece per thread per row; rows / columns outside the matrix are clipped by the tensor map.
+      // the row's sequence index and the bias of the tile's columns are fetched while the main loop runs (epi_math16p)
+      int seq = 0;
+      if (rin && ep.row2seq) seq = ep.row2seq[r];
+      const bool valid = rin && (!ep.row2seq || seq >= 0);
+      for (int i = threadIdx.x - 64; i < BN; i += 256) s_bias[i] = (ep.bias && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&bar_acc), 0);
       if (threadIdx.x == 64) stamp(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -408,6 +464,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
       for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         if (n0 + c >= N) break;
+        const bool full32 = n0 + c + 32 <= N;
         uint32_t ra[16], rb[16];
         tmem_ld16_nowait(trow0 + (uint32_t)c, ra);             // two loads in flight, one wait
         tmem_ld16_nowait(trow0 + (uint32_t)(c + 16), rb);
@@ -415,13 +472,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float acc[16], v[16], w2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
-        epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
+        if (full32) epi_math16p(ep, r, rin, seq, valid, s_bias, c, n0 + c, acc, v, w2);
+        else epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
         stage_store16(stg1, ep.out_dtype, row, c, v);
         if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
         if (n0 + c + 16 < N) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rb[i]);
-          epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
+          if (full32) epi_math16p(ep, r, rin, seq, valid, s_bias, c + 16, n0 + c + 16, acc, v, w2);
+          else epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
           stage_store16(stg1, ep.out_dtype, row, c + 16, v);
           if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c + 16, w2);
         }
@@ -585,6 +644,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   __shared__ __align__(8) uint64_t bar_accf[2];
   __shared__ __align__(8) uint64_t bar_acce[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[2][BN];      // bias of the current / next tile's columns (epilogue warps)
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -663,22 +723,41 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int row = q * 32 + lane;
     const uint32_t out_tile_bytes = (uint32_t)TC_BM * BN * (ep.out_dtype == DT_F32 ? 4u : 2u);
     uint32_t tcount = 0;
+    // operands of a tile's epilogue that do not depend on its accumulator are fetched ONE TILE AHEAD, under the previous tile's
+    // column loop: the row's sequence index (register) and the bias of the tile's columns (shared memory, two buffers)
+    auto fetch_seq = [&](int tile) -> int {
+      const int rr = (tile / ntn) * TC_BM + row;
+      return (tile < ntiles && rr < rowsOut && ep.row2seq) ? ep.row2seq[rr] : 0;
+    };
+    auto fetch_bias = [&](int tile, uint32_t b) {
+      if (tile >= ntiles) return;
+      const int nn = (tile % ntn) * BN;
+      for (int i = threadIdx.x - 64; i < BN; i += ETHREADS) s_bias[b][i] = (ep.bias && nn + i < N) ? ep.bias[nn + i] : 0.f;
+    };
+    int seq_next = fetch_seq(blockIdx.x);
+    fetch_bias(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int r0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
       const int r = r0 + row;
       const bool rin = r < rowsOut;
       const uint32_t buf = tcount & 1u, use = tcount >> 1;
+      const int seq = seq_next;
+      const bool valid = rin && (!ep.row2seq || seq >= 0);
+      seq_next = fetch_seq(tile + gridDim.x);
+      fetch_bias(tile + gridDim.x, (tcount + 1) & 1u);      // every thread is past the column loop of the tile that used this buffer
       // staging tile of this iteration: with two buffers the one used two tiles ago has been read by its TMA store
       // (thread 64 waited for that before reaching this barrier)
-      if (tcount > 0) asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
       const uint32_t stg1 = stg_base + (stg_bufs == 2 ? (tcount & 1u) * 32768u : 0u);
       const uint32_t stg2 = stg1 + out_tile_bytes;
+      const float* sb = s_bias[tcount & 1u];
       mbar_wait(smem_u32(&bar_accf[buf]), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow0 = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c = part * CPP; c < (part + 1) * CPP; c += 32) {
         if (n0 + c >= N) break;
+        const bool full32 = n0 + c + 32 <= N;
         uint32_t ra[16], rb[16];
         tmem_ld16_nowait(trow0 + (uint32_t)c, ra);
         tmem_ld16_nowait(trow0 + (uint32_t)(c + 16), rb);
@@ -686,13 +765,15 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         float acc[16], v[16], w2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
-        epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
+        if (full32) epi_math16p(ep, r, rin, seq, valid, sb, c, n0 + c, acc, v, w2);
+        else epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
         stage_store16(stg1, ep.out_dtype, row, c, v);
         if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
         if (n0 + c + 16 < N) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rb[i]);
-          epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
+          if (full32) epi_math16p(ep, r, rin, seq, valid, sb, c + 16, n0 + c + 16, acc, v, w2);
+          else epi_math16(ep, r, rin, n0 + c + 16, N, acc, v, w2);
           stage_store16(stg1, ep.out_dtype, row, c + 16, v);
           if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c + 16, w2);
         }
