@@ -655,6 +655,12 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = (K + TC_BK - 1) / TC_BK;
   const int iters = taps * kchunks;
+  // "part mode": with 16 epilogue warps and a single staging tile, the 64 (16-bit) / 32 (fp32) columns of one group of four warps
+  // are exactly one 16 KB TMA sub-tile.  Each group then runs its own staging pipeline (own named barrier, own elected thread
+  // issuing its sub-tile's store and waiting for it only right before the NEXT tile's first staging write), instead of all 16
+  // warps meeting at two CTA-wide barriers around one thread that issues four stores and waits ~1 us for the whole 64 KB tile to
+  // be read (ablation in profiles/r02_flow.md: the store path cost 19 of 79 us of a to_qkv launch).
+  const bool pm = EW == 16 && stg_bufs == 1 && ep.out2 == nullptr && (BN / 4) * (ep.out_dtype == DT_F32 ? 4 : 2) == 128;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -663,7 +669,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_accf[b]), 1);
-      mbar_init(smem_u32(&bar_acce[b]), 1);
+      mbar_init(smem_u32(&bar_acce[b]), pm ? 4 : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -729,10 +735,17 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       const int rr = (tile / ntn) * TC_BM + row;
       return (tile < ntiles && rr < rowsOut && ep.row2seq) ? ep.row2seq[rr] : 0;
     };
+    const int pt = (int)threadIdx.x - 64 - part * 128;     // index inside the group of four warps that shares `part`
+    const bool elected = pt == 0;
+    const int part_bar = 2 + part;                         // named barriers 2..5 (1 = all epilogue warps, 0 = __syncthreads)
     auto fetch_bias = [&](int tile, uint32_t b) {
       if (tile >= ntiles) return;
       const int nn = (tile % ntn) * BN;
-      for (int i = threadIdx.x - 64; i < BN; i += ETHREADS) s_bias[b][i] = (ep.bias && nn + i < N) ? ep.bias[nn + i] : 0.f;
+      if (pm) {
+        for (int i = pt; i < CPP; i += 128) s_bias[b][part * CPP + i] = (ep.bias && nn + part * CPP + i < N) ? ep.bias[nn + part * CPP + i] : 0.f;
+      } else {
+        for (int i = threadIdx.x - 64; i < BN; i += ETHREADS) s_bias[b][i] = (ep.bias && nn + i < N) ? ep.bias[nn + i] : 0.f;
+      }
     };
     int seq_next = fetch_seq(blockIdx.x);
     fetch_bias(blockIdx.x, 0);
@@ -744,16 +757,17 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       const int seq = seq_next;
       const bool valid = rin && (!ep.row2seq || seq >= 0);
       seq_next = fetch_seq(tile + gridDim.x);
-      fetch_bias(tile + gridDim.x, (tcount + 1) & 1u);      // every thread is past the column loop of the tile that used this buffer
+      fetch_bias(tile + gridDim.x, (tcount + 1) & 1u);      // every thread (of the part) is past the column loop of the tile that used this buffer
       // staging tile of this iteration: with two buffers the one used two tiles ago has been read by its TMA store
       // (thread 64 waited for that before reaching this barrier)
-      asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+      if (!pm) asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
       const uint32_t stg1 = stg_base + (stg_bufs == 2 ? (tcount & 1u) * 32768u : 0u);
       const uint32_t stg2 = stg1 + out_tile_bytes;
       const float* sb = s_bias[tcount & 1u];
       mbar_wait(smem_u32(&bar_accf[buf]), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow0 = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      bool may_stage = !pm;
 #pragma unroll 1
       for (int c = part * CPP; c < (part + 1) * CPP; c += 32) {
         if (n0 + c >= N) break;
@@ -767,6 +781,13 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
         if (full32) epi_math16p(ep, r, rin, seq, valid, sb, c, n0 + c, acc, v, w2);
         else epi_math16(ep, r, rin, n0 + c, N, acc, v, w2);
+        if (!may_stage) {
+          // part mode: the sub-tile may be overwritten once the store of the previous tile has read it (and the bias written by the
+          // part's threads for this tile is visible)
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
+          may_stage = true;
+        }
         stage_store16(stg1, ep.out_dtype, row, c, v);
         if (ep.out2) stage_store16(stg2, ep.out2_dtype, row, c, w2);
         if (n0 + c + 16 < N) {
@@ -780,6 +801,17 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (pm) {
+        asm volatile("bar.sync %0, 128;" ::"r"(part_bar) : "memory");
+        if (elected) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          mbar_arrive(smem_u32(&bar_acce[buf]));      // 4 arrivals: every part has finished reading this accumulator
+          const int w1 = ep.out_dtype == DT_F32 ? 32 : 64;
+          if (n0 + part * w1 < N) tma_store_2d(&tmap_o, stg1 + (uint32_t)part * 16384u, n0 + part * w1, r0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
       if (threadIdx.x == 64) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -795,6 +827,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
+    if (pm && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
