@@ -147,12 +147,29 @@ __device__ __forceinline__ float apply_act_fast(int act, float x, float param, f
 // 16 values at once: the dispatch on the (run-time) activation kind happens ONCE, outside the element loop.  With the switch
 // inside an unrolled loop every element paid the whole dispatch (~60 issue slots per element, measured: any activation made the
 // tcgen05 GEMM epilogue 2.4x slower than none).
+// tanh-form GELU of 16 values with the tanh of TWO arguments per MUFU instruction (tanh.approx.f16x2): the GELU epilogue of
+// ff.net.0 is MUFU-bound (32 768 tanh per 128 x 256 tile at 16 per clock per SM; +11 us per launch against no activation).  The
+// half-precision tanh is off by <= 5e-4 absolute, i.e. <= 2.5e-4 |x| in the GELU - below the bf16 rounding of the stored result
+// (3.9e-3 |x|); only the bf16-mode epilogues come here.
+__device__ __forceinline__ void gelu16_packed(float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float x0 = v[i], x1 = v[i + 1];
+    const float u0 = fminf(fmaxf(x0 * fmaf(x0 * x0, 0.0356774081f, 0.7978845608f), -10.f), 10.f);
+    const float u1 = fminf(fmaxf(x1 * fmaf(x1 * x1, 0.0356774081f, 0.7978845608f), -10.f), 10.f);
+    const __half2 h = __floats2half2_rn(u0, u1);
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&h)));
+    const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&t));
+    v[i] = 0.5f * x0 * (1.f + tf.x);
+    v[i + 1] = 0.5f * x1 * (1.f + tf.y);
+  }
+}
 __device__ __forceinline__ void act16_fast(int act, float* v, float param, const float* __restrict__ alpha /*per column or null*/) {
   switch (act) {
     case ACT_NONE: break;
     case ACT_GELU:
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(ACT_GELU, v[i], 0.f, 1.f);
+      gelu16_packed(v);
       break;
     case ACT_SILU:
 #pragma unroll
@@ -183,8 +200,7 @@ __device__ __forceinline__ void act16_fast(int act, float* v, float param, const
       for (int i = 0; i < 16; ++i) v[i] = fabsf(v[i]);
       break;
     case ACT_GELU_TANH:
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(ACT_GELU_TANH, v[i], 0.f, 1.f);
+      gelu16_packed(v);
       break;
     default: break;
   }

@@ -155,3 +155,31 @@ def test_overlapping_tts_requests_do_not_share_lm_sessions(golden):
     # the idle pool holds both sessions now and stays bounded
     assert sum(len(v) for v in m._free_sessions.values()) >= 2
     assert len(m._session_lru) <= m.max_idle_sessions
+
+
+def test_batcher_over_tts_batch(golden):
+    """cosyvoice_b200.batcher.TtsBatcher over the real model: requests submitted while the worker is busy are served as ragged batches
+    and every request gets the waveform tts_batch gives for that batch (first request = the reference's offline waveform), as float
+    tensors and as the servers' int16 PCM bytes."""
+    from cosyvoice_b200.batcher import TtsBatcher, pcm16
+    g = golden("stream_tts")
+    m = model()
+    req, U = request()
+    req2 = dict(req)
+    g2 = torch.Generator().manual_seed(123)
+    req2["text"] = torch.randint(0, 151643, (1, 5), generator=g2, dtype=torch.int32)
+    Ub = torch.rand(141, 2, 2, generator=g2)
+    Ub[:, 0] = U[:141]
+    m.uniforms_override = Ub
+    m.noise_fn = lambda n: stream_noise(0, n).to(m.device)
+    try:
+        want = m.tts_batch([req, req2])
+        with TtsBatcher(m, max_batch=2, max_wait_ms=2000) as b:
+            f1, f2 = b.submit(**req), b.submit_pcm(**req2)
+            w1, p2 = f1.result(timeout=120), f2.result(timeout=120)
+        assert b.batches == [2]
+    finally:
+        m.uniforms_override, m.noise_fn = None, None
+    assert torch.equal(w1, want[0]) and p2 == pcm16(want[1])
+    ref = torch.from_numpy(g["offline_wav"])
+    assert w1.shape == ref.shape and maxdiff(w1[:, :24000], ref[:, :24000]) < 5e-3
