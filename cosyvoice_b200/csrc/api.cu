@@ -533,5 +533,17 @@ int cvk_mel_spectrogram_ex(cvk_ctx* ctx, const float* wav, const int* lens, int 
   mel_spectrogram(ctx, wav, lens, B, fmax_hz, mel, (cudaStream_t)stream);
   CVK_API_END
 }
+int cvk_whisper_log_mel(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(wav && lens && out && B > 0, "cvk_whisper_log_mel: bad arguments");
+  whisper_log_mel(ctx, wav, lens, B, out, (cudaStream_t)stream);
+  CVK_API_END
+}
+int cvk_kaldi_fbank(cvk_ctx* ctx, const float* wav, const int* lens, int B, int subtract_mean, float* out, void* stream) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(wav && lens && out && B > 0, "cvk_kaldi_fbank: bad arguments");
+  kaldi_fbank80(ctx, wav, lens, B, subtract_mean, out, (cudaStream_t)stream);
+  CVK_API_END
+}
 
 }  // extern "C"

@@ -171,6 +171,7 @@ struct cvk_ctx {
   DitModel* dit = nullptr;                  // CosyVoice3 flow (stage "flow3")
   LlmModel* llm = nullptr;
   void* mel_model = nullptr;
+  void* prompt_feat_model = nullptr;      // prompt_feat.cu (whisper log-mel / kaldi fbank constants), built on first use
   void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled entry point
   std::atomic<int64_t> launches{0};         // kernels launched by this library (bench.py gpu_launches); LM-session calls and workspace calls may run on two threads
   int op_out_bf16 = 0;                      // cvk_op_conv1d: bf16 output matrix (the estimator's usual epilogue) instead of fp32
@@ -291,6 +292,9 @@ struct KvGeom {
   const int* d_klen = nullptr;
   const int* d_qoff = nullptr;
 };
+// prompt-side acoustic features (prompt_feat.cu)
+void whisper_log_mel(cvk_ctx* ctx, const float* wav, const int* lens, int B, float* out, cudaStream_t st);
+void kaldi_fbank80(cvk_ctx* ctx, const float* wav, const int* lens, int B, int subtract_mean, float* out, cudaStream_t st);
 // incremental streaming flow (flow.cu)
 struct cvk_flow_stream;
 cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps);

@@ -74,6 +74,8 @@ SIGNATURES = {
     "cvk_ras_sample": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "cvk_mel_spectrogram": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
     "cvk_mel_spectrogram_ex": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "cvk_whisper_log_mel": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, _vp, _vp]),
+    "cvk_kaldi_fbank": (ctypes.c_int, [_vp, _vp, _c_int_p, ctypes.c_int, ctypes.c_int, _vp, _vp]),
 }
 
 
@@ -435,6 +437,20 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ mel
+    def whisper_log_mel(self, wav, lens):
+        """wav [sum N_b] at 16 kHz -> [sum N_b // 160, 128] (whisper.log_mel_spectrogram(n_mels=128), time-major)"""
+        wav = _f32(wav, self.device)
+        out = torch.empty(sum(int(l) // 160 for l in lens), 128, device=self.device)
+        self._check(self.lib.cvk_whisper_log_mel(self.h, _ptr(wav), _ints(lens), len(lens), _ptr(out), _stream()))
+        return out
+
+    def kaldi_fbank(self, wav, lens, subtract_mean=True):
+        """wav [sum N_b] at 16 kHz -> [sum 1 + (N_b - 400) // 160, 80] (kaldi.fbank(num_mel_bins=80, dither=0) [- mean over frames])"""
+        wav = _f32(wav, self.device)
+        out = torch.empty(sum(1 + (int(l) - 400) // 160 for l in lens), 80, device=self.device)
+        self._check(self.lib.cvk_kaldi_fbank(self.h, _ptr(wav), _ints(lens), len(lens), int(bool(subtract_mean)), _ptr(out), _stream()))
+        return out
+
     def mel_spectrogram(self, wav, lens, fmax=8000):
         """wav [sum N_b] -> mel [sum N_b // 480, 80]; fmax 8000 (CosyVoice2) or None / 12000 (CosyVoice3)"""
         wav = _f32(wav, self.device)

@@ -237,6 +237,17 @@ int cvk_mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens_host, in
  * examples/libritts/cosyvoice3/conf/cosyvoice3.yaml:140-147) */
 int cvk_mel_spectrogram_ex(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, int fmax_hz, float* mel, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- prompt-side features (16 kHz)
+ * the two feature extractors the reference frontend runs on the CPU before its ONNX sessions.
+ * cvk_whisper_log_mel replaces whisper.log_mel_spectrogram(speech, n_mels=128) at cosyvoice/cli/frontend.py:98 (hann 400 / hop 160,
+ * center, 128 Slaney mels, log10, floor at max - 8, (x + 4) / 4): wav [sum N_b] (N_b > 200) -> out [sum floor(N_b/160), 128],
+ * time-major (the reference tensor [1,128,T] transposed).
+ * cvk_kaldi_fbank replaces kaldi.fbank(speech, num_mel_bins=80, dither=0, sample_frequency=16000) at frontend.py:108-112 and, with
+ * subtract_mean != 0, the mean normalisation of :113: wav [sum N_b] (N_b >= 400) -> out [sum 1 + floor((N_b-400)/160), 80].
+ * The speech tokenizer / CAM++ networks that consume them are ONNX files outside the repository and are not rebuilt. */
+int cvk_whisper_log_mel(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, float* out, void* stream);
+int cvk_kaldi_fbank(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, int subtract_mean, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
