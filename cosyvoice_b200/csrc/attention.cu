@@ -192,10 +192,46 @@ void attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, co
   CVK_LAUNCH_CHECK();
 }
 
+void relpos_attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& qu, const Mat& qv, const Mat& k, const Mat& v, const Mat& pos, int pos_rows,
+                             int pos_center, const Seqs& s, int H, int chunk, float scale, const Mat& U, const Mat& out);
+
+namespace {
+// qu = q + pos_bias_u, qv = q + pos_bias_v (transformer/attention.py:303-306), bf16
+__global__ void add_pos_bias_kernel(const bf16* __restrict__ q, int ldq, const float* __restrict__ bu, const float* __restrict__ bv, int rows, int C,
+                                    bf16* __restrict__ qu, bf16* __restrict__ qv, int ldo) {
+  size_t total = (size_t)rows * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = i / C, c = i % C;
+    const float x = __bfloat162float(q[(size_t)r * ldq + c]);
+    qu[(size_t)r * ldo + c] = __float2bfloat16_rn(x + bu[c]);
+    qv[(size_t)r * ldo + c] = __float2bfloat16_rn(x + bv[c]);
+  }
+}
+}  // namespace
+
 void relpos_attention_fwd(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k, const Mat& v, const Mat& pos, int pos_center,
                           const float* bias_u, const float* bias_v, const Seqs& s, int H, int chunk, float scale, const Mat& out) {
   CVK_REQUIRE(q.dtype == k.dtype && q.dtype == v.dtype && q.dtype == out.dtype && q.dtype == pos.dtype, "attention: mixed dtypes");
   CVK_REQUIRE(pos.rows >= 2 * s.max_len - 1 + 0 && pos_center >= s.max_len - 1 + 0, "relative position table too small");
+  const int pos_rows = 2 * pos_center + 1;
+  if (q.dtype == DT_BF16 && ctx->use_tc_attn && ctx->enc_tc_attn && pos.rows >= round_up(pos_rows, 64)) {
+    // tensor-core path: the position term of every (query, table row) pair first (relpos_u_kernel), then the one-pass attention
+    // kernel with that term as an additive bias (attention_tc.cu)
+    double fl = 0;
+    for (int b = 0; b < s.B; ++b) fl += 6.0 * (double)s.len[b] * s.len[b] * 64 * H * (chunk > 0 ? 0.5 : 1.0);
+    ProfScope ps(ctx, st, FAM_ATTN, fl, (double)s.sum_len * H * 64 * 4 * q.esize());
+    const size_t mark = ctx->arena.off;
+    const int C = H * HD;
+    Mat qu = arena_mat(ctx, DT_BF16, s.R, C), qv = arena_mat(ctx, DT_BF16, s.R, C);
+    add_pos_bias_kernel<<<148 * 8, 256, 0, st>>>(q.b16(), q.ld, bias_u, bias_v, s.R, C, qu.b16(), qv.b16(), qu.ld);
+    ctx->launches++;
+    CVK_LAUNCH_CHECK();
+    const int ldu = round_up(pos_rows, 64);
+    Mat U = arena_mat(ctx, DT_F32, s.R * H, ldu, ldu);
+    relpos_attention_fwd_tc(ctx, st, qu, qv, k, v, pos, pos_rows, pos_center, s, H, chunk, scale, U, out);
+    ctx->arena.off = mark;
+    return;
+  }
   dim3 grid(ceil_div(s.max_len, BQ), H, s.B);
   if (q.dtype == DT_F32)
     attn_simt_kernel<float, true><<<grid, 128, 0, st>>>(q.f32(), q.ld, k.f32(), k.ld, v.f32(), v.ld, pos.f32(), pos.ld, pos.rows, pos_center, bias_u,

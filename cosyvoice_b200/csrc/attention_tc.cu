@@ -360,10 +360,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 // partial results are merged flash-decoding style at the end: O = (w_A O_A + w_B O_B) / (w_A l_A + w_B l_B), w = 2^(m - max m).
 // TMEM: S half tiles in two 64-column buffers [0,64) [64,128); 256 columns per CTA, two CTAs per SM as before.
 constexpr float AT_LAZY = 8.f;
+// BIAS: an additive score term read from global memory, bias(i, j) = ubias[((s0 + i) * H + h) * ldu + ucenter - i + j]: the
+// relative-position term of the conformer attention (transformer/attention.py:249-330), where row t of U = (q + pos_bias_v) p[t]^T
+// has been produced by relpos_u_kernel and the reference's rel_shift (attention.py:225-247) is the index map (i, j) -> center - (i - j).
+template <bool BIAS>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const __grid_constant__ CUtensorMap tmv,
                 const int* __restrict__ start, const int* __restrict__ len, int chunk, float scale_log2e, int kv_div,
-                bf16* __restrict__ out, int ldo, const int* __restrict__ kstart, const int* __restrict__ klen, const int* __restrict__ qoff) {
+                bf16* __restrict__ out, int ldo, const int* __restrict__ kstart, const int* __restrict__ klen, const int* __restrict__ qoff,
+                const float* __restrict__ ubias, int ldu, int ucenter) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_o;
   __shared__ __align__(8) uint64_t bar_full[AT_KVST], bar_empty[AT_KVST];   // K/V stages
@@ -471,11 +476,24 @@ attn_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       const bool full = j0 + 32 <= klim;
       uint32_t rr[2][16];
       const uint32_t tS = tbase + (uint32_t)pb * 64u + trow + (uint32_t)cb2;
+      float bia[BIAS ? 32 : 1];
+      if (BIAS) {       // issued before the TMEM load: the two latencies overlap
+        const float* ub = ubias + ((size_t)(s0 + i) * gridDim.y + h) * ldu + (ucenter - (q0 + i) + j0);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) bia[e] = (j0 + e < klim) ? __ldg(ub + e) : 0.f;
+      }
       tmem_ld16_nowait(tS, rr[0]);
       tmem_ld16_nowait(tS + 16u, rr[1]);
       tmem_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&s_free[pb]));
+      if (BIAS) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          rr[0][e] = __float_as_uint(__uint_as_float(rr[0][e]) + bia[e]);
+          rr[1][e] = __float_as_uint(__uint_as_float(rr[1][e]) + bia[16 + e]);
+        }
+      }
       float tm = -INFINITY;
       if (full) {
 #pragma unroll
@@ -578,6 +596,114 @@ attn_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 }
 
 
+// ---- relative-position scores of the conformer attention ---------------------------------------------------------------------
+// U[(s0 + i) * H + h][t] = (q_i + pos_bias_v)_h . p[t]_h for the table rows t that query tile i0 can address (t = center - (i - j),
+// j < L): one CTA per (query tile, head, sequence), 64-row tiles of the position table through the same TMA / tcgen05 pipeline as
+// the score pass of the attention kernel; the eight epilogue warps write fp32 rows (two threads per query row, 32 columns each).
+__global__ void __launch_bounds__(AT_THREADS, 2)
+relpos_u_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmp, const int* __restrict__ start,
+                const int* __restrict__ len, int center, int pos_rows, float* __restrict__ U, int ldu) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q;
+  __shared__ __align__(8) uint64_t bar_full[AT_KVST], bar_empty[AT_KVST];
+  __shared__ __align__(8) uint64_t s_full[3], s_free[3];
+  __shared__ uint32_t tmem_slot;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int L = len[b], s0 = start[b];
+  const int i0 = blockIdx.x * AT_BQ;
+  if (i0 >= L) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sP = base + Q_BYTES;
+  const int i_hi = min(i0 + AT_BQ, L) - 1;
+  const int t_lo = max(center - i_hi, 0), t_hi = min(center - i0 + L - 1, pos_rows - 1);
+  const int t0 = (t_lo / AT_BK) * AT_BK;
+  const int G = (t_hi - t0) / AT_BK + 1;
+  constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar_q), 1);
+    for (int s = 0; s < AT_KVST; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_free[s]), 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_slot;
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
+      tma_load_2d(sQ, &tmq, smem_u32(&bar_q), h * AT_HD, s0 + i0);
+      for (int g = 0; g < G; ++g) {
+        const int st = g % AT_KVST;
+        mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)(((g / AT_KVST) & 1) ^ 1));
+        const uint32_t fb = smem_u32(&bar_full[st]);
+        mbar_expect_tx(fb, K_BYTES);
+        tma_load_2d(sP + st * K_BYTES, &tmp, fb, h * AT_HD, t0 + g * AT_BK);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bar_q), 0);
+      for (int g = 0; g < G; ++g) {
+        const int st = g % AT_KVST, sb = g % 3;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((g / AT_KVST) & 1));
+        mbar_wait(smem_u32(&s_free[sb]), (uint32_t)(((g / 3) & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sK = sP + st * K_BYTES;
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) umma(tbase + (uint32_t)sb * 64u, desc_sw128(sQ + k * 32), desc_sw128(sK + k * 32), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[sb]));
+        umma_commit(smem_u32(&bar_empty[st]));
+      }
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const int i = i0 + row;
+    const uint32_t trow = ((uint32_t)(q4 * 32) << 16);
+    const int cb2 = half * 32;
+    float* urow = U + ((size_t)(s0 + i) * gridDim.y + h) * ldu;
+    for (int g = 0; g < G; ++g) {
+      const int sb = g % 3;
+      mbar_wait(smem_u32(&s_full[sb]), (uint32_t)((g / 3) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t rr[2][16];
+      const uint32_t tS = tbase + (uint32_t)sb * 64u + trow + (uint32_t)cb2;
+      tmem_ld16_nowait(tS, rr[0]);
+      tmem_ld16_nowait(tS + 16u, rr[1]);
+      tmem_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&s_free[sb]));
+      if (i < L) {
+        float4* dst = reinterpret_cast<float4*>(urow + t0 + g * AT_BK + cb2);      // ldu and t0 are multiples of 4
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4)
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            dst[c4 * 4 + (e >> 2)] = make_float4(__uint_as_float(rr[c4][e]), __uint_as_float(rr[c4][e + 1]), __uint_as_float(rr[c4][e + 2]),
+                                                 __uint_as_float(rr[c4][e + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+  }
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -613,16 +739,50 @@ void attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& q, const Mat& k,
   static bool attr = false;
   if (!attr) {
     CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(relpos_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
     attr = true;
   }
   dim3 grid(ceil_div(s.max_len, AT_BQ), H, s.B);
   if (ctx->attn_single_pass)
-    attn_tc1_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
-                                                       kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr);
+    attn_tc1_kernel<false><<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
+                                                              kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr,
+                                                              nullptr, 0, 0);
   else
   attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, kv_div, out.b16(), out.ld,
                                                     kg ? kg->d_kstart : nullptr, kg ? kg->d_klen : nullptr, kg ? kg->d_qoff : nullptr);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+}
+
+// Conformer relative-position attention on the tensor cores (bf16 operands): score(i, j) = ((q_i + u) . k_j + (q_i + v) . p[center - (i - j)]) * scale.
+// qu = q + pos_bias_u and qv = q + pos_bias_v are materialised by the caller; U (fp32 [rows * H, ldu], workspace) receives the second
+// term for every addressable table row, the attention kernel adds it as a bias.
+void relpos_attention_fwd_tc(cvk_ctx* ctx, cudaStream_t st, const Mat& qu, const Mat& qv, const Mat& k, const Mat& v, const Mat& pos, int pos_rows,
+                             int pos_center, const Seqs& s, int H, int chunk, float scale, const Mat& U, const Mat& out) {
+  CVK_REQUIRE(qu.dtype == DT_BF16 && qv.dtype == DT_BF16 && k.dtype == DT_BF16 && v.dtype == DT_BF16 && pos.dtype == DT_BF16 && out.dtype == DT_BF16 &&
+              U.dtype == DT_F32, "relpos_attention_fwd_tc: bf16 operands, fp32 workspace");
+  CVK_REQUIRE(U.ld % 4 == 0 && U.ld >= round_up(pos_rows, AT_BK) && U.rows >= s.R * H, "relpos_attention_fwd_tc: workspace too small");
+  CVK_REQUIRE(pos.rows >= round_up(pos_rows, AT_BK), "relpos_attention_fwd_tc: position table must be padded to a multiple of 64 rows");
+  CUtensorMap tq, tqv, tk, tv, tp;
+  make_map(ctx, &tq, qu, AT_BQ);
+  make_map(ctx, &tqv, qv, AT_BQ);
+  make_map(ctx, &tk, k, AT_BK);
+  make_map(ctx, &tv, v, AT_BK);
+  make_map(ctx, &tp, pos, AT_BK);
+  static bool attr = false;
+  if (!attr) {
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CVK_CHECK_CUDA(cudaFuncSetAttribute(relpos_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    attr = true;
+  }
+  dim3 grid(ceil_div(s.max_len, AT_BQ), H, s.B);
+  relpos_u_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tqv, tp, s.d_start, s.d_len, pos_center, pos_rows, U.f32(), U.ld);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  attn_tc1_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, s.d_start, s.d_len, chunk, scale * 1.4426950408889634f, 1, out.b16(), out.ld,
+                                                          nullptr, nullptr, nullptr, U.f32(), U.ld, pos_center);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
 }

@@ -198,6 +198,7 @@ struct cvk_ctx {
   int lm_fused = 1;                         // LM decode: fused finish+rmsnorm / rope+attention / SwiGLU-epilogue kernels
   int hift_f16 = 1;                         // tensor-core mode: vocoder operands in IEEE half (TF32-class mantissa) instead of bf16
   int build_f16 = 0;                        // set while a stage whose weights need the half copy is being finalised
+  int enc_tc_attn = 1;                      // conformer relative-position attention on the tcgen05 kernels (attention_tc.cu) instead of CUDA cores
   int attn_single_pass = 1;                 // flow attention: one-pass kernel with per-thread lazy maxima (attention_tc.cu)
   int lm_mega = 0;                          // LM decode: all layers of a step in one persistent cooperative kernel (llm_mega.cu); measured
                                             // 973 us / step against 886 us for the PDL-chained per-op path at batch 32 (profiles/r02_lm_decode.md): off by default

@@ -129,6 +129,28 @@ def test_persistent_gemm_flow_bit_identical():
     assert torch.equal(outs[0], outs[1]), maxdiff(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_encoder_relpos_attention_tensor_core_vs_cuda_core(tag):
+    """the conformer relative-position attention on the tcgen05 kernels (position scores by relpos_u_kernel, added as a bias inside the
+    one-pass attention kernel) against the CUDA-core flash kernel it replaces (same bf16 operands, fp32 math): ragged batch, offline
+    and with the streaming chunk masks + look-ahead context.  Output = after_norm rows, unit scale."""
+    c, sd, cfg = model("bf16", tag)
+    g = torch.Generator().manual_seed(5)
+    lens = [203, 77, 150]
+    toks = torch.randint(0, 6561, (sum(lens),), generator=g, dtype=torch.int32)
+    for streaming, ctxl in ((False, 0), (True, 3)):
+        outs = []
+        for on in (1, 0):
+            c.set_option("enc_tc_attn", on)
+            try:
+                outs.append(c.flow_encoder(toks, lens, streaming=streaming, context_len=ctxl).clone())
+            finally:
+                c.set_option("enc_tc_attn", 1)
+        assert torch.isfinite(outs[0]).all()
+        d = maxdiff(outs[0], outs[1])
+        assert d < 0.06, (streaming, d)          # bf16 re-rounding of P / of the intermediate activations through 3 (small) / 10 (full) layers
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("tag", ["small", "full"])
 def test_incremental_stream_equals_prefix_recompute(precision, tag):
