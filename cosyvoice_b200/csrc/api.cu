@@ -44,6 +44,7 @@ void llm_ras_sample(cvk_ctx* ctx, float* logp, int B, int V, const int32_t* hist
                     const float* uniforms, const int32_t* ignore_eos, int32_t* out_ids, cudaStream_t st);
 void mel_spectrogram(cvk_ctx* ctx, const float* wav, const int* lens, int B, int fmax_hz, float* mel, cudaStream_t st);
 void mel_init(cvk_ctx* ctx);
+void prompt_feat_init(cvk_ctx* ctx);
 
 #define CVK_API_BEGIN            \
   if (!ctx) return CVK_ERR_INVALID; \
@@ -209,6 +210,7 @@ int cvk_finalize(cvk_ctx* ctx, const char* stage, const int* cfg, int ncfg) {
   else if (s == "hift3") hift3_build(ctx);
   else if (s == "llm") llm_build(ctx, cfg, ncfg);
   else if (s == "mel") mel_init(ctx);
+  else if (s == "prompt") prompt_feat_init(ctx);
   else throw CvkError(CVK_ERR_INVALID, "unknown stage: " + s);
   CVK_CHECK_CUDA(cudaDeviceSynchronize());
   // raw tensors of this stage are no longer needed

@@ -83,7 +83,7 @@ __global__ void whisper_log_kernel(float* __restrict__ x, int ld, const int* __r
 }
 
 // kaldi: x = log(max(x, FLT_EPSILON)); optionally minus the utterance's mean over frames (frontend.py:113).  One CTA per
-// (utterance, group of 8 bins): the column sums run over the frames in a fixed order per thread, then a tree over the threads.
+// utterance, bin after bin: a column's sum runs over the frames in a fixed order per thread, then a tree over the threads.
 __global__ void kaldi_log_cmn_kernel(float* __restrict__ x, int ld, const int* __restrict__ start, const int* __restrict__ len, int subtract_mean) {
   __shared__ float part[256];
   const int b = blockIdx.x, s0 = start[b], L = len[b];
@@ -194,8 +194,7 @@ PromptFeatModel* build(cvk_ctx* ctx) {
     }
     m->k_mel = upload_w(ctx, fb, K_MEL, K_BINS, 1);
   }
-  CVK_CHECK_CUDA(cudaDeviceSynchronize());
-  return m;
+  return m;      // every upload above is a blocking cudaMemcpy: nothing in flight, no device-wide synchronisation needed
 }
 
 // shared body: frames of 3 rows of 160 -> DFT conv-GEMM -> power -> filterbank; returns the [R, n_mel] matrix in geometry sf
@@ -247,6 +246,9 @@ PromptFeatModel* model(cvk_ctx* ctx) {
   return (PromptFeatModel*)ctx->prompt_feat_model;
 }
 }  // namespace
+
+// cvk_finalize(ctx, "prompt"): build the constant matrices at set-up time (otherwise they are built by the first feature call)
+void prompt_feat_init(cvk_ctx* ctx) { model(ctx); }
 
 // wav: the utterances back to back (16 kHz, float), lens[b] samples each (> 200: reflect padding); out [sum lens[b]/160, 128]
 // time-major (the reference's [1, 128, T] transposed)

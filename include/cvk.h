@@ -244,7 +244,8 @@ int cvk_mel_spectrogram_ex(cvk_ctx* ctx, const float* wav, const int* lens_host,
  * time-major (the reference tensor [1,128,T] transposed).
  * cvk_kaldi_fbank replaces kaldi.fbank(speech, num_mel_bins=80, dither=0, sample_frequency=16000) at frontend.py:108-112 and, with
  * subtract_mean != 0, the mean normalisation of :113: wav [sum N_b] (N_b >= 400) -> out [sum 1 + floor((N_b-400)/160), 80].
- * The speech tokenizer / CAM++ networks that consume them are ONNX files outside the repository and are not rebuilt. */
+ * The speech tokenizer / CAM++ networks that consume them are ONNX files outside the repository and are not rebuilt.
+ * cvk_finalize(ctx, "prompt", NULL, 0) builds the constant DFT / filterbank matrices at set-up time (else: on the first call). */
 int cvk_whisper_log_mel(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, float* out, void* stream);
 int cvk_kaldi_fbank(cvk_ctx* ctx, const float* wav, const int* lens_host, int B, int subtract_mean, float* out, void* stream);
 
