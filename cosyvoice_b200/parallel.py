@@ -106,8 +106,9 @@ def gather_flat(flat, lens, dist, device, counts=None):
     all_lens = torch.zeros(world * maxn, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(all_lens, lens_p)
     if rank != 0:
-        if flat.numel():
-            dist.send(flat, dst=0)
+        if flat.numel():          # batched like the receiving side (an un-batched send is serialised with every other op of the group)
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat, 0)]):
+                w.wait()
         return None
     al = all_lens.view(world, maxn).tolist()
     per_rank = [[int(x) for x in al[r][:counts[r]]] for r in range(world)]
