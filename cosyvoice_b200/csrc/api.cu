@@ -401,7 +401,13 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
 int cvk_flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out) {
   CVK_API_BEGIN
   CVK_REQUIRE(out != nullptr, "cvk_flow_stream_create: bad arguments");
-  *out = flow_stream_create(ctx, max_frames, n_timesteps);
+  *out = flow_stream_create(ctx, max_frames, n_timesteps, 0);
+  CVK_API_END
+}
+int cvk_flow3_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out) {
+  CVK_API_BEGIN
+  CVK_REQUIRE(out != nullptr, "cvk_flow3_stream_create: bad arguments");
+  *out = flow_stream_create(ctx, max_frames, n_timesteps, 1);
   CVK_API_END
 }
 void cvk_flow_stream_destroy(cvk_ctx* ctx, cvk_flow_stream* fs) {

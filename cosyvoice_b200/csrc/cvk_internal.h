@@ -298,7 +298,7 @@ void whisper_log_mel(cvk_ctx* ctx, const float* wav, const int* lens, int B, flo
 void kaldi_fbank80(cvk_ctx* ctx, const float* wav, const int* lens, int B, int subtract_mean, float* out, cudaStream_t st);
 // incremental streaming flow (flow.cu)
 struct cvk_flow_stream;
-cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps);
+cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, int kind);
 void flow_stream_destroy(cvk_flow_stream* fs);
 size_t flow_stream_bytes(const cvk_flow_stream* fs);
 void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding, cudaStream_t st);

@@ -62,6 +62,10 @@ struct FlowModel {
 // new frames.  Per Euler step: K/V rows of every estimator transformer block for both CFG sequences, and the two-row tails of
 // every causal convolution's input.
 struct cvk_flow_stream {
+  int kind = 0;                 // 0: CosyVoice2 U-Net estimator (stage "flow"), 1: CosyVoice3 DiT (stage "flow3")
+  int kv_width = 1024;          // K | V columns per cached row: 2 x 512 (U-Net blocks), 2 x 1024 (DiT blocks)
+  int tail_rows = 2;            // rows a causal convolution reads in front of a chunk: k3 -> 2, the DiT's k31 position convolutions -> 30
+  int conv_c = 512;             // widest convolution input
   int cap = 0, n_steps = 0, adt = DT_F32, n_tb = 0, n_conv = 0;
   void* kv = nullptr;
   void* conv = nullptr;
@@ -569,8 +573,9 @@ struct EstBuffers {
 // convolution the last two input rows, are all a later call needs.  The reference recomputes the prefix instead
 // (cli/model.py:346-363).
 struct EstInc {
-  void* kv = nullptr;        // [n_tblocks][2 * cap + 64][1024] act dtype: K | V rows of CFG sequence 0 then 1
-  void* conv = nullptr;      // [n_convs][2 seqs][2 rows][512] act dtype
+  void* kv = nullptr;        // [n_tblocks][2 * cap + 64][kv_width] act dtype: K | V rows of CFG sequence 0 then 1
+  void* conv = nullptr;      // [n_convs][2 seqs][tail_rows][conv_c] act dtype
+  int kv_width = 1024, tail_rows = 2, conv_c = 512;
   int cap = 0;               // cache rows per sequence
   int t_prev = 0;            // frames already cached
   int tb_idx = 0, conv_idx = 0;
@@ -578,41 +583,63 @@ struct EstInc {
 };
 
 template <typename T>
-__global__ void conv_state_kernel(T* __restrict__ x, int ld, int C, const int* __restrict__ start, const int* __restrict__ len, T* __restrict__ state) {
-  // gap rows start-2, start-1 <- saved tail of the previous chunk; saved tail <- last two rows of this chunk
+__global__ void conv_state_kernel(T* __restrict__ x, int ld, int C, const int* __restrict__ start, const int* __restrict__ len, T* __restrict__ state,
+                                  int tail, int cstride) {
+  // gap rows start-tail .. start-1 <- saved tail of the previous chunk; saved tail <- last `tail` rows of this chunk (chunks are at
+  // least 50 rows, so the two row ranges never overlap)
   const int b = blockIdx.x, r = blockIdx.y;
-  T* srow = state + ((size_t)b * 2 + r) * 512;
-  T* gap = x + (size_t)(start[b] - 2 + r) * ld;
-  const T* tail = x + (size_t)(start[b] + len[b] - 2 + r) * ld;
+  T* srow = state + ((size_t)b * tail + r) * cstride;
+  T* gap = x + (size_t)(start[b] - tail + r) * ld;
+  const T* tl = x + (size_t)(start[b] + len[b] - tail + r) * ld;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     gap[c] = srow[c];
-    srow[c] = tail[c];
+    srow[c] = tl[c];
   }
 }
 
+// rows of a chunk's K | V columns (qkv columns [koff, koff + width)) appended to the cache of its sequence; the chunk's first row
+// goes to cache row qoff[b] (device memory, so that a captured launch stays valid from chunk to chunk)
 template <typename T>
-__global__ void kv_append_kernel(const T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len, T* __restrict__ cache,
-                                 int cap, int t_prev) {
+__global__ void kv_append_kernel(const T* __restrict__ qkv, int ld, int koff, int width, const int* __restrict__ start, const int* __restrict__ len,
+                                 T* __restrict__ cache, int cap, const int* __restrict__ qoff) {
   const int b = blockIdx.y;
-  const int L = len[b];
+  const int L = len[b], t_prev = qoff[b];
   for (int i = blockIdx.x; i < L; i += gridDim.x) {
-    const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(start[b] + i) * ld + 512);
-    uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)b * cap + t_prev + i) * 1024);
-    for (int c = threadIdx.x; c < 1024 * (int)sizeof(T) / 16; c += blockDim.x) dst[c] = src[c];
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(start[b] + i) * ld + koff);
+    uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)b * cap + t_prev + i) * width);
+    for (int c = threadIdx.x; c < width * (int)sizeof(T) / 16; c += blockDim.x) dst[c] = src[c];
   }
 }
 
 // the two rows a causal k=3 convolution reads in front of the chunk (call right before the convolution that consumes `in`)
 void conv_state(cvk_ctx* ctx, cudaStream_t st, EstInc* inc, const Mat& in, const Seqs& s) {
   if (!inc) return;
-  CVK_REQUIRE(in.cols <= 512 && s.B == 2, "conv_state: unexpected operand");
+  CVK_REQUIRE(in.cols <= inc->conv_c && s.B == 2, "conv_state: unexpected operand");
   const size_t es = in.esize();
-  char* state = (char*)inc->conv + (size_t)inc->conv_idx * 2 * 2 * 512 * es;
+  char* state = (char*)inc->conv + (size_t)inc->conv_idx * 2 * inc->tail_rows * inc->conv_c * es;
   ++inc->conv_idx;
-  if (in.dtype == DT_F32) conv_state_kernel<float><<<dim3(s.B, 2), 128, 0, st>>>(in.f32(), in.ld, in.cols, s.d_start, s.d_len, (float*)state);
-  else conv_state_kernel<bf16><<<dim3(s.B, 2), 128, 0, st>>>(in.b16(), in.ld, in.cols, s.d_start, s.d_len, (bf16*)state);
+  if (in.dtype == DT_F32)
+    conv_state_kernel<float><<<dim3(s.B, inc->tail_rows), 128, 0, st>>>(in.f32(), in.ld, in.cols, s.d_start, s.d_len, (float*)state, inc->tail_rows, inc->conv_c);
+  else
+    conv_state_kernel<bf16><<<dim3(s.B, inc->tail_rows), 128, 0, st>>>(in.b16(), in.ld, in.cols, s.d_start, s.d_len, (bf16*)state, inc->tail_rows, inc->conv_c);
   ctx->launches++;
   CVK_LAUNCH_CHECK();
+}
+
+// append the chunk's K | V rows (columns [koff, koff + kv_width) of qkv) to the cache of the next block and return that cache
+Mat kv_cache_append(cvk_ctx* ctx, cudaStream_t st, EstInc* inc, const Mat& qkv, int koff, const Seqs& s) {
+  const size_t es = qkv.esize();
+  const int crow = 2 * inc->cap + 64;
+  Mat cache((char*)inc->kv + (size_t)inc->tb_idx * crow * inc->kv_width * es, qkv.dtype, crow, inc->kv_width, inc->kv_width);
+  ++inc->tb_idx;
+  int bx = s.max_len < 256 ? s.max_len : 256;
+  if (qkv.dtype == DT_F32)
+    kv_append_kernel<float><<<dim3(bx, s.B), 128, 0, st>>>(qkv.f32(), qkv.ld, koff, inc->kv_width, s.d_start, s.d_len, cache.f32(), inc->cap, inc->kg.d_qoff);
+  else
+    kv_append_kernel<bf16><<<dim3(bx, s.B), 128, 0, st>>>(qkv.b16(), qkv.ld, koff, inc->kv_width, s.d_start, s.d_len, cache.b16(), inc->cap, inc->kg.d_qoff);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  return cache;
 }
 
 void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstBuffers& b, int chunk, const Mat* out2, EstInc* inc = nullptr) {
@@ -624,17 +651,7 @@ void tblock(cvk_ctx* ctx, cudaStream_t st, const TBlockW& t, const Seqs& s, EstB
     conv_gemm(ctx, st, b.xn, t.qkv, e);
   }
   if (inc) {
-    const size_t es = b.qkv.esize();
-    const int crow = 2 * inc->cap + 64;
-    Mat cache((char*)inc->kv + (size_t)inc->tb_idx * crow * 1024 * es, b.qkv.dtype, crow, 1024, 1024);
-    ++inc->tb_idx;
-    int bx = s.max_len < 256 ? s.max_len : 256;
-    if (b.qkv.dtype == DT_F32)
-      kv_append_kernel<float><<<dim3(bx, s.B), 128, 0, st>>>(b.qkv.f32(), b.qkv.ld, s.d_start, s.d_len, cache.f32(), inc->cap, inc->t_prev);
-    else
-      kv_append_kernel<bf16><<<dim3(bx, s.B), 128, 0, st>>>(b.qkv.b16(), b.qkv.ld, s.d_start, s.d_len, cache.b16(), inc->cap, inc->t_prev);
-    ctx->launches++;
-    CVK_LAUNCH_CHECK();
+    Mat cache = kv_cache_append(ctx, st, inc, b.qkv, 512, s);
     attention_fwd(ctx, st, b.qkv.slice(0, 512), cache.slice(0, 512), cache.slice(512, 512), s, H_EST, chunk, 0.125f, b.att, 1, &inc->kg);
   } else
   attention_fwd(ctx, st, b.qkv.slice(0, 512), b.qkv.slice(512, 512), b.qkv.slice(1024, 512), s, H_EST, chunk, 0.125f, b.att);
@@ -781,7 +798,8 @@ void estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& 
 }
 
 // mu, cond, x: fp32 [R1,80] (ld 80) in geometry s1; spks [B,80].  Runs n Euler steps in place on x.
-void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out);
+void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out,
+                           EstInc* inc);
 
 // `dit`: 0 = CosyVoice2 causal U-Net estimator, 1 = CosyVoice3 DiT (32 gap rows: its causal position convolution looks 30 rows back)
 void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* lens, const Mat& mu, const Mat& cond, const float* spks,
@@ -821,17 +839,19 @@ void cfm_solve_packed(cvk_ctx* ctx, cudaStream_t st, const Seqs& s1, const int* 
       cfg_pack_kernel<bf16><<<dim3(bx, 2 * B), 96, 0, st>>>(x.f32(), mu.f32(), cond.f32(), spks, s1.d_start, s2.d_start, s1.d_len, B, in0.b16(), in0.ld);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
-    if (dit) dit_estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
-    else if (fs) {
+    if (fs) {
       EstInc inc;
       inc.kv = (char*)fs->kv + (size_t)step * fs->kv_step_bytes;
       inc.conv = (char*)fs->conv + (size_t)step * fs->conv_step_bytes;
       inc.cap = fs->cap;
       inc.t_prev = fs->frames_done;
       inc.kg = fs->kg;
-      estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v, &inc);
+      inc.kv_width = fs->kv_width; inc.tail_rows = fs->tail_rows; inc.conv_c = fs->conv_c;
+      if (dit) dit_estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v, &inc);
+      else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v, &inc);
       CVK_REQUIRE(inc.tb_idx == fs->n_tb && inc.conv_idx == fs->n_conv, "flow stream: cache slots do not match the estimator");
-    } else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
+    } else if (dit) dit_estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v, nullptr);
+    else estimator_forward(ctx, st, s2, in0, t_dev + (size_t)step * 2 * B, streaming, v);
     cfg_euler_kernel<<<dim3(bx, B), 96, 0, st>>>(x.f32(), v.f32(), v.ld, s1.d_start, s2.d_start, s1.d_len, B, dts[step], cfg_rate);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
@@ -958,14 +978,14 @@ __global__ void dit_gate_add_kernel(float* __restrict__ x, int ldx, const float*
 // x_transformers partial rotary on the first 64 channels of q (columns 0..63 of the fused qkv row) and k (columns 1024..1087):
 // freqs duplicated in adjacent channels, pairs (2i, 2i+1) -> (a cos - b sin, b cos + a sin), angle = position * 10000^(-2i/64)
 template <typename T>
-__global__ void dit_rope_kernel(T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len) {
-  const int b = blockIdx.y, L = len[b];
+__global__ void dit_rope_kernel(T* __restrict__ qkv, int ld, const int* __restrict__ start, const int* __restrict__ len, const int* __restrict__ qoff) {
+  const int b = blockIdx.y, L = len[b], p0 = qoff ? qoff[b] : 0;
   for (int t = blockIdx.x; t < L; t += gridDim.x) {
     T* row = qkv + (size_t)(start[b] + t) * ld;
     for (int e = threadIdx.x; e < 64; e += blockDim.x) {       // 32 pairs of q, 32 pairs of k
       const int which = e >> 5, i = e & 31;
       T* p = row + which * DIT_D + 2 * i;
-      const float ang = (float)t * exp2f(-(float)(2 * i) / 64.f * 13.287712379549449f);    // log2(10000)
+      const float ang = (float)(p0 + t) * exp2f(-(float)(2 * i) / 64.f * 13.287712379549449f);    // log2(10000)
       const float c = cosf(ang), sn = sinf(ang);
       const float a = to_f32(p[0]), bb = to_f32(p[1]);
       p[0] = from_f32<T>(a * c - bb * sn);
@@ -1005,7 +1025,8 @@ void gate_add(cvk_ctx* ctx, cudaStream_t st, const Mat& x, const Mat& o, const S
 }
 
 // in0: act [R,320] packed [x | mu | spks | cond]; t_dev [B]; out fp32 [R,80]
-void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out) {
+void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const Mat& in0, const float* t_dev, int streaming, const Mat& out,
+                           EstInc* inc) {
   DitModel* m = ctx->dit;
   CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
   const int adt = ctx->act_dtype;
@@ -1052,6 +1073,7 @@ void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const M
     convert_mat(ctx, st, x, xa);
   }
   Mat c1 = att;                   // act [R,1024], free at this point
+  conv_state(ctx, st, inc, xa, s);        // streaming session: the 30 rows the k31 position convolution reads in front of the chunk
   for (int g = 0; g < DIT_GROUPS; ++g) {
     Epilogue e;
     e.act1 = ACT_MISH;
@@ -1059,6 +1081,7 @@ void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const M
     e.out = c1.slice(g * 64, 64);
     conv_gemm(ctx, st, xa.slice(g * 64, 64), m->pos1[g], e);
   }
+  conv_state(ctx, st, inc, c1, s);
   for (int g = 0; g < DIT_GROUPS; ++g) {
     Epilogue e;
     e.act1 = ACT_MISH;
@@ -1078,10 +1101,15 @@ void dit_estimator_forward(cvk_ctx* ctx, cudaStream_t st, const Seqs& s, const M
       e.out = qkv;
       conv_gemm(ctx, st, xn, w.qkv, e);
     }
-    if (adt == DT_F32) dit_rope_kernel<float><<<dim3(bx, s.B), 64, 0, st>>>(qkv.f32(), qkv.ld, s.d_start, s.d_len);
-    else dit_rope_kernel<bf16><<<dim3(bx, s.B), 64, 0, st>>>(qkv.b16(), qkv.ld, s.d_start, s.d_len);
+    const int* qoff = inc ? inc->kg.d_qoff : nullptr;      // absolute position of the chunk's first row (streaming session)
+    if (adt == DT_F32) dit_rope_kernel<float><<<dim3(bx, s.B), 64, 0, st>>>(qkv.f32(), qkv.ld, s.d_start, s.d_len, qoff);
+    else dit_rope_kernel<bf16><<<dim3(bx, s.B), 64, 0, st>>>(qkv.b16(), qkv.ld, s.d_start, s.d_len, qoff);
     ctx->launches++;
     CVK_LAUNCH_CHECK();
+    if (inc) {
+      Mat cache = kv_cache_append(ctx, st, inc, qkv, DIT_D, s);
+      attention_fwd(ctx, st, qkv.slice(0, DIT_D), cache.slice(0, DIT_D), cache.slice(DIT_D, DIT_D), s, DIT_H, chunk, 0.125f, att, 1, &inc->kg);
+    } else
     attention_fwd(ctx, st, qkv.slice(0, DIT_D), qkv.slice(DIT_D, DIT_D), qkv.slice(2 * DIT_D, DIT_D), s, DIT_H, chunk, 0.125f, att);
     {
       Epilogue e;
@@ -1226,20 +1254,34 @@ void flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, 
 }
 
 // ================================================================================================ incremental streaming flow
-cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps) {
-  FlowModel* m = ctx->flow;
-  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+static Mat dit_mu_forward(cvk_ctx* ctx, cudaStream_t st, const int32_t* tokens, const int* token_lens, int B, int ctxl, Seqs* s2_out);
+
+// kind 0: CosyVoice2 U-Net estimator (stage "flow"); kind 1: CosyVoice3 DiT (stage "flow3")
+cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, int kind) {
+  CVK_REQUIRE(kind == 0 || kind == 1, "flow stream: unknown estimator kind");
   CVK_REQUIRE(max_frames >= 2 * CHUNK_TOK && n_timesteps >= 1, "flow stream: bad capacity / step count");
   cvk_flow_stream* fs = new cvk_flow_stream();
+  fs->kind = kind;
   fs->cap = round_up(max_frames, 64);
   fs->n_steps = n_timesteps;
   fs->adt = ctx->act_dtype;
   const size_t es = fs->adt == DT_F32 ? 4 : 2;
-  const int nst = (int)m->stages.size();
-  fs->n_tb = nst * m->n_blocks;
-  fs->n_conv = 2 * nst + 3;
-  fs->kv_step_bytes = (size_t)fs->n_tb * (2 * fs->cap + 64) * 1024 * es;
-  fs->conv_step_bytes = (size_t)fs->n_conv * 2 * 2 * 512 * es;
+  if (kind == 0) {
+    FlowModel* m = ctx->flow;
+    CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+    const int nst = (int)m->stages.size();
+    fs->n_tb = nst * m->n_blocks;
+    fs->n_conv = 2 * nst + 3;
+    fs->kv_width = 1024; fs->tail_rows = 2; fs->conv_c = 512;
+  } else {
+    DitModel* m = ctx->dit;
+    CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
+    fs->n_tb = m->depth;
+    fs->n_conv = 2;                   // the two grouped k31 position convolutions of the input embedding
+    fs->kv_width = 2 * DIT_D; fs->tail_rows = DIT_CK - 1; fs->conv_c = DIT_D;
+  }
+  fs->kv_step_bytes = (size_t)fs->n_tb * (2 * fs->cap + 64) * fs->kv_width * es;
+  fs->conv_step_bytes = (size_t)fs->n_conv * 2 * fs->tail_rows * fs->conv_c * es;
   CVK_CHECK_CUDA(cudaMalloc(&fs->kv, fs->kv_step_bytes * n_timesteps));
   CVK_CHECK_CUDA(cudaMalloc(&fs->conv, fs->conv_step_bytes * n_timesteps));
   CVK_CHECK_CUDA(cudaMalloc(&fs->prompt_feat, sizeof(float) * (size_t)fs->cap * N_MEL));
@@ -1262,8 +1304,8 @@ size_t flow_stream_bytes(const cvk_flow_stream* fs) { return (fs->kv_step_bytes 
 
 // new utterance: prompt mel [prompt_frames][80] and speaker embedding [192] (device pointers); clears the caches
 void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding, cudaStream_t st) {
-  FlowModel* m = ctx->flow;
-  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+  CVK_REQUIRE(fs->kind == 0 ? (ctx->flow && ctx->flow->tok_emb) : (ctx->dit && ctx->dit->tok_emb), "flow stage of this session not finalised");
+  const ConvW& spk_affine = fs->kind == 0 ? ctx->flow->spk_affine : ctx->dit->spk_affine;
   CVK_REQUIRE(fs->adt == ctx->act_dtype, "flow stream was created under another precision");
   CVK_REQUIRE(prompt_frames >= 0 && prompt_frames < fs->cap, "flow stream: prompt longer than the cache");
   ctx->arena.reset();
@@ -1277,7 +1319,7 @@ void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_fe
   {
     Epilogue e;
     e.out = Mat(fs->spk, DT_F32, 1, N_MEL, N_MEL);
-    conv_gemm_simt(ctx, st, en, m->spk_affine, e);
+    conv_gemm_simt(ctx, st, en, spk_affine, e);
   }
   fs->prompt_frames = prompt_frames;
   fs->frames_done = 0;
@@ -1290,8 +1332,9 @@ void flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_fe
 // mel_out [*, 80]; returns their count.  Both chunk ends must be multiples of the 50-frame static chunk (the reference's hop
 // schedule guarantees it: cli/model.py:346-352 pads the first hop to the 25-token grid).
 int flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, int n_tokens, float* mel_out, int mel_cap_frames, cudaStream_t st) {
-  FlowModel* m = ctx->flow;
-  CVK_REQUIRE(m && m->tok_emb, "flow stage not finalised");
+  CVK_REQUIRE(fs->kind == 0 ? (ctx->flow && ctx->flow->tok_emb) : (ctx->dit && ctx->dit->tok_emb), "flow stage of this session not finalised");
+  CVK_REQUIRE(ctx->flow && ctx->flow->noise, "cvk_cfm_set_noise has not been called");
+  FlowModel* m = ctx->flow;          // holds the CFM noise for both estimator kinds
   CVK_REQUIRE(fs->begun, "cvk_flow_stream_begin has not been called");
   const int CH = 2 * CHUNK_TOK;
   const int T_total = 2 * (n_tokens - 3);
@@ -1304,23 +1347,26 @@ int flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, 
   const int skip = fs->prompt_frames > T_prev ? fs->prompt_frames - T_prev : 0;   // prompt rows are computed but not returned
   CVK_REQUIRE(n_new - skip <= mel_cap_frames, "flow stream: output buffer too small");
   ctx->arena.reset();
-  // encoder over the whole prefix (1.5 % of the flow FLOPs; its chunk mask + look-ahead make the prefix rows final as well)
   Seqs s2;
   int lens_tok[1] = {n_tokens};
-  Mat h = encoder_forward(ctx, st, tokens, lens_tok, 1, 1, 3, &s2);
-  CVK_REQUIRE(s2.len[0] == T_total, "flow stream: encoder length mismatch");
-  Mat ha = h;
-  if (ctx->act_dtype != DT_F32) {
-    ha = arena_mat(ctx, ctx->act_dtype, s2.R, D_ENC);
-    convert_mat(ctx, st, h, ha);
-  }
-  Mat mu_full = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
-  {
+  Mat mu_full;
+  if (fs->kind == 0) {
+    // encoder over the whole prefix (1.5 % of the flow FLOPs; its chunk mask + look-ahead make the prefix rows final as well)
+    Mat h = encoder_forward(ctx, st, tokens, lens_tok, 1, 1, 3, &s2);
+    Mat ha = h;
+    if (ctx->act_dtype != DT_F32) {
+      ha = arena_mat(ctx, ctx->act_dtype, s2.R, D_ENC);
+      convert_mat(ctx, st, h, ha);
+    }
+    mu_full = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
     Epilogue e;
     e.row2seq = s2.d_row2seq;
     e.out = mu_full;
     conv_gemm(ctx, st, ha, m->enc_proj, e);
+  } else {
+    mu_full = dit_mu_forward(ctx, st, tokens, lens_tok, 1, 3, &s2);      // token embedding + look-ahead layer + x2 repeat: row-local
   }
+  CVK_REQUIRE(s2.len[0] == T_total, "flow stream: conditioning length mismatch");
   // geometry of the new rows
   int lens_new[1] = {n_new};
   Seqs s1 = make_seqs(ctx, lens_new, 1, 8, 1, 0, st);
@@ -1336,7 +1382,7 @@ int flow_stream_chunk(cvk_ctx* ctx, cvk_flow_stream* fs, const int32_t* tokens, 
   int geo[6] = {0, fs->cap, T_total, T_total, T_prev, T_prev};
   int* d_tmp = upload(ctx, std::vector<int>(geo, geo + 6), st);
   CVK_CHECK_CUDA(cudaMemcpyAsync(fs->d_geo, d_tmp, sizeof(int) * 6, cudaMemcpyDeviceToDevice, st));
-  cfm_solve_packed(ctx, st, s1, lens_new, mu, cond, fs->spk, x, fs->n_steps, 0.7f, 1, 0, fs);
+  cfm_solve_packed(ctx, st, s1, lens_new, mu, cond, fs->spk, x, fs->n_steps, 0.7f, 1, fs->kind, fs);
   CVK_CHECK_CUDA(cudaMemcpyAsync(mel_out, x.f32() + (size_t)(s1.start[0] + skip) * N_MEL, rowb * (n_new - skip), cudaMemcpyDeviceToDevice, st));
   fs->frames_done = T_total;
   return n_new - skip;
@@ -1414,29 +1460,16 @@ void dit_estimator(cvk_ctx* ctx, const float* x, const float* mu, const float* t
   ctx->launches++;
   CVK_LAUNCH_CHECK();
   Mat v = arena_mat(ctx, DT_F32, s.R, N_MEL, N_MEL);
-  dit_estimator_forward(ctx, st, s, in0, t, streaming, v);
+  dit_estimator_forward(ctx, st, s, in0, t, streaming, v, nullptr);
   unpack_rows(ctx, st, v, s, 0, out, N_MEL);
 }
 
 // flow.py:369-414 CausalMaskedDiffWithDiT.inference, batched over ragged utterances
-void flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
-                     const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, cudaStream_t st) {
+// CosyVoice3 conditioning: token embedding (80 wide) -> PreLookaheadLayer(80, 1024, 3) -> + input -> repeat_interleave(2): mu in the
+// mel geometry *s2_out (flow/flow.py:385-393, upsample_encoder.py:82-103); ctxl look-ahead tokens are consumed and dropped
+static Mat dit_mu_forward(cvk_ctx* ctx, cudaStream_t st, const int32_t* tokens, const int* token_lens, int B, int ctxl, Seqs* s2_out) {
   DitModel* m = ctx->dit;
-  CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
-  CVK_REQUIRE(ctx->flow && ctx->flow->noise, "cvk_cfm_set_noise has not been called");
-  ctx->arena.reset();
   const int adt = ctx->act_dtype;
-  const int ctxl = finalize ? 0 : 3;
-  Mat en = arena_mat(ctx, DT_F32, B, 192), spk = arena_mat(ctx, DT_F32, B, N_MEL, N_MEL);
-  l2norm_kernel<<<B, 64, 0, st>>>(embedding, en.f32(), 192);
-  ctx->launches++;
-  CVK_LAUNCH_CHECK();
-  {
-    Epilogue e;
-    e.out = spk;
-    conv_gemm_simt(ctx, st, en, m->spk_affine, e);
-  }
-  // token embedding (80 wide) -> PreLookaheadLayer(80, 1024, 3) -> + input (upsample_encoder.py:82-103)
   Seqs sf = make_seqs(ctx, token_lens, B, 8, 1, 0, st);
   Seqs s1 = ctxl > 0 ? shrink_seqs(ctx, sf, ctxl, st) : sf;
   int* toff = upload(ctx, prefix(token_lens, B), st);
@@ -1480,6 +1513,29 @@ void flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens,
     ctx->launches++;
     CVK_LAUNCH_CHECK();
   }
+  *s2_out = s2;
+  return mu;
+}
+
+void flow3_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, const float* prompt_feat, const int* prompt_feat_lens,
+                     const float* embedding, int B, int n_timesteps, int streaming, int finalize, float* mel, cudaStream_t st) {
+  DitModel* m = ctx->dit;
+  CVK_REQUIRE(m && m->tok_emb, "flow3 stage not finalised");
+  CVK_REQUIRE(ctx->flow && ctx->flow->noise, "cvk_cfm_set_noise has not been called");
+  ctx->arena.reset();
+  const int adt = ctx->act_dtype;
+  const int ctxl = finalize ? 0 : 3;
+  Mat en = arena_mat(ctx, DT_F32, B, 192), spk = arena_mat(ctx, DT_F32, B, N_MEL, N_MEL);
+  l2norm_kernel<<<B, 64, 0, st>>>(embedding, en.f32(), 192);
+  ctx->launches++;
+  CVK_LAUNCH_CHECK();
+  {
+    Epilogue e;
+    e.out = spk;
+    conv_gemm_simt(ctx, st, en, m->spk_affine, e);
+  }
+  Seqs s2;
+  Mat mu = dit_mu_forward(ctx, st, tokens, token_lens, B, ctxl, &s2);
   Mat cond = arena_mat(ctx, DT_F32, s2.R, N_MEL, N_MEL);
   zero_mat(ctx, st, cond);
   std::vector<int> mel_lens(B);

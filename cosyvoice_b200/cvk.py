@@ -52,6 +52,7 @@ SIGNATURES = {
     "cvk_cfm_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int_p, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, _vp, _vp]),
     "cvk_flow_inference": (ctypes.c_int, [_vp, _vp, _c_int_p, _vp, _c_int_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "cvk_flow_stream_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "cvk_flow3_stream_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "cvk_flow_stream_destroy": (None, [_vp, _vp]),
     "cvk_flow_stream_bytes": (ctypes.c_longlong, [_vp]),
     "cvk_flow_stream_begin": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
@@ -350,9 +351,11 @@ class Context:
         return mel, out_lens
 
     # ------------------------------------------------------------------ incremental streaming flow (cvk.h: cvk_flow_stream_*)
-    def flow_stream(self, max_frames, n_timesteps=10):
+    def flow_stream(self, max_frames, n_timesteps=10, dit=False):
+        """dit=False: CosyVoice2 U-Net estimator (stage "flow"); dit=True: CosyVoice3 DiT (stage "flow3")"""
         s = ctypes.c_void_p()
-        self._check(self.lib.cvk_flow_stream_create(self.h, int(max_frames), int(n_timesteps), ctypes.byref(s)))
+        fn = self.lib.cvk_flow3_stream_create if dit else self.lib.cvk_flow_stream_create
+        self._check(fn(self.h, int(max_frames), int(n_timesteps), ctypes.byref(s)))
         return s
 
     def flow_stream_destroy(self, fs):

@@ -62,8 +62,9 @@ class B200CosyVoice2Model:
     bistream_max_tokens = None
     # streaming synthesis: intermediate chunks through the cached flow session (cvk_flow_stream_*: each chunk computes only its new
     # frames) instead of the reference's prefix recompute (cli/model.py:346-363); same frames either way.  The U-Net estimator of
-    # CosyVoice2 only (B200CosyVoice3Model switches it off: the DiT has no session yet).
+    # B200CosyVoice3Model uses the same sessions for its DiT.
     incremental_flow = True
+    flow_stream_dit = False              # which estimator the sessions cache: the CosyVoice2 U-Net (stage "flow") or the CosyVoice3 DiT ("flow3")
     stream_cache_frames = 2048           # mel frames (prompt included) one streaming request can cache (41 s); ~2.3 MB per frame in bf16
 
     def __init__(self, llm=None, flow=None, hift=None, fp16=False, precision="bf16", device=0, workspace_gb=24.0):
@@ -476,7 +477,7 @@ class B200CosyVoice2Model:
                 with self._pool_lock:
                     fs = self._idle_flow_streams.pop() if self._idle_flow_streams else None
                 if fs is None:
-                    fs = self.ctx.flow_stream(self.stream_cache_frames, self.n_timesteps)
+                    fs = self.ctx.flow_stream(self.stream_cache_frames, self.n_timesteps, dit=self.flow_stream_dit)
                 self.flow_stream_dict[uuid] = fs
                 self.ctx.flow_stream_begin(fs, prompt_feat[0].to(d, non_blocking=True), embedding.reshape(-1).to(d, non_blocking=True))
             toks = torch.cat([prompt_token.reshape(-1).to(d, non_blocking=True), token.reshape(-1).to(d, non_blocking=True)]).to(torch.int32)

@@ -18,7 +18,7 @@ class B200CosyVoice3Model(B200CosyVoice2Model):
     bistream_fill_token = 6564
     bistream_eos_token = 6562
     bistream_eop_token = 151646
-    incremental_flow = False          # cvk_flow_stream_* caches the CosyVoice2 U-Net estimator only
+    flow_stream_dit = True            # streaming chunks through cvk_flow3_stream_create sessions (DiT K/V + position-convolution tails)
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
@@ -57,9 +57,12 @@ class B200CosyVoice3Model(B200CosyVoice2Model):
 
     def token2wav(self, token, prompt_token, prompt_feat, embedding, token_offset, uuid, stream=False, finalize=False, speed=1.0):
         """cli/model.py:425-450"""
-        mel, _ = self.flow_batch([token.to(torch.int32)], [prompt_token], [prompt_feat], [embedding], streaming=stream, finalize=finalize)
+        new_mel = self._flow_stream_chunk(token.to(torch.int32), prompt_token, prompt_feat, embedding, token_offset, uuid) \
+            if (stream and not finalize) else None
+        if new_mel is None:
+            mel, _ = self.flow_batch([token.to(torch.int32)], [prompt_token], [prompt_feat], [embedding], streaming=stream, finalize=finalize)
         with torch.cuda.stream(self.stream):
-            tts_mel = mel[token_offset * TOKEN_MEL_RATIO:]
+            tts_mel = new_mel if new_mel is not None else mel[token_offset * TOKEN_MEL_RATIO:]
             cache = self.hift_cache_dict[uuid]
             if cache is not None:
                 tts_mel = torch.cat([cache["mel"], tts_mel], 0)

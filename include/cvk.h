@@ -151,6 +151,10 @@ int cvk_flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_len
  * Calls on one session are serialised by the caller, like every workspace call of the context. */
 typedef struct cvk_flow_stream cvk_flow_stream;
 int cvk_flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out);
+/* the same session for the CosyVoice3 DiT (stage "flow3", flow/flow.py:369-414 with streaming=True): K/V rows of the 22 blocks
+ * (rotary positions absolute) and the 30-row input tails of the two grouped k31 position convolutions (DiT/modules.py:115-145);
+ * begin / chunk / destroy / bytes are shared */
+int cvk_flow3_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, cvk_flow_stream** out);
 void cvk_flow_stream_destroy(cvk_ctx* ctx, cvk_flow_stream* fs);
 long long cvk_flow_stream_bytes(const cvk_flow_stream* fs);
 int cvk_flow_stream_begin(cvk_ctx* ctx, cvk_flow_stream* fs, const float* prompt_feat, int prompt_frames, const float* embedding,

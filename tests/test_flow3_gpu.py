@@ -79,3 +79,34 @@ def test_dit_ragged_batch_equals_single(golden):
         single = c.dit_estimator(xs[b], mus[b], t[b:b + 1], spks[b:b + 1], conds[b], [T], streaming=True)
         assert maxdiff(out[o:o + T], single) < 1e-5
         o += T
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("depth", [2, 22])
+def test_dit_incremental_stream_equals_prefix_recompute(precision, depth):
+    """cvk_flow3_stream_create + the shared session calls for the DiT estimator: K/V rows of every block (rotary positions absolute) and the
+    30-row input tails of the two grouped k31 position convolutions per Euler step, against flow3_inference(streaming=True,
+    finalize=False) re-run on the growing prefix (what CosyVoice3Model.tts does per chunk, cli/model.py:346-363, 425-450).  Same
+    chunk schedule as the CosyVoice2 test: prompt 30 tokens, hops 45 / 25 / 50."""
+    c = model(precision, depth)
+    g = torch.Generator().manual_seed(78)
+    P, hops = 30, (45, 25, 50)
+    toks = torch.randint(0, 6561, (P + sum(hops) + 3,), generator=g, dtype=torch.int32)
+    pfeat = torch.rand(2 * P, 80, generator=g) * 13.5 - 11.5
+    emb = torch.randn(1, 192, generator=g)
+    fs = c.flow_stream(max_frames=512, n_timesteps=10, dit=True)
+    try:
+        c.flow_stream_begin(fs, pfeat, emb)
+        n, done = P, 0
+        for hop in hops:
+            n += hop
+            ref, lens = c.flow3_inference(toks[:n + 3], [n + 3], pfeat, [2 * P], emb, streaming=True, finalize=False)
+            new = c.flow_stream_chunk(fs, toks[:n + 3])
+            want = ref[max(done - 2 * P, 0):]
+            assert new.shape == want.shape, (new.shape, want.shape)
+            assert torch.isfinite(new).all()
+            d = maxdiff(new, want)
+            assert d < (1e-5 if precision == "fp32" else 1e-3), (hop, d)
+            done = 2 * n
+    finally:
+        c.flow_stream_destroy(fs)

@@ -163,7 +163,32 @@ class FakeCtx3:
         self.rand_ini, self.sine_noise = rand_ini, sine_noise
         self.dit, self.hc = dit, hift_causal
         self.lock = threading.Lock()
-        self.flow_calls, self.hift_calls = [], []
+        self.flow_calls, self.hift_calls, self.stream_calls = [], [], []
+
+    # ---- cvk_flow_stream_* / cvk_flow3_stream_create: a session returns, per chunk, the frames of the streaming flow call on the prefix
+    # that it has not returned yet (tests/test_flow_gpu.py / test_flow3_gpu.py hold the library to exactly that)
+    def flow_stream(self, max_frames, n_timesteps=10, dit=False):
+        return {"done": 0, "cap": max_frames, "dit": dit}
+
+    def flow_stream_begin(self, fs, prompt_feat, embedding):
+        fs.update(done=0, pf=prompt_feat, emb=embedding.reshape(1, -1))
+
+    def _prefix_mel(self, fs, toks):
+        assert fs["dit"]
+        P = self._P
+        return self.dit.inference(self.fsd, toks[None, P:], toks[None, :P], fs["pf"][None], fs["emb"], self.depth, 10, True, False)[0].t()
+
+    def flow_stream_chunk(self, fs, toks):
+        self.stream_calls.append(int(toks.numel()))
+        mel = self._prefix_mel(fs, toks)
+        Tp = fs["pf"].shape[0]
+        out = mel[max(fs["done"] - Tp, 0):]
+        fs["done"] = Tp + mel.shape[0]
+        assert fs["done"] % 50 == 0 and fs["done"] <= fs["cap"]
+        return out.contiguous()
+
+    def flow_stream_destroy(self, fs):
+        pass
 
     # ---- LM: prefill stores the prompt, decode releases the oracle's ids n_steps at a time
     def lm_session(self, B, ctx_len):
@@ -242,17 +267,25 @@ def test_cosyvoice3_model_host_glue_matches_reference(golden, monkeypatch):
         m.silent_tokens = [1, 2, 28, 29, 55, 248, 494, 2241, 2242, 2322, 2323]
         m.token_hop_len, m.token_max_hop_len, m.stream_scale_factor = 25, 100, 2
         m.min_token_text_ratio, m.max_token_text_ratio, m.n_timesteps = 2.0, 20.0, 10
-        ctx.flow_calls.clear()
-        ctx.hift_calls.clear()
-        chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
-                                                 llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
-                                                 stream=stream)]
-        assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
-        d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
-        assert d[:, :24000].max() < 2e-3 and d.max() < 1e-2
+        for incremental in ((True, False) if stream else (True,)):
+            m.incremental_flow = incremental
+            m.token_hop_len = 25
+            ctx.flow_calls.clear()
+            ctx.hift_calls.clear()
+            ctx.stream_calls.clear()
+            chunks = [o["tts_speech"] for o in m.tts(text=text, flow_embedding=emb, llm_embedding=emb, prompt_text=ptext,
+                                                     llm_prompt_speech_token=ptok, flow_prompt_speech_token=ptok, prompt_speech_feat=pfeat,
+                                                     stream=stream)]
+            assert [c.shape[1] for c in chunks] == g[mode + "_lens"].tolist()
+            d = np.abs(torch.cat(chunks, 1).numpy() - g[mode + "_wav"])
+            assert d[:, :24000].max() < 2e-3 and d.max() < 1e-2
+            assert not m.flow_stream_dict
+            if stream and incremental:
+                # DiT sessions for the two streaming chunks, flow3_inference for the final non-streaming call
+                assert ctx.stream_calls == [9 + 41 + 3, 9 + 41 + 50 + 3] and ctx.flow_calls == [(9 + 140, False, True)]
         if stream:
-            # two streaming calls on growing prefixes (hop 25 padded to 41, then 50; 3 look-ahead tokens each) + the final
-            # non-streaming call on all 140 tokens (cli/model.py:346-373)
+            # last pass = the reference's schedule: two streaming calls on growing prefixes (hop 25 padded to 41, then 50; 3 look-ahead
+            # tokens each) + the final non-streaming call on all 140 tokens (cli/model.py:346-373)
             assert ctx.flow_calls == [(9 + 41 + 3, True, False), (9 + 41 + 50 + 3, True, False), (9 + 140, False, True)]
             assert [f for _, f in ctx.hift_calls] == [False, False, True]
             assert m.token_hop_len == 100
@@ -267,27 +300,11 @@ class FakeCtx2(FakeCtx3):
         self.lock = threading.Lock()
         self.flow_calls, self.hift_calls, self.stream_calls = [], [], []
 
-    # cvk_flow_stream_*: a session returns, per chunk, the frames of flow.inference(streaming=True, finalize=False) on the prefix
-    # that it has not returned yet (tests/test_flow_gpu.py::test_incremental_stream_equals_prefix_recompute holds the library to it)
-    def flow_stream(self, max_frames, n_timesteps=10):
-        return {"done": 0, "cap": max_frames}
-
-    def flow_stream_begin(self, fs, prompt_feat, embedding):
-        fs.update(done=0, pf=prompt_feat, emb=embedding.reshape(1, -1))
-
-    def flow_stream_chunk(self, fs, toks):
+    def _prefix_mel(self, fs, toks):
         from oracle import flow
+        assert not fs["dit"]
         P = self._P
-        self.stream_calls.append(int(toks.numel()))
-        mel = flow.inference(self.fsd, toks[None, P:], toks[None, :P], fs["pf"][None], fs["emb"], self.fcfg, 10, True, False)[0].t()
-        Tp = fs["pf"].shape[0]
-        out = mel[max(fs["done"] - Tp, 0):]
-        fs["done"] = Tp + mel.shape[0]
-        assert fs["done"] % 50 == 0 and fs["done"] <= fs["cap"]
-        return out.contiguous()
-
-    def flow_stream_destroy(self, fs):
-        pass
+        return flow.inference(self.fsd, toks[None, P:], toks[None, :P], fs["pf"][None], fs["emb"], self.fcfg, 10, True, False)[0].t()
 
     def _run(self, sess, U, min_len, max_len):
         sd = self.lsd
