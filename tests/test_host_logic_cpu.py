@@ -7,6 +7,7 @@ host logic of `B200CosyVoice2Model.lm_generate_bistream` is checked against the 
 import threading
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import cases, lm, sampling
@@ -411,3 +412,21 @@ def test_padded_cosyvoice3_head_is_sampling_neutral():
         hist = [int(np.argmax(logits))] * 3
         for u1, u2, ign in ((0.05, 0.9, True), (0.5, 0.5, False), (0.79, 0.01, True), (0.999, 0.999, False)):
             assert sampling.ras_sample(lp, hist, u1, u2, ign) == sampling.ras_sample(lpp, hist, u1, u2, ign)
+
+
+def test_frontend_wrappers_refuse_configurations_the_library_does_not_implement():
+    """cosyvoice_b200/frontend.py: argument checks happen before any device work (no silent fallback to another configuration)"""
+    from cosyvoice_b200 import frontend
+    w = torch.zeros(1, 16000)
+    with pytest.raises(ValueError):
+        frontend.kaldi_fbank(w, num_mel_bins=40)
+    with pytest.raises(ValueError):
+        frontend.kaldi_fbank(w, dither=1.0)
+    with pytest.raises(ValueError):
+        frontend.kaldi_fbank(torch.zeros(2, 16000))
+    with pytest.raises(ValueError):
+        frontend.log_mel_spectrogram(w, n_mels=80)
+    with pytest.raises(ValueError):
+        frontend.mel_spectrogram(torch.zeros(1, 24000), n_fft=1024)
+    with pytest.raises(ValueError):
+        frontend.mel_spectrogram(torch.zeros(1, 24000), fmax=7600)
