@@ -18,7 +18,9 @@
  *    cvk_lm_feed, cvk_lm_next_logp, cvk_lm_last_logits) and cvk_ras_sample own no shared state: they may run
  *    concurrently with workspace calls and with each other on DISTINCT sessions and streams - this is the reference's
  *    own concurrency (LM side thread + side stream next to token2wav, cli/model.py:101-129, 268; several requests in
- *    flight, runtime/python/grpc/server.py:69).  One session is never used by two host threads at once.
+ *    flight, runtime/python/grpc/server.py:69).  One session is never used by two host threads at once.  Streaming-flow
+ *    sessions (cvk_flow_stream_*) hold caches only: their begin / chunk calls use the workspace and are serialised like every
+ *    other flow call.
  *  - Return value: 0 on success, a negative cvk_status otherwise; cvk_last_error(ctx) holds the message.  No C++
  *    exception crosses the ABI.  There is NO CPU fallback: without a CUDA device cvk_create fails.
  */
@@ -57,10 +59,13 @@ int64_t cvk_launch_count(cvk_ctx* ctx);
 double cvk_last_op_ms(cvk_ctx* ctx);
 /* debug: copy (and clear) the device timeline buffer filled by instrumented kernels when "debug_timeline" is on */
 int cvk_debug_read(cvk_ctx* ctx, long long* out, int n);
-/* debug switch: 1 (default) = bf16 GEMMs on the tcgen05 kernel, 0 = same operands through the SIMT kernel */
 /* workspace arena of the context (SURVEY.md §8b `cvk_workspace_bytes`): capacity given to cvk_create and the high-water mark of
  * the calls made so far - what a caller needs to size cvk_create for its largest batch. */
 int cvk_workspace_bytes(cvk_ctx* ctx, size_t* capacity, size_t* high_water);
+/* Test / measurement switches, NOT part of the drop-in surface (every default is the benchmarked configuration): kernel-variant
+ * A/B ("use_tc", "tc_persist", "tc_bn256", "tc_pbn256", "tc_epi", "use_tc_attn", "attn_single_pass", "enc_tc_attn", "use_skinny",
+ * "lm_fused", "lm_mega", "mega_coop", "pdl", "use_graph", "hift_f16" - the last one takes effect at the next cvk_finalize("hift")),
+ * probes ("op_iters", "op_out_bf16", "debug_timeline", "chain_timeline").  Unknown keys return CVK_ERR_INVALID. */
 int cvk_set_option(cvk_ctx* ctx, const char* key, int value);
 
 /* Per-kernel-family device timing for the roofline report of bench.py: CUDA events are recorded around every launch
