@@ -477,7 +477,12 @@ class B200CosyVoice2Model:
                 with self._pool_lock:
                     fs = self._idle_flow_streams.pop() if self._idle_flow_streams else None
                 if fs is None:
-                    fs = self.ctx.flow_stream(self.stream_cache_frames, self.n_timesteps, dit=self.flow_stream_dit)
+                    try:
+                        fs = self.ctx.flow_stream(self.stream_cache_frames, self.n_timesteps, dit=self.flow_stream_dit)
+                    except cvk.CvkError:
+                        # no memory for another session's caches (several GB each): this request recomputes the prefix like the reference
+                        self.flow_stream_dict[uuid] = False
+                        return None
                 self.flow_stream_dict[uuid] = fs
                 self.ctx.flow_stream_begin(fs, prompt_feat[0].to(d, non_blocking=True), embedding.reshape(-1).to(d, non_blocking=True))
             toks = torch.cat([prompt_token.reshape(-1).to(d, non_blocking=True), token.reshape(-1).to(d, non_blocking=True)]).to(torch.int32)
