@@ -1255,6 +1255,7 @@ void flow_inference(cvk_ctx* ctx, const int32_t* tokens, const int* token_lens, 
 
 // ================================================================================================ incremental streaming flow
 static Mat dit_mu_forward(cvk_ctx* ctx, cudaStream_t st, const int32_t* tokens, const int* token_lens, int B, int ctxl, Seqs* s2_out);
+void flow_stream_destroy(cvk_flow_stream* fs);
 
 // kind 0: CosyVoice2 U-Net estimator (stage "flow"); kind 1: CosyVoice3 DiT (stage "flow3")
 cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timesteps, int kind) {
@@ -1282,12 +1283,18 @@ cvk_flow_stream* flow_stream_create(cvk_ctx* ctx, int max_frames, int n_timestep
   }
   fs->kv_step_bytes = (size_t)fs->n_tb * (2 * fs->cap + 64) * fs->kv_width * es;
   fs->conv_step_bytes = (size_t)fs->n_conv * 2 * fs->tail_rows * fs->conv_c * es;
-  CVK_CHECK_CUDA(cudaMalloc(&fs->kv, fs->kv_step_bytes * n_timesteps));
-  CVK_CHECK_CUDA(cudaMalloc(&fs->conv, fs->conv_step_bytes * n_timesteps));
-  CVK_CHECK_CUDA(cudaMalloc(&fs->prompt_feat, sizeof(float) * (size_t)fs->cap * N_MEL));
-  CVK_CHECK_CUDA(cudaMalloc(&fs->spk, sizeof(float) * N_MEL));
-  CVK_CHECK_CUDA(cudaMalloc(&fs->d_geo, sizeof(int) * 6));
-  CVK_CHECK_CUDA(cudaMemset(fs->kv, 0, fs->kv_step_bytes * n_timesteps));   // masked key rows of a partial tile must be finite
+  try {
+    CVK_CHECK_CUDA(cudaMalloc(&fs->kv, fs->kv_step_bytes * n_timesteps));
+    CVK_CHECK_CUDA(cudaMalloc(&fs->conv, fs->conv_step_bytes * n_timesteps));
+    CVK_CHECK_CUDA(cudaMalloc(&fs->prompt_feat, sizeof(float) * (size_t)fs->cap * N_MEL));
+    CVK_CHECK_CUDA(cudaMalloc(&fs->spk, sizeof(float) * N_MEL));
+    CVK_CHECK_CUDA(cudaMalloc(&fs->d_geo, sizeof(int) * 6));
+    CVK_CHECK_CUDA(cudaMemset(fs->kv, 0, fs->kv_step_bytes * n_timesteps));   // masked key rows of a partial tile must be finite
+  } catch (...) {                      // out of memory half way: give back what was taken
+    cudaGetLastError();
+    flow_stream_destroy(fs);
+    throw;
+  }
   fs->kg.d_kstart = fs->d_geo;
   fs->kg.d_klen = fs->d_geo + 2;
   fs->kg.d_qoff = fs->d_geo + 4;
